@@ -1,0 +1,218 @@
+/*
+ * ttl_b200.h -- C ABI of libttl_b200.so, the B200 (sm_100a) implementation of the
+ * TrackToLearn batched tracking step, SAC actor forward and TractOracle-Net scoring.
+ *
+ * The reference (levje/TrackToLearn) is pure Python and has no FFI; its boundary for this
+ * path is the duck-typed class API of TrackingEnvironment / SACActorCritic /
+ * OracleSingleton.  Each entry point below names the reference method(s) it replaces
+ * (paths relative to /root/reference/TrackToLearn).  The Python classes in
+ * tracktolearn_b200/ keep those names and call these functions through ctypes; a
+ * maintainer of the reference would bind them the same way.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless the name ends in _host; nothing is
+ * allocated or freed behind the caller's back except the opaque plan objects
+ * (ttl_actor_plan_*, ttl_oracle_plan_*); every function enqueues work on `stream`
+ * (a cudaStream_t passed as void*) and returns 0 or a cudaError_t / negative ttl error;
+ * no function synchronises the stream.  There is no CPU fallback.
+ */
+#ifndef TTL_B200_H
+#define TTL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTL_ABI_VERSION 1
+
+/* StoppingFlags, environments/stopping_criteria.py:10-20 */
+#define TTL_STOPPING_MASK 1
+#define TTL_STOPPING_LENGTH 2
+#define TTL_STOPPING_CURVATURE 4
+#define TTL_STOPPING_ORACLE 64
+
+#define TTL_ERR_BAD_ARG (-1)
+#define TTL_ERR_UNSUPPORTED (-2)
+#define TTL_ERR_DRIVER (-3)
+
+/* Subject data resident in HBM (environments/env.py:143-260, load_subject). */
+typedef struct ttl_volume {
+  const float* sh;         /* [X][Y][Z][CP] fp32 SH coefficients, channel-padded, z fastest */
+  int32_t X, Y, Z;         /* SH volume dims */
+  int32_t C;               /* real coefficient count (45 for order 8) */
+  int32_t CP;              /* padded channel stride in floats, multiple of 4 */
+  const double* mask_coef; /* [MX][MY][MZ] f64 cubic B-spline coefficients of the tracking mask
+                              (scipy spline_filter output, stopping_criteria.py:58-59) */
+  int32_t MX, MY, MZ;
+  const float* peaks;      /* [PX][PY][PZ][15] fp32 or NULL (local_reward.py:23-27) */
+  int32_t PX, PY, PZ;
+} ttl_volume;
+
+/* Tracking parameters (environments/env.py:108-138,196-213). */
+typedef struct ttl_params {
+  double step_vox;          /* step size in voxels, np.float64 (datasets/utils.py:88-124) */
+  double mask_threshold;    /* binary_stopping_threshold */
+  double alignment_weighting;
+  float theta_rad;          /* float32(deg2rad(theta)), numpy-1.23 comparison precision */
+  int32_t max_nb_steps;     /* int(max_length / step_size_mm) */
+  int32_t n_dirs;           /* previous directions in the state (100) */
+  int32_t dir_f64;          /* 1: NoisyTrackingEnvironment arithmetic (float64 directions,
+                               noisy_tracking_env.py:63-77); 0: float32 (TrackingEnvironment) */
+  int32_t compute_reward;   /* 1: alignment reward (reward.py:46-79, local_reward.py:29-107) */
+  int32_t state_stopped;    /* 1: also build the state rows of streamlines that stop this step
+                               (the reference does, tracking_env.py:214-215); 0: skip them */
+} ttl_params;
+
+/* Per-batch mutable state in HBM (tracking_env.py:91-133 allocates the equivalent). */
+typedef struct ttl_batch {
+  int32_t n;               /* streamlines in this batch */
+  int32_t capacity;        /* rows allocated in every per-row buffer */
+  int32_t max_pts;         /* points per row = max_nb_steps + 1 */
+  int32_t ld_state;        /* floats per state row (>= state size, multiple of 4) */
+  int32_t state_size;      /* 7*C + 3*n_dirs (615) */
+  float* points;           /* [capacity][max_pts][3] fp32 streamline coordinates (voxel space) */
+  int32_t* flags;          /* [capacity] StoppingFlags per global row */
+  int32_t* lengths;        /* [capacity] points per global row */
+  uint8_t* dones;          /* [capacity] */
+  int32_t* alive[2];       /* ping-pong lists of alive global rows, ascending */
+  int32_t* ctrl;           /* [8] device ints: [0],[1] alive count of alive[0],alive[1];
+                              [2] L = points so far in every alive row */
+  uint8_t* stop;           /* [capacity] per rank (position in the alive list): stopped this step */
+  int32_t* dest;           /* [capacity] per rank: row of state[next] that holds its new state */
+  int32_t* step_flags;     /* [capacity] per rank: flags raised this step */
+  float* reward;           /* [capacity] per rank */
+  float* state[2];         /* ping-pong [capacity][ld_state] fp32 state rows.  state[cur] rows
+                              [0, n_alive) are the states of alive[cur] in order. */
+} ttl_batch;
+
+/* ---- one-time / load-time helpers ------------------------------------------------------ */
+
+/* [V][C] -> [V][CP] channel padding (zero fill) of the SH volume (env.py:179-180 uploads the
+ * unpadded volume; the padding makes every voxel a whole number of float4). */
+int ttl_pad_channels(const float* src, float* dst, int64_t n_voxels, int32_t C, int32_t CP,
+                     void* stream);
+
+/* ---- TrackingEnvironment ------------------------------------------------------------------ */
+
+/* TrackingEnvironment.reset / nreset (tracking_env.py:47-133): seeds [n][3] float64 voxel
+ * coordinates -> first points, zeroed flags, lengths 1, alive = 0..n-1, L = 1 and the initial
+ * state rows in state[0].  After this call cur = 0. */
+int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b,
+                  const double* seeds, void* stream);
+
+/* TrackingEnvironment.step (tracking_env.py:135-221; NoisyTrackingEnvironment.step when
+ * prm->dir_f64): actions [n_alive][lda] fp32 for the alive rows of alive[cur], optional
+ * `noise` [n_alive][3] f64 added first.  Normalise+scale (env.py:493-502), first-step flip,
+ * grow, stopping flags (env.py:567-603, utils.py:127-173, stopping_criteria.py:38-82), reward,
+ * ordered compaction into alive[cur^1] / ctrl[cur^1], new state rows into state[cur^1]
+ * (survivors first, in order; then stopped rows if prm->state_stopped), L += 1.
+ * `n_upper` >= current alive count bounds the launch (the kernels read the true count from
+ * ctrl[cur] on the device, so no host sync is needed between steps).
+ * The caller flips cur afterwards: that flip is TrackingEnvironment.harvest (:223-245). */
+int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                 const float* actions, int32_t lda, const double* noise, int32_t n_upper,
+                 void* stream);
+
+/* state[cur^1][dest[r]] -> out[r] for r < n_rows: the `self.state[self.continue_idx]` that
+ * step() returns, in the order of the pre-harvest alive list (tracking_env.py:217-218). */
+int ttl_env_gather_step_state(const ttl_batch* b, int32_t cur, int32_t n_rows, float* out,
+                              int32_t ld_out, void* stream);
+
+/* _format_state alone (env.py:504-565) for arbitrary streamlines: points [n][L][3] fp32 ->
+ * out [n][ld_out].  Used by parity tests and get_state_size. */
+int ttl_format_state(const ttl_volume* vol, const ttl_params* prm, const float* points,
+                     int32_t n, int32_t L, float* out, int32_t ld_out, void* stream);
+
+/* _compute_stopping_flags alone (env.py:567-603) for arbitrary streamlines [n][L][3]:
+ * out_flags [n] int32 (0 = continue). */
+int ttl_stopping_flags(const ttl_volume* vol, const ttl_params* prm, const float* points,
+                       int32_t n, int32_t L, int32_t* out_flags, double* out_mask_value,
+                       float* out_reward, void* stream);
+
+/* get_streamlines (tracking_env.py:247-294): effective lengths (last point dropped when the
+ * CURVATURE or MASK bit is set) and their exclusive prefix sum: offsets [n+1] int64. */
+int ttl_streamline_offsets(const ttl_batch* b, int64_t* offsets, void* stream);
+/* ... then the ragged copy: out_points [offsets[n]][3] fp32. */
+int ttl_pack_streamlines(const ttl_batch* b, const int64_t* offsets, float* out_points,
+                         void* stream);
+
+/* ---- SAC actor (algorithms/shared/offpolicy.py:61-140, shared/utils.py:41-51) -------------- */
+
+#define TTL_ACTOR_MAX_LAYERS 8
+#define TTL_PRECISION_BF16 0   /* tcgen05 bf16 operands, fp32 TMEM accumulators */
+#define TTL_PRECISION_FP32 1   /* CUDA-core fp32 reference-precision path */
+
+typedef struct ttl_actor_weights {
+  int32_t n_layers;                         /* linear layers (4 for 1024-1024-1024) */
+  int32_t in_dim[TTL_ACTOR_MAX_LAYERS];     /* true fan-in  (615,1024,1024,1024) */
+  int32_t out_dim[TTL_ACTOR_MAX_LAYERS];    /* true fan-out (1024,1024,1024,6) */
+  const float* w[TTL_ACTOR_MAX_LAYERS];     /* [out][in] fp32, nn.Linear layout */
+  const float* b[TTL_ACTOR_MAX_LAYERS];     /* [out] fp32 */
+} ttl_actor_weights;
+
+typedef struct ttl_actor_plan ttl_actor_plan; /* opaque: packed bf16 weights, TMA maps, scratch */
+
+/* Host-side: packs weights (bf16, K padded to 64, N padded to the tile) into `workspace`
+ * (device, ttl_actor_workspace_bytes() bytes) and encodes the TMA descriptors for batches of
+ * up to max_rows states.  Enqueues the packing kernels on `stream`. */
+int64_t ttl_actor_workspace_bytes(const ttl_actor_weights* w, int32_t max_rows);
+int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int32_t max_rows,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+void ttl_actor_plan_destroy(ttl_actor_plan* plan);
+
+/* MaxEntropyActor.forward (offpolicy.py:94-140): state [n][ld_state] fp32 ->
+ * action [n][3] = tanh(mu + exp(clamp(log_std,-20,2)) * probabilistic * eps), logp [n]
+ * (may be NULL), pre [n][2*action] raw network output (may be NULL).
+ * n is read from *n_rows_dev when that is non-NULL (no host sync), else n_rows_max.
+ * eps [n][3] fp32 may be NULL when probabilistic == 0. */
+int ttl_actor_forward(ttl_actor_plan* plan, const float* state, int32_t ld_state,
+                      const int32_t* n_rows_dev, int32_t n_rows_max, float probabilistic,
+                      const float* eps, float* action, float* logp, float* pre,
+                      int32_t precision, void* stream);
+
+/* Stand-alone dense layer used by the actor and exposed for tests:
+ * C[m][ldc] (bf16) = act(A[m][k] (bf16) . W[n][k]^T (bf16) + bias[n]), tcgen05/TMEM/TMA. */
+int ttl_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t m,
+                  int32_t n, int32_t k, int32_t ldc, int32_t relu, const int32_t* m_dev,
+                  void* stream);
+
+/* ---- TractOracle-Net (oracles/oracle.py:39-89, transformer_oracle.py:77-92) ----------------- */
+
+typedef struct ttl_oracle_weights {
+  int32_t n_layers, n_head, d_model, d_ff, n_tokens; /* 4,4,32,2048,128 */
+  const float* cls_token;   /* [3] */
+  const float* emb_w;       /* [d][3] */
+  const float* emb_b;       /* [d] */
+  const float* pe;          /* [n_tokens][d] */
+  const float* in_proj_w[8];  /* [3d][d] */
+  const float* in_proj_b[8];  /* [3d] */
+  const float* out_proj_w[8]; /* [d][d] */
+  const float* out_proj_b[8]; /* [d] */
+  const float* lin1_w[8];     /* [ff][d] */
+  const float* lin1_b[8];     /* [ff] */
+  const float* lin2_w[8];     /* [d][ff] */
+  const float* lin2_b[8];     /* [d] */
+  const float* norm1_w[8]; const float* norm1_b[8];
+  const float* norm2_w[8]; const float* norm2_b[8];
+  const float* head_w;      /* [d] */
+  const float* head_b;      /* [1] */
+} ttl_oracle_weights;
+
+/* dipy set_number_of_points(s,128) + np.diff (oracle.py:52-54) on device: ragged points
+ * [offsets[n]][3] fp32 -> dirs [n][127][3] fp32. */
+int ttl_oracle_features(const float* points, const int64_t* offsets, int32_t n, float* dirs,
+                        void* stream);
+/* TransformerOracle.forward: dirs [n][127][3] -> scores [n] fp32. */
+int ttl_oracle_forward(const ttl_oracle_weights* w, const float* dirs, int32_t n, float* scores,
+                       void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+int ttl_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t ttl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTL_B200_H */

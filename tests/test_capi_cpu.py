@@ -1,0 +1,58 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/ttl_b200.h declares;
+the ctypes structures have the C layout."""
+import ctypes
+import os
+import re
+import subprocess
+import tempfile
+
+from tracktolearn_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'ttl_b200.h')
+
+
+def test_library_builds_and_exports_declared_symbols():
+    build.build()
+    lib = _lib.load()
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    declared = set(re.findall(r'\b(ttl_[a-z0-9_]+)\s*\(', text))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.ttl_abi_version() == 1
+    assert lib.ttl_launch_count() >= 0
+
+
+def test_ctypes_struct_layout_matches_header():
+    src = r'''
+#include "ttl_b200.h"
+#include <stdio.h>
+#include <stddef.h>
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ttl_volume), sizeof(ttl_params), sizeof(ttl_batch),
+         sizeof(ttl_actor_weights), sizeof(ttl_oracle_weights), offsetof(ttl_batch, alive),
+         offsetof(ttl_batch, state), offsetof(ttl_params, theta_rad));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, 't.c')
+        open(c, 'w').write(src)
+        exe = os.path.join(d, 't')
+        subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
+        got = [int(x) for x in subprocess.check_output([exe]).split()]
+    want = [ctypes.sizeof(_lib.Volume), ctypes.sizeof(_lib.Params), ctypes.sizeof(_lib.Batch),
+            ctypes.sizeof(_lib.ActorWeights), ctypes.sizeof(_lib.OracleWeights),
+            _lib.Batch.alive.offset, _lib.Batch.state.offset, _lib.Params.theta_rad.offset]
+    assert got == want
+
+
+def test_product_refuses_cpu_device():
+    import numpy as np
+    import pytest
+    import torch
+    from tracktolearn_b200.algorithms.shared.offpolicy import SACActorCritic
+    with pytest.raises(_lib.TTLError):
+        SACActorCritic(615, 3, '64-64-64', torch.device('cpu'))

@@ -1,0 +1,109 @@
+"""ctypes binding of libttl_b200.so (C ABI declared in include/ttl_b200.h).
+
+There is no fallback: if the library is missing or a call fails, we raise.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'lib', 'libttl_b200.so')
+
+c_i32, c_i64, c_f32, c_f64, c_vp = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
+                                    ctypes.c_void_p)
+MAX_LAYERS = 8
+PRECISION_BF16, PRECISION_FP32 = 0, 1
+
+
+class Volume(ctypes.Structure):
+    _fields_ = [('sh', c_vp), ('X', c_i32), ('Y', c_i32), ('Z', c_i32), ('C', c_i32), ('CP', c_i32),
+                ('mask_coef', c_vp), ('MX', c_i32), ('MY', c_i32), ('MZ', c_i32),
+                ('peaks', c_vp), ('PX', c_i32), ('PY', c_i32), ('PZ', c_i32)]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [('step_vox', c_f64), ('mask_threshold', c_f64), ('alignment_weighting', c_f64),
+                ('theta_rad', c_f32), ('max_nb_steps', c_i32), ('n_dirs', c_i32), ('dir_f64', c_i32),
+                ('compute_reward', c_i32), ('state_stopped', c_i32)]
+
+
+class Batch(ctypes.Structure):
+    _fields_ = [('n', c_i32), ('capacity', c_i32), ('max_pts', c_i32), ('ld_state', c_i32),
+                ('state_size', c_i32), ('points', c_vp), ('flags', c_vp), ('lengths', c_vp),
+                ('dones', c_vp), ('alive', c_vp * 2), ('ctrl', c_vp), ('stop', c_vp), ('dest', c_vp),
+                ('step_flags', c_vp), ('reward', c_vp), ('state', c_vp * 2)]
+
+
+class ActorWeights(ctypes.Structure):
+    _fields_ = [('n_layers', c_i32), ('in_dim', c_i32 * MAX_LAYERS), ('out_dim', c_i32 * MAX_LAYERS),
+                ('w', c_vp * MAX_LAYERS), ('b', c_vp * MAX_LAYERS)]
+
+
+class OracleWeights(ctypes.Structure):
+    _fields_ = ([('n_layers', c_i32), ('n_head', c_i32), ('d_model', c_i32), ('d_ff', c_i32),
+                 ('n_tokens', c_i32), ('cls_token', c_vp), ('emb_w', c_vp), ('emb_b', c_vp), ('pe', c_vp)]
+                + [(name, c_vp * 8) for name in ('in_proj_w', 'in_proj_b', 'out_proj_w', 'out_proj_b',
+                                                 'lin1_w', 'lin1_b', 'lin2_w', 'lin2_b')]
+                + [('norm1_w', c_vp * 8), ('norm1_b', c_vp * 8), ('norm2_w', c_vp * 8), ('norm2_b', c_vp * 8),
+                   ('head_w', c_vp), ('head_b', c_vp)])
+
+
+P = ctypes.POINTER
+SIGNATURES = {
+    'ttl_abi_version': (c_i32, []),
+    'ttl_launch_count': (c_i64, []),
+    'ttl_pad_channels': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    'ttl_env_reset': (c_i32, [P(Volume), P(Params), P(Batch), c_vp, c_vp]),
+    'ttl_env_step': (c_i32, [P(Volume), P(Params), P(Batch), c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]),
+    'ttl_env_gather_step_state': (c_i32, [P(Batch), c_i32, c_i32, c_vp, c_i32, c_vp]),
+    'ttl_format_state': (c_i32, [P(Volume), P(Params), c_vp, c_i32, c_i32, c_vp, c_i32, c_vp]),
+    'ttl_stopping_flags': (c_i32, [P(Volume), P(Params), c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    'ttl_streamline_offsets': (c_i32, [P(Batch), c_vp, c_vp]),
+    'ttl_pack_streamlines': (c_i32, [P(Batch), c_vp, c_vp, c_vp]),
+    'ttl_actor_workspace_bytes': (c_i64, [P(ActorWeights), c_i32]),
+    'ttl_actor_plan_create': (c_i32, [P(c_vp), P(ActorWeights), c_i32, c_vp, c_i64, c_vp]),
+    'ttl_actor_plan_destroy': (None, [c_vp]),
+    'ttl_actor_forward': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
+    'ttl_gemm_bf16': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'ttl_oracle_features': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'ttl_oracle_forward': (c_i32, [P(OracleWeights), c_vp, c_i32, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+class TTLError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TTLError('%s not found: build it with `python -m tracktolearn_b200.build` '
+                       '(there is no CPU fallback)' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise TTLError('%s failed with code %d' % (what, rc))
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / None."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

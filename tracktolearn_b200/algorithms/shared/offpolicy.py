@@ -1,0 +1,208 @@
+"""SAC actor/critic holder with the reference's checkpoint format and calling convention
+(reference: algorithms/shared/offpolicy.py:234-482).
+
+The actor forward -- the only dense contraction on the tracking path -- runs through
+``ttl_actor_forward`` (csrc/ttl_actor.cu): tcgen05 tensor cores in bf16 with fp32 TMEM
+accumulators by default, or the CUDA-core fp32 tier with ``precision='fp32'``.
+The critic is only carried for checkpoint compatibility (``load`` reads both files like the
+reference does, offpolicy.py:342-357); training updates are out of this package's hot path.
+"""
+import ctypes
+import os
+from os.path import join as pjoin
+
+import numpy as np
+import torch
+
+from tracktolearn_b200 import _lib
+
+
+def format_widths(widths_str):
+    """Reference: algorithms/shared/utils.py:37-38."""
+    return np.asarray([int(i) for i in str(widths_str).split('-')])
+
+
+class MaxEntropyActor(object):
+    """Weights of the reference's ``MaxEntropyActor`` (offpolicy.py:61-140) + device forward.
+
+    ``state_dict`` keys: ``layers.{0,2,4,..}.{weight,bias}`` (shared/utils.py:41-51)."""
+
+    def __init__(self, state_dim, action_dim, hidden_dims, device, precision='bf16'):
+        self.state_dim = int(state_dim)
+        self.action_dim = int(action_dim)
+        self.hidden_layers = format_widths(hidden_dims)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.TTLError('the actor forward runs on a CUDA device only (got %s)' % (self.device,))
+        self.precision = precision
+        self._lib = _lib.load()
+        dims = [self.state_dim] + [int(w) for w in self.hidden_layers] + [2 * self.action_dim]
+        self._dims = dims
+        g = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 31))
+        self._sd = {}
+        for li in range(len(dims) - 1):   # nn.Linear default init (kaiming_uniform(a=sqrt(5)))
+            bound = 1.0 / np.sqrt(dims[li])
+            self._sd['layers.%d.weight' % (2 * li)] = \
+                ((torch.rand((dims[li + 1], dims[li]), generator=g) * 2 - 1) * bound).to(self.device)
+            self._sd['layers.%d.bias' % (2 * li)] = \
+                ((torch.rand((dims[li + 1],), generator=g) * 2 - 1) * bound).to(self.device)
+        self._plan = None
+        self._plan_rows = 0
+        self._workspace = None
+
+    # -- checkpoint format ---------------------------------------------------------------
+    def state_dict(self):
+        return {k: v.detach().clone() for k, v in self._sd.items()}
+
+    def load_state_dict(self, sd):
+        missing = [k for k in self._sd if k not in sd]
+        unexpected = [k for k in sd if k not in self._sd]
+        if missing or unexpected:
+            raise RuntimeError('Error(s) in loading state_dict for MaxEntropyActor: missing %s, '
+                               'unexpected %s' % (missing, unexpected))
+        for k in self._sd:
+            if tuple(sd[k].shape) != tuple(self._sd[k].shape):
+                raise RuntimeError('size mismatch for %s: %s vs %s' % (k, tuple(sd[k].shape),
+                                                                       tuple(self._sd[k].shape)))
+            self._sd[k] = sd[k].detach().to(self.device, dtype=torch.float32).contiguous()
+        self._drop_plan()
+
+    def parameters(self):
+        return list(self._sd.values())
+
+    # -- forward -------------------------------------------------------------------------
+    def _drop_plan(self):
+        if self._plan is not None:
+            self._lib.ttl_actor_plan_destroy(self._plan)
+        self._plan = None
+        self._plan_rows = 0
+        self._workspace = None
+
+    def __del__(self):
+        try:
+            self._drop_plan()
+        except Exception:
+            pass
+
+    def _weights_struct(self):
+        w = _lib.ActorWeights()
+        nl = len(self._dims) - 1
+        w.n_layers = nl
+        for i in range(nl):
+            w.in_dim[i] = self._dims[i]
+            w.out_dim[i] = self._dims[i + 1]
+            w.w[i] = self._sd['layers.%d.weight' % (2 * i)].data_ptr()
+            w.b[i] = self._sd['layers.%d.bias' % (2 * i)].data_ptr()
+        return w
+
+    def _ensure_plan(self, rows):
+        if self._plan is not None and rows <= self._plan_rows:
+            return
+        self._drop_plan()
+        rows = max(int(rows), 128)
+        w = self._weights_struct()
+        nbytes = self._lib.ttl_actor_workspace_bytes(ctypes.byref(w), rows)
+        if nbytes < 0:
+            raise _lib.TTLError('unsupported actor architecture %s' % (self._dims,))
+        self._workspace = torch.zeros((nbytes + 1024,), dtype=torch.uint8, device=self.device)
+        base = (self._workspace.data_ptr() + 1023) // 1024 * 1024
+        plan = ctypes.c_void_p()
+        _lib.check(self._lib.ttl_actor_plan_create(ctypes.byref(plan), ctypes.byref(w), rows,
+                                                   ctypes.c_void_p(base), nbytes,
+                                                   _lib.stream_ptr(self.device)), 'ttl_actor_plan_create')
+        self._plan = plan
+        self._plan_rows = rows
+        self._w_struct = w
+
+    def forward_device(self, state, probabilistic, n_rows_dev=None, n_rows=None, eps=None,
+                       want_logp=True, want_pre=False, out_action=None):
+        """state: CUDA fp32 [rows, >= state_dim] (row stride free).  ``n_rows_dev``: optional
+        device int32 tensor with the live row count (no host sync).  Returns
+        (action [rows,3], logp [rows] or None, pre [rows,6] or None)."""
+        if state.dim() < 2:
+            state = state[None, :]
+        if state.device != self.device or state.dtype != torch.float32 or state.stride(1) != 1:
+            state = state.to(self.device, dtype=torch.float32).contiguous()
+        rows = int(n_rows if n_rows is not None else state.shape[0])
+        A = self.action_dim
+        action = out_action if out_action is not None else torch.empty((rows, A), dtype=torch.float32,
+                                                                       device=self.device)
+        logp = torch.empty((rows,), dtype=torch.float32, device=self.device) if want_logp else None
+        pre = torch.empty((rows, 2 * A), dtype=torch.float32, device=self.device) if want_pre else None
+        if rows == 0:
+            return action, logp, pre
+        if probabilistic != 0.0 and eps is None:
+            eps = torch.randn((rows, A), dtype=torch.float32, device=self.device)
+        self._ensure_plan(rows)
+        prec = _lib.PRECISION_BF16 if self.precision == 'bf16' else _lib.PRECISION_FP32
+        ld = state.stride(0) if state.shape[0] > 1 else state.shape[1]
+        _lib.check(self._lib.ttl_actor_forward(
+            self._plan, _lib.ptr(state), int(ld), _lib.ptr(n_rows_dev), rows, float(probabilistic),
+            _lib.ptr(eps), _lib.ptr(action), _lib.ptr(logp), _lib.ptr(pre), prec,
+            _lib.stream_ptr(self.device)), 'ttl_actor_forward')
+        self._keep = (state, eps)
+        return action, logp, pre
+
+    def __call__(self, state, probabilistic):
+        """Reference: MaxEntropyActor.forward (offpolicy.py:94-140) -> (pi_action, logp_pi)."""
+        action, logp, _ = self.forward_device(state, probabilistic)
+        return action, logp
+
+    def eval(self):
+        return self
+
+    def train(self):
+        return self
+
+    def to(self, device):
+        return self
+
+
+class SACActorCritic(object):
+    """Reference: algorithms/shared/offpolicy.py:407-482 (+ ActorCritic base :234-372)."""
+
+    def __init__(self, state_dim, action_dim, hidden_dims, device, precision='bf16'):
+        self.device = torch.device(device)
+        self.actor = MaxEntropyActor(state_dim, action_dim, hidden_dims, self.device, precision)
+        self.critic_state_dict = None   # carried for save/load symmetry; not evaluated here
+
+    def act(self, state, probabilistic=1.0):
+        return self.actor(state, probabilistic)
+
+    def select_action(self, state, probabilistic=1.0):
+        if len(state.shape) < 2:
+            state = state[None, :]
+        action, _ = self.act(state, probabilistic)
+        return action
+
+    def parameters(self):
+        return self.actor.parameters()
+
+    def load_state_dict(self, state_dict):
+        actor_state_dict, critic_state_dict = state_dict
+        self.actor.load_state_dict(actor_state_dict)
+        self.critic_state_dict = critic_state_dict
+
+    def state_dict(self):
+        return self.actor.state_dict(), self.critic_state_dict
+
+    def save(self, path, filename):
+        """Reference: offpolicy.py:327-340."""
+        if self.critic_state_dict is not None:
+            torch.save(self.critic_state_dict, pjoin(path, filename + "_critic.pth"))
+        torch.save({k: v.cpu() for k, v in self.actor.state_dict().items()},
+                   pjoin(path, filename + "_actor.pth"))
+
+    def load(self, path, filename):
+        """Reference: offpolicy.py:342-357 (both files are read; the critic is kept as-is)."""
+        critic_file = pjoin(path, filename + '_critic.pth')
+        if os.path.exists(critic_file):
+            self.critic_state_dict = torch.load(critic_file, map_location='cpu')
+        self.actor.load_state_dict(torch.load(pjoin(path, filename + '_actor.pth'),
+                                              map_location=self.device))
+
+    def eval(self):
+        self.actor.eval()
+
+    def train(self):
+        self.actor.train()

@@ -1,0 +1,688 @@
+// SAC actor forward for B200 (sm_100a): the only dense contraction on the tracking path.
+//
+// Reference: algorithms/shared/offpolicy.py:94-140 (MaxEntropyActor.forward) over the
+// nn.Sequential built by algorithms/shared/utils.py:41-51 (Linear+ReLU x3, Linear), which the
+// reference runs as four cuBLAS sgemm calls plus ~15 small elementwise launches.
+//
+// Here:
+//   pack_state   fp32 state rows [n][ld] -> bf16 [n][K0 padded to 64]
+//   dense layers C = relu(A . W^T + b), bf16 operands staged by TMA (128B swizzle) into a
+//                4-stage shared-memory ring, tcgen05.mma (cta_group::1, M=128, N=256, K=16)
+//                issued by one thread, fp32 accumulators double-buffered in TMEM (2 x 256
+//                columns), epilogue warps read them back with tcgen05.ld, add bias, ReLU,
+//                convert to bf16 and store; persistent CTAs walk the tile list.
+//   head         last (6-wide) layer on CUDA cores in fp32 + clamp/exp/tanh/log-prob policy
+//                head fused in one kernel (a 6-column GEMM has no tensor-core shape).
+// A CUDA-core fp32 tier (TTL_PRECISION_FP32) reproduces the reference's fp32 arithmetic to
+// ~1e-6 for parity tests and users who want it.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "ttl_common.cuh"
+
+namespace {
+
+// ==========================================================================================
+// PTX wrappers
+// ==========================================================================================
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ==========================================================================================
+// Dense layer: C[m][ldc] = act(A[m][k] . W[n][k]^T + bias)
+// ==========================================================================================
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4, ACC_STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES = BN * BK * 2;          // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 256;             // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
+constexpr int TMEM_COLS = ACC_STAGES * BN;    // 512: all of tensor memory
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+
+// UMMA shared-memory descriptor: K-major operand tile, rows of 64 bf16 (128 B) under the
+// 128-byte swizzle TMA wrote; 8-row groups are 1024 B apart (SBO); descriptor version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
+  d |= (uint64_t)1 << 46;                             // version = 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256.
+__device__ __forceinline__ constexpr uint32_t umma_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dense_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ C, int ldc,
+                  const int* __restrict__ m_dev, int m_max, int n_pad, int k_pad, int relu) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ttl_smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tempty = [&](int s) { return bar0 + 8u * (2 * STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int m = m_dev ? *m_dev : m_max;
+  m = min(m, m_max);
+  const int n_m = (m + BM - 1) / BM, n_n = (n_pad + BN - 1) / BN;
+  const int total = n_m * n_n, kblocks = k_pad / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m_blk = tile / n_n, n_blk = tile - m_blk * n_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full(stage), STAGE_BYTES);
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          tma_load_2d(sa, &tma_a, full(stage), kb * BK, m_blk * BM);
+          tma_load_2d(sa + A_BYTES, &tma_b, full(stage), kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      constexpr uint32_t idesc = umma_idesc();
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint64_t da = umma_desc(sa), db = umma_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes per K=16 slice inside the 128-byte swizzle row: +2 in 16-byte units
+            tc_mma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                        (uint32_t)((kb | k) != 0));
+          }
+          tc_commit(empty(stage));   // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull(acc));       // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {  // ===== epilogue: TMEM -> registers -> bias/ReLU -> bf16 -> HBM =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int m_blk = tile / n_n, n_blk = tile - m_blk * n_n;
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < m;
+      __nv_bfloat16* crow = C + (size_t)row * ldc;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col0 = n_blk * BN + ch * 32;
+        if (col0 >= ldc) break;  // warp-uniform
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+        tc_wait_ld();
+        if (row_ok) {
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x0 = __uint_as_float(v[2 * j]) + __ldg(bias + col0 + 2 * j);
+            float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + col0 + 2 * j + 1);
+            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ==========================================================================================
+// Packing kernels
+// ==========================================================================================
+__global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                        int n_out, int n_in, int n_pad, int k_pad) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_pad * k_pad) return;
+  const int r = (int)(t / k_pad), c = (int)(t - (long long)r * k_pad);
+  const float x = (r < n_out && c < n_in) ? w[(size_t)r * n_in + c] : 0.f;
+  out[t] = __float2bfloat16_rn(x);
+}
+__global__ void pack_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int n_out, int n_pad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_pad) out[t] = t < n_out ? b[t] : 0.f;
+}
+// fp32 state rows -> bf16 rows padded to k_pad (8 outputs = one 16-byte store per thread)
+__global__ void __launch_bounds__(256) pack_state_bf16_kernel(const float* __restrict__ state, int ld,
+                                                              int width, const int* __restrict__ n_dev,
+                                                              int n_max, __nv_bfloat16* __restrict__ out,
+                                                              int k_pad) {
+  int n = n_dev ? *n_dev : n_max;
+  n = min(n, n_max);
+  const int per_row = k_pad >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * per_row) return;
+  const int r = (int)(t / per_row), g = (int)(t - (long long)r * per_row);
+  const float* s = state + (size_t)r * ld + g * 8;
+  uint32_t p[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = g * 8 + 2 * j;
+    const float x0 = c < width ? s[2 * j] : 0.f;
+    const float x1 = c + 1 < width ? s[2 * j + 1] : 0.f;
+    __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    p[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)r * k_pad + g * 8) = make_uint4(p[0], p[1], p[2], p[3]);
+}
+
+// ==========================================================================================
+// Head: last linear layer (<= 8 outputs) in fp32 + SAC policy head (offpolicy.py:116-140)
+// ==========================================================================================
+constexpr int HEAD_MAX_OUT = 8;
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T x);
+template <>
+__device__ __forceinline__ float to_f32<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+__device__ __forceinline__ float softplus_f(float x) {  // F.softplus, threshold 20
+  return x > 20.f ? x : log1pf(expf(x));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ h, int ldh, int k,
+                                                   const float* __restrict__ w, const float* __restrict__ b,
+                                                   int n_out, const int* __restrict__ n_dev, int n_max,
+                                                   float prob, const float* __restrict__ eps,
+                                                   float* __restrict__ action, float* __restrict__ logp,
+                                                   float* __restrict__ pre) {
+  extern __shared__ float s_w[];  // [n_out][k]
+  for (int t = threadIdx.x; t < n_out * k; t += blockDim.x) s_w[t] = w[t];
+  __syncthreads();
+  int n = n_dev ? *n_dev : n_max;
+  n = min(n, n_max);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int A = n_out >> 1;
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp; r < n; r += warps_total) {
+    float acc[HEAD_MAX_OUT];
+#pragma unroll
+    for (int o = 0; o < HEAD_MAX_OUT; ++o) acc[o] = 0.f;
+    const T* row = h + (size_t)r * ldh;
+    for (int c = lane; c < k; c += 32) {
+      const float x = to_f32<T>(row[c]);
+#pragma unroll
+      for (int o = 0; o < HEAD_MAX_OUT; ++o)
+        if (o < n_out) acc[o] = fmaf(x, s_w[o * k + c], acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < HEAD_MAX_OUT; ++o)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+    if (lane == 0) {
+      float lp = 0.f;
+#pragma unroll
+      for (int o = 0; o < HEAD_MAX_OUT; ++o)
+        if (o < n_out) {
+          acc[o] += b[o];
+          if (pre) pre[(size_t)r * n_out + o] = acc[o];
+        }
+#pragma unroll
+      for (int a = 0; a < HEAD_MAX_OUT / 2; ++a) {
+        if (a >= A) break;
+        const float mu = acc[a];
+        const float log_std = fminf(fmaxf(acc[A + a], -20.f), 2.f);
+        const float std = expf(log_std) * prob;
+        const float e = eps ? eps[(size_t)r * A + a] : 0.f;
+        const float pi = eps ? fmaf(std, e, mu) : mu;
+        if (logp) {
+          // Normal(mu,std).log_prob(pi) and the tanh correction of offpolicy.py:131-135
+          const float z = pi - mu;
+          lp += -(z * z) / (2.f * std * std) - logf(std) - 0.9189385332046727f;
+          lp -= 2.f * (0.6931471805599453f - pi - softplus_f(-2.f * pi));
+        }
+        action[(size_t)r * A + a] = tanhf(pi);
+      }
+      if (logp) logp[r] = lp;
+    }
+  }
+}
+
+// ==========================================================================================
+// fp32 tier: plain tiled SGEMM on CUDA cores (reference precision)
+// ==========================================================================================
+constexpr int SG_T = 64, SG_K = 16;
+__global__ void __launch_bounds__(256) dense_f32_kernel(const float* __restrict__ A, int lda,
+                                                        const float* __restrict__ W,
+                                                        const float* __restrict__ bias,
+                                                        float* __restrict__ C, int ldc, int m, int n,
+                                                        int k, int relu) {
+  __shared__ float sA[SG_K][SG_T + 1];
+  __shared__ float sB[SG_K][SG_T + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < k; k0 += SG_K) {
+    for (int t = threadIdx.x; t < SG_T * SG_K; t += 256) {
+      const int r = t / SG_K, c = t - r * SG_K;
+      sA[c][r] = (m0 + r < m && k0 + c < k) ? A[(size_t)(m0 + r) * lda + k0 + c] : 0.f;
+      sB[c][r] = (n0 + r < n && k0 + c < k) ? W[(size_t)(n0 + r) * k + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_K; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; bb[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + ty * 4 + i, c = n0 + tx * 4 + j;
+      if (r < m && c < n) {
+        float x = acc[i][j] + bias[c];
+        if (relu) x = fmaxf(x, 0.f);
+        C[(size_t)r * ldc + c] = x;
+      }
+    }
+}
+
+// ==========================================================================================
+// Host side: TMA descriptors, plan
+// ==========================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 row-major [rows][cols] tensor, box = [box_rows][64 cols], 128-byte swizzle.
+int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return TTL_ERR_DRIVER;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : TTL_ERR_DRIVER;
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+int launch_dense_bf16(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, __nv_bfloat16* C,
+                      int ldc, const int* m_dev, int m_max, int n_pad, int k_pad, int relu,
+                      cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dense_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GEMM_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = ttl_div_up(m_max, BM) * ttl_div_up(n_pad, BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (grid <= 0) return 0;
+  dense_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ta, tb, bias, C, ldc, m_dev, m_max, n_pad,
+                                                         k_pad, relu);
+  TTL_LAUNCHED();
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+}  // namespace
+
+struct ttl_actor_plan {
+  ttl_actor_weights w;
+  int max_rows;
+  int k_pad[TTL_ACTOR_MAX_LAYERS];   // padded fan-in of layer i  (multiple of 64)
+  int n_pad[TTL_ACTOR_MAX_LAYERS];   // padded fan-out of layer i (= k_pad[i+1])
+  __nv_bfloat16* wq[TTL_ACTOR_MAX_LAYERS];
+  float* bq[TTL_ACTOR_MAX_LAYERS];
+  __nv_bfloat16* act[2];             // ping-pong activations [max_rows][max_kpad]
+  float* f32[2];                     // fp32-tier scratch [F32_CHUNK][max_width]
+  int max_kpad, max_width;
+  CUtensorMap map_w[TTL_ACTOR_MAX_LAYERS];
+  CUtensorMap map_a[TTL_ACTOR_MAX_LAYERS];  // A operand of layer i
+};
+
+namespace {
+constexpr int F32_CHUNK = 8192;
+
+struct Layout {
+  int64_t total;
+  int64_t off_w[TTL_ACTOR_MAX_LAYERS], off_b[TTL_ACTOR_MAX_LAYERS], off_act[2], off_f32[2];
+  int k_pad[TTL_ACTOR_MAX_LAYERS], n_pad[TTL_ACTOR_MAX_LAYERS];
+  int max_kpad, max_width;
+};
+
+int plan_layout(const ttl_actor_weights* w, int max_rows, Layout* L) {
+  if (!w || w->n_layers < 2 || w->n_layers > TTL_ACTOR_MAX_LAYERS || max_rows <= 0) return TTL_ERR_BAD_ARG;
+  if (w->out_dim[w->n_layers - 1] > HEAD_MAX_OUT || (w->out_dim[w->n_layers - 1] & 1)) return TTL_ERR_UNSUPPORTED;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+  L->max_kpad = 0;
+  L->max_width = 0;
+  for (int i = 0; i < w->n_layers; ++i) {
+    if (i > 0 && w->in_dim[i] != w->out_dim[i - 1]) return TTL_ERR_BAD_ARG;
+    L->k_pad[i] = round_up(w->in_dim[i], BK);
+    L->n_pad[i] = round_up(w->out_dim[i], BK);
+    if (L->k_pad[i] > L->max_kpad) L->max_kpad = L->k_pad[i];
+    if (w->in_dim[i] > L->max_width) L->max_width = w->in_dim[i];
+    if (w->out_dim[i] > L->max_width) L->max_width = w->out_dim[i];
+  }
+  for (int i = 0; i < w->n_layers - 1; ++i) {
+    L->off_w[i] = take((int64_t)L->n_pad[i] * L->k_pad[i] * 2);
+    L->off_b[i] = take((int64_t)round_up(L->n_pad[i], BN) * 4);
+  }
+  for (int j = 0; j < 2; ++j) L->off_act[j] = take((int64_t)max_rows * L->max_kpad * 2);
+  for (int j = 0; j < 2; ++j) L->off_f32[j] = take((int64_t)F32_CHUNK * L->max_width * 4);
+  L->total = off;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t ttl_actor_workspace_bytes(const ttl_actor_weights* w, int32_t max_rows) {
+  Layout L;
+  if (plan_layout(w, max_rows, &L)) return -1;
+  return L.total;
+}
+
+int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int32_t max_rows,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!out || !workspace) return TTL_ERR_BAD_ARG;
+  Layout L;
+  int rc = plan_layout(w, max_rows, &L);
+  if (rc) return rc;
+  if (workspace_bytes < L.total || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return TTL_ERR_BAD_ARG;
+  ttl_actor_plan* p = new (std::nothrow) ttl_actor_plan();
+  if (!p) return TTL_ERR_BAD_ARG;
+  p->w = *w;
+  p->max_rows = max_rows;
+  p->max_kpad = L.max_kpad;
+  p->max_width = L.max_width;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int j = 0; j < 2; ++j) {
+    p->act[j] = reinterpret_cast<__nv_bfloat16*>(ws + L.off_act[j]);
+    p->f32[j] = reinterpret_cast<float*>(ws + L.off_f32[j]);
+  }
+  const int nl = w->n_layers;
+  for (int i = 0; i < nl; ++i) { p->k_pad[i] = L.k_pad[i]; p->n_pad[i] = L.n_pad[i]; }
+  for (int i = 0; i < nl - 1; ++i) {  // hidden layers run on tensor cores
+    p->wq[i] = reinterpret_cast<__nv_bfloat16*>(ws + L.off_w[i]);
+    p->bq[i] = reinterpret_cast<float*>(ws + L.off_b[i]);
+    const long long tot = (long long)L.n_pad[i] * L.k_pad[i];
+    pack_weight_bf16_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(w->w[i], p->wq[i], w->out_dim[i],
+                                                                w->in_dim[i], L.n_pad[i], L.k_pad[i]);
+    TTL_LAUNCHED();
+    const int bp = round_up(L.n_pad[i], BN);
+    pack_bias_kernel<<<ttl_div_up(bp, 256), 256, 0, s>>>(w->b[i], p->bq[i], w->out_dim[i], bp);
+    TTL_LAUNCHED();
+    rc = make_tmap(&p->map_w[i], p->wq[i], (uint64_t)L.n_pad[i], (uint64_t)L.k_pad[i], BN);
+    if (rc) { delete p; return rc; }
+    // A operand of layer i lives in act[i & 1] with row pitch k_pad[i]
+    rc = make_tmap(&p->map_a[i], p->act[i & 1], (uint64_t)max_rows, (uint64_t)L.k_pad[i], BM);
+    if (rc) { delete p; return rc; }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { delete p; return (int)e; }
+  *out = p;
+  return 0;
+}
+
+void ttl_actor_plan_destroy(ttl_actor_plan* plan) { delete plan; }
+
+int ttl_actor_forward(ttl_actor_plan* p, const float* state, int32_t ld_state, const int32_t* n_rows_dev,
+                      int32_t n_rows_max, float probabilistic, const float* eps, float* action,
+                      float* logp, float* pre, int32_t precision, void* stream) {
+  if (!p || !state || !action || n_rows_max > p->max_rows) return TTL_ERR_BAD_ARG;
+  if (probabilistic != 0.f && !eps) return TTL_ERR_BAD_ARG;
+  if (n_rows_max <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const ttl_actor_weights& w = p->w;
+  const int nl = w.n_layers;
+  const int n_out = w.out_dim[nl - 1], k_last = w.in_dim[nl - 1];
+  const size_t head_smem = (size_t)n_out * k_last * sizeof(float);
+  const int head_grid = num_sms() * 2;
+
+  if (precision == TTL_PRECISION_BF16) {
+    static bool head_attr = false;
+    if (!head_attr && head_smem > 48 * 1024) {
+      cudaFuncSetAttribute(head_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      head_attr = true;
+    }
+    const long long tot = (long long)n_rows_max * (p->k_pad[0] >> 3);
+    pack_state_bf16_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(state, ld_state, w.in_dim[0], n_rows_dev,
+                                                              n_rows_max, p->act[0], p->k_pad[0]);
+    TTL_LAUNCHED();
+    for (int i = 0; i < nl - 1; ++i) {
+      // layer i: act[i&1] (pitch k_pad[i]) -> act[(i+1)&1] (pitch k_pad[i+1] = n_pad[i])
+      int rc = launch_dense_bf16(p->map_a[i], p->map_w[i], p->bq[i], p->act[(i + 1) & 1], p->n_pad[i],
+                                 n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1, s);
+      if (rc) return rc;
+    }
+    head_kernel<__nv_bfloat16><<<head_grid, 256, head_smem, s>>>(
+        p->act[(nl - 1) & 1], p->k_pad[nl - 1], k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
+        n_rows_max, probabilistic, eps, action, logp, pre);
+    TTL_LAUNCHED();
+    TTL_CHECK_LAST();
+    return 0;
+  }
+  if (precision == TTL_PRECISION_FP32) {
+    // Reference-precision tier; needs the row count on the host.
+    int n = n_rows_max;
+    if (n_rows_dev) {
+      cudaError_t e = cudaMemcpyAsync(&n, n_rows_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) return (int)e;
+      if (n > n_rows_max) n = n_rows_max;
+    }
+    static bool head_attr32 = false;
+    if (!head_attr32 && head_smem > 48 * 1024) {
+      cudaFuncSetAttribute(head_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      head_attr32 = true;
+    }
+    const int A = n_out / 2;
+    for (int r0 = 0; r0 < n; r0 += F32_CHUNK) {
+      const int m = (n - r0) < F32_CHUNK ? (n - r0) : F32_CHUNK;
+      const float* in = state + (size_t)r0 * ld_state;
+      int ld_in = ld_state;
+      for (int i = 0; i < nl - 1; ++i) {
+        float* o = p->f32[i & 1];
+        dim3 grid(ttl_div_up(w.out_dim[i], SG_T), ttl_div_up(m, SG_T));
+        dense_f32_kernel<<<grid, 256, 0, s>>>(in, ld_in, w.w[i], w.b[i], o, p->max_width, m, w.out_dim[i],
+                                              w.in_dim[i], 1);
+        TTL_LAUNCHED();
+        in = o;
+        ld_in = p->max_width;
+      }
+      head_kernel<float><<<head_grid, 256, head_smem, s>>>(
+          in, ld_in, k_last, w.w[nl - 1], w.b[nl - 1], n_out, nullptr, m, probabilistic,
+          eps ? eps + (size_t)r0 * A : nullptr, action + (size_t)r0 * A, logp ? logp + r0 : nullptr,
+          pre ? pre + (size_t)r0 * n_out : nullptr);
+      TTL_LAUNCHED();
+    }
+    TTL_CHECK_LAST();
+    return 0;
+  }
+  return TTL_ERR_UNSUPPORTED;
+}
+
+int ttl_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t m, int32_t n,
+                  int32_t k, int32_t ldc, int32_t relu, const int32_t* m_dev, void* stream) {
+  if (!A || !W || !bias || !C || (k % BK) || (n % BK) || ldc < n || (ldc % 8)) return TTL_ERR_BAD_ARG;
+  if (m <= 0) return 0;
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, (uint64_t)m, (uint64_t)k, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tb, W, (uint64_t)n, (uint64_t)k, BN);
+  if (rc) return rc;
+  // bias must be readable up to the tile edge: caller pads it to a multiple of 256 floats
+  return launch_dense_bf16(ta, tb, bias, static_cast<__nv_bfloat16*>(C), ldc, m_dev, m, n, k, relu,
+                           (cudaStream_t)stream);
+}
+
+}  // extern "C"

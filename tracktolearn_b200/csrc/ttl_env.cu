@@ -1,0 +1,711 @@
+// Batched tracking-environment step for B200 (sm_100a).
+//
+// Replaces, on the device and without host round trips, what the reference does per step in
+// numpy + dwi_ml + scipy (paths relative to /root/reference/TrackToLearn):
+//   environments/env.py:493-502        _format_actions  (normalise, scale to the step size)
+//   environments/tracking_env.py:165-183  first-step flip and streamline growth
+//   environments/env.py:567-603        _compute_stopping_flags
+//   environments/utils.py:127-173      is_too_long, is_too_curvy
+//   environments/stopping_criteria.py:38-82  cubic B-spline tracking-mask criterion
+//   environments/local_reward.py:29-107     peaks alignment reward
+//   environments/tracking_env.py:192-202,223-245  continue_idx bookkeeping / harvest
+//   environments/env.py:504-565        _format_state (7-point trilinear SH + previous dirs)
+//
+// Data layout in HBM: SH volume [X][Y][Z][CP] fp32 with the 45 coefficients padded to CP=48
+// floats so a voxel is 12 aligned float4 (192 B) and the two z-corners of a trilinear cell
+// are one contiguous 384 B run; streamline points [row][max_pts][3] fp32; state rows
+// [rank][ld_state=616] fp32 so rows start 16-byte aligned.
+//
+// Three launches per step, none of which needs the host:
+//   propagate_stop  one thread per alive streamline (byte/flag work, 64 fp64 spline taps)
+//   compact         one CTA, ordered stream compaction of the alive list (keeps the
+//                   reference's ascending continue_idx order)
+//   build_state     one warp per streamline: float4 gathers of the 7x8 trilinear corners
+//                   (unique footprint ~26 voxels, duplicates hit L1), row staged in shared
+//                   memory and written with coalesced 16-byte stores.
+#include "ttl_common.cuh"
+
+std::atomic<long long> g_ttl_launches{0};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// float helpers that refuse FMA contraction, so sums of products round like numpy's
+// (no-FMA) einsum loops.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot3f(float ax, float ay, float az, float bx, float by, float bz) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+__device__ __forceinline__ double dot3d(double ax, double ay, double az, double bx, double by,
+                                        double bz) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
+}
+
+// scipy NI_GeometricTransform tap index reflection for the 'mirror' spline boundary.
+__device__ __forceinline__ int mirror_idx(int idx, int n) {
+  if (n <= 1) return 0;
+  const int s2 = 2 * n - 2;
+  if (idx < 0) {
+    idx = s2 * (int)(-idx / s2) + idx;
+    return idx <= 1 - n ? idx + s2 : -idx;
+  }
+  if (idx >= n) {
+    idx -= s2 * (int)(idx / s2);
+    if (idx >= n) idx = s2 - idx;
+  }
+  return idx;
+}
+
+// scipy get_spline_interpolation_weights(order 3)
+__device__ __forceinline__ void bspline3(double y, double w[4]) {
+  const double z = 1.0 - y;
+  w[1] = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(y, y), y - 2.0), 3.0), 4.0), 6.0);
+  w[2] = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(z, z), z - 2.0), 3.0), 4.0), 6.0);
+  w[0] = __ddiv_rn(__dmul_rn(__dmul_rn(z, z), z), 6.0);
+  w[3] = ((1.0 - w[0]) - w[1]) - w[2];
+}
+
+// stopping_criteria.py:79-82: map_coordinates(coef, p - 0.5, order=3, mode='constant',
+// cval=0, prefilter=False).  0 for NaN/inf or anything outside [0, n-1].
+__device__ double mask_spline_value(const ttl_volume& v, float px, float py, float pz) {
+  const double c[3] = {(double)__fsub_rn(px, 0.5f), (double)__fsub_rn(py, 0.5f),
+                       (double)__fsub_rn(pz, 0.5f)};
+  const int dims[3] = {v.MX, v.MY, v.MZ};
+  int start[3];
+  double w[3][4];
+  bool edge = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (!(c[a] >= 0.0 && c[a] <= (double)(dims[a] - 1))) return 0.0;
+    const double fl = floor(c[a]);
+    start[a] = (int)fl - 1;
+    edge |= (start[a] < 0) || (start[a] + 3 >= dims[a]);
+    bspline3(c[a] - fl, w[a]);
+  }
+  int xi[4], yi[4], zi[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    xi[t] = edge ? mirror_idx(start[0] + t, dims[0]) : start[0] + t;
+    yi[t] = edge ? mirror_idx(start[1] + t, dims[1]) : start[1] + t;
+    zi[t] = edge ? mirror_idx(start[2] + t, dims[2]) : start[2] + t;
+  }
+  double out = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double* line = v.mask_coef + ((size_t)xi[i] * v.MY + yi[j]) * v.MZ;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        double t = __ldg(line + zi[k]);
+        t = __dmul_rn(t, w[0][i]);
+        t = __dmul_rn(t, w[1][j]);
+        t = __dmul_rn(t, w[2][k]);
+        out = __dadd_rn(out, t);
+      }
+    }
+  }
+  return out;
+}
+
+// utils.py:145-173 on the last three points (fp32, no clipping: NaN compares False).
+__device__ __forceinline__ bool too_curvy(const float* p3, float theta_rad) {
+  const float ux = __fsub_rn(p3[6], p3[3]), uy = __fsub_rn(p3[7], p3[4]), uz = __fsub_rn(p3[8], p3[5]);
+  const float vx = __fsub_rn(p3[3], p3[0]), vy = __fsub_rn(p3[4], p3[1]), vz = __fsub_rn(p3[5], p3[2]);
+  const float nu = __fsqrt_rn(dot3f(ux, uy, uz, ux, uy, uz));
+  const float nv = __fsqrt_rn(dot3f(vx, vy, vz, vx, vy, vz));
+  const float d = dot3f(__fdiv_rn(ux, nu), __fdiv_rn(uy, nu), __fdiv_rn(uz, nu),
+                        __fdiv_rn(vx, nv), __fdiv_rn(vy, nv), __fdiv_rn(vz, nv));
+  return acosf(d) > theta_rad;
+}
+
+// env.py:567-603 in the dict order LENGTH, CURVATURE, MASK (env.py:233-260).
+// P = first point of the row, L = number of points.
+__device__ int stopping_flags(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
+                              double* mask_value_out) {
+  int f = 0;
+  if (L >= prm.max_nb_steps) f |= TTL_STOPPING_LENGTH;
+  if (L >= 3 && too_curvy(P + (size_t)(L - 3) * 3, prm.theta_rad)) f |= TTL_STOPPING_CURVATURE;
+  const float* tip = P + (size_t)(L - 1) * 3;
+  const double mv = mask_spline_value(v, tip[0], tip[1], tip[2]);
+  if (mask_value_out) *mask_value_out = mv;
+  if (mv < prm.mask_threshold) f |= TTL_STOPPING_MASK;
+  return f;
+}
+
+__device__ __forceinline__ float nan_to_num(float x) {
+  if (isnan(x)) return 0.f;
+  if (isinf(x)) return x > 0 ? 3.4028234663852886e+38f : -3.4028234663852886e+38f;
+  return x;
+}
+
+// local_reward.py:29-107.  P = row start, L >= 2.
+__device__ float alignment_reward(const ttl_volume& v, const float* P, int L) {
+  const float* p2 = P + (size_t)(L - 2) * 3;  // streamlines[:, -2]
+  const float* p1 = P + (size_t)(L - 1) * 3;
+  // .astype(int32) truncates toward zero; interpolation.py:20-23 rounds (no-op) and clips
+  int ix = min(max(__float2int_rz(p2[0]), 0), v.PX - 1);
+  int iy = min(max(__float2int_rz(p2[1]), 0), v.PY - 1);
+  int iz = min(max(__float2int_rz(p2[2]), 0), v.PZ - 1);
+  const float* pk = v.peaks + (((size_t)ix * v.PY + iy) * v.PZ + iz) * 15;
+  float ux = __fsub_rn(p1[0], p2[0]), uy = __fsub_rn(p1[1], p2[1]), uz = __fsub_rn(p1[2], p2[2]);
+  {
+    const float n = __fsqrt_rn(dot3f(ux, uy, uz, ux, uy, uz));
+    ux = nan_to_num(__fdiv_rn(ux, n));
+    uy = nan_to_num(__fdiv_rn(uy, n));
+    uz = nan_to_num(__fdiv_rn(uz, n));
+  }
+  float best = 0.f;
+  bool best_nan = false;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    float a = __ldg(pk + 3 * k), b = __ldg(pk + 3 * k + 1), c = __ldg(pk + 3 * k + 2);
+    const float n = __fsqrt_rn(dot3f(a, b, c, a, b, c));
+    a = nan_to_num(__fdiv_rn(a, n));
+    b = nan_to_num(__fdiv_rn(b, n));
+    c = nan_to_num(__fdiv_rn(c, n));
+    const float d = fabsf(dot3f(a, b, c, ux, uy, uz));
+    if (isnan(d)) best_nan = true;   // np.amax propagates NaN
+    best = fmaxf(best, d);
+  }
+  float r = best_nan ? __int_as_float(0x7fc00000) : best;
+  if (L >= 3) {
+    const float* p3 = P + (size_t)(L - 3) * 3;
+    float wx = __fsub_rn(p2[0], p3[0]), wy = __fsub_rn(p2[1], p3[1]), wz = __fsub_rn(p2[2], p3[2]);
+    const float n = __fsqrt_rn(dot3f(wx, wy, wz, wx, wy, wz));
+    wx = nan_to_num(__fdiv_rn(wx, n));
+    wy = nan_to_num(__fdiv_rn(wy, n));
+    wz = nan_to_num(__fdiv_rn(wz, n));
+    // np.einsum(..., out=float64 factors): the dot product is taken in double
+    const double f = dot3d((double)ux, (double)uy, (double)uz, (double)wx, (double)wy, (double)wz);
+    r = (float)__dmul_rn((double)r, f);  // rewards(f32) *= factors(f64)
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: reset
+// ------------------------------------------------------------------------------------------
+__global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    b.ctrl[0] = b.n;
+    b.ctrl[1] = 0;
+    b.ctrl[2] = 1;
+  }
+  if (i >= b.n) return;
+  float* P = b.points + (size_t)i * b.max_pts * 3;
+  P[0] = (float)seeds[3 * i + 0];
+  P[1] = (float)seeds[3 * i + 1];
+  P[2] = (float)seeds[3 * i + 2];
+  b.flags[i] = 0;
+  b.lengths[i] = 1;
+  b.dones[i] = 0;
+  b.alive[0][i] = i;
+  b.dest[i] = i;
+  b.stop[i] = 0;
+  b.step_flags[i] = 0;
+  b.reward[i] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: propagate + stopping criteria + reward, one thread per alive streamline
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) propagate_stop_kernel(
+    ttl_volume v, ttl_params prm, ttl_batch b, int cur, const float* __restrict__ actions,
+    int lda, const double* __restrict__ noise) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_alive = b.ctrl[cur];
+  if (r >= n_alive) return;
+  const int L = b.ctrl[2];  // points so far
+  const int i = b.alive[cur][r];
+  float* P = b.points + (size_t)i * b.max_pts * 3;
+  const float px = P[(L - 1) * 3 + 0], py = P[(L - 1) * 3 + 1], pz = P[(L - 1) * 3 + 2];
+  const float ax = actions[(size_t)r * lda + 0], ay = actions[(size_t)r * lda + 1],
+              az = actions[(size_t)r * lda + 2];
+
+  float qx, qy, qz;  // the new point
+  if (prm.dir_f64) {
+    // noisy_tracking_env.py:74-77 then env.py:493-502, all float64
+    double dx = (double)ax, dy = (double)ay, dz = (double)az;
+    if (noise) {
+      dx = __dadd_rn(dx, noise[3 * (size_t)r + 0]);
+      dy = __dadd_rn(dy, noise[3 * (size_t)r + 1]);
+      dz = __dadd_rn(dz, noise[3 * (size_t)r + 2]);
+    }
+    const double nrm = __dsqrt_rn(dot3d(dx, dy, dz, dx, dy, dz));
+    dx = __dmul_rn(__ddiv_rn(dx, nrm), prm.step_vox);
+    dy = __dmul_rn(__ddiv_rn(dy, nrm), prm.step_vox);
+    dz = __dmul_rn(__ddiv_rn(dz, nrm), prm.step_vox);
+    qx = (float)__dadd_rn((double)px, dx);
+    qy = (float)__dadd_rn((double)py, dy);
+    qz = (float)__dadd_rn((double)pz, dz);
+    if (L == 1) {  // tracking_env.py:165-178: flip if the first step would stop
+      P[3] = qx; P[4] = qy; P[5] = qz;
+      if (stopping_flags(v, prm, P, 2, nullptr) != 0) {
+        qx = (float)__dadd_rn((double)px, -dx);
+        qy = (float)__dadd_rn((double)py, -dy);
+        qz = (float)__dadd_rn((double)pz, -dz);
+      }
+    }
+  } else {
+    const float stepf = (float)prm.step_vox;
+    const float nrm = __fsqrt_rn(dot3f(ax, ay, az, ax, ay, az));
+    const float dx = __fmul_rn(__fdiv_rn(ax, nrm), stepf);
+    const float dy = __fmul_rn(__fdiv_rn(ay, nrm), stepf);
+    const float dz = __fmul_rn(__fdiv_rn(az, nrm), stepf);
+    qx = __fadd_rn(px, dx); qy = __fadd_rn(py, dy); qz = __fadd_rn(pz, dz);
+    if (L == 1) {
+      P[3] = qx; P[4] = qy; P[5] = qz;
+      if (stopping_flags(v, prm, P, 2, nullptr) != 0) {
+        qx = __fadd_rn(px, -dx); qy = __fadd_rn(py, -dy); qz = __fadd_rn(pz, -dz);
+      }
+    }
+  }
+  P[L * 3 + 0] = qx; P[L * 3 + 1] = qy; P[L * 3 + 2] = qz;
+  const int Ln = L + 1;
+  const int f = stopping_flags(v, prm, P, Ln, nullptr);
+  b.step_flags[r] = f;
+  b.stop[r] = f != 0;
+  if (f) {
+    b.flags[i] = f;
+    b.dones[i] = 1;
+    b.lengths[i] = Ln;  // the reference records it in harvest(); nothing reads it in between
+  }
+  if (prm.compute_reward && v.peaks) {
+    // reward.py:63-67: w * f(...) stays float32 (weak python scalar)
+    b.reward[r] = __fmul_rn((float)prm.alignment_weighting, alignment_reward(v, P, Ln));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: ordered compaction of the alive list, one CTA.
+// Survivors keep their relative order (the reference's continue_idx[~stopping]); rank r gets
+// dest[r] = its row in state[next]: survivors first, stopped rows after them.
+// ------------------------------------------------------------------------------------------
+constexpr int kCompactThreads = 1024;
+
+__global__ void __launch_bounds__(kCompactThreads) compact_kernel(ttl_batch b, int cur) {
+  __shared__ int s_keep[kCompactThreads];
+  __shared__ int s_stop[kCompactThreads];
+  const int n = b.ctrl[cur];
+  const int tid = threadIdx.x;
+  int per = (n + kCompactThreads - 1) / kCompactThreads;
+  per = (per + 15) & ~15;  // whole uint4 of flags per thread; stop[] is cudaMalloc-aligned
+  const int beg = min(n, tid * per), end = min(n, beg + per);
+  int n_stop = 0;
+  for (int r = beg; r < end; r += 16) {
+    const uint4 q = *reinterpret_cast<const uint4*>(b.stop + r);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int left = end - (r + 4 * k);
+      uint32_t x = w[k];
+      if (left < 4) x &= left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left)));
+      n_stop += __popc(x & 0x01010101u);
+    }
+  }
+  s_keep[tid] = (end - beg) - n_stop;
+  s_stop[tid] = n_stop;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int off = 1; off < kCompactThreads; off <<= 1) {
+    int a = 0, c = 0;
+    if (tid >= off) { a = s_keep[tid - off]; c = s_stop[tid - off]; }
+    __syncthreads();
+    s_keep[tid] += a;
+    s_stop[tid] += c;
+    __syncthreads();
+  }
+  const int total_keep = s_keep[kCompactThreads - 1];
+  int kpos = s_keep[tid] - ((end - beg) - n_stop);
+  int spos = total_keep + s_stop[tid] - n_stop;
+  const int* alive_cur = b.alive[cur];
+  int* alive_next = b.alive[cur ^ 1];
+  for (int r = beg; r < end; ++r) {
+    if (b.stop[r]) {
+      b.dest[r] = spos++;
+    } else {
+      b.dest[r] = kpos;
+      alive_next[kpos++] = alive_cur[r];
+    }
+  }
+  if (tid == 0) {
+    b.ctrl[cur ^ 1] = total_keep;
+    b.ctrl[2] = b.ctrl[2] + 1;
+    b.ctrl[3] = n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: state rows.  One warp per streamline.
+// ------------------------------------------------------------------------------------------
+constexpr int kStateWarps = 8;
+constexpr int kMaxStateLd = 640;   // floats staged per row (>= ld_state)
+constexpr int kMaxDirPts = 104;    // n_dirs + 1 points staged (n_dirs <= 103)
+
+struct TriAxis {  // one axis of one neighbourhood point
+  int i0, i1;     // clamped lower / upper lattice index
+  float d;        // unclamped fractional part
+};
+
+__device__ __forceinline__ TriAxis tri_axis(float c, int n) {
+  TriAxis t;
+  const float fl = floorf(c);
+  t.d = __fsub_rn(c, fl);
+  // clamp in float first: NaN -> -1 -> index 0, +-inf and huge values saturate safely
+  const float lo = fminf(fmaxf(fl, -1.f), (float)n);
+  const int i = (int)lo;
+  t.i0 = min(max(i, 0), n - 1);
+  t.i1 = min(max(i + 1, 0), n - 1);
+  return t;
+}
+
+// dwi_ml torch_trilinear_interpolation weights: W = B1^T . Q1 in float32 (polynomial form).
+__device__ __forceinline__ void tri_weights(float dx, float dy, float dz, float w[8]) {
+  const float xy = dx * dy, yz = dy * dz, xz = dx * dz, xyz = xy * dz;
+  w[0] = 1.f - dx - dy - dz + xy + yz + xz - xyz;   // 000
+  w[1] = dz - yz - xz + xyz;                        // 001
+  w[2] = dy - xy - yz + xyz;                        // 010
+  w[3] = yz - xyz;                                  // 011
+  w[4] = dx - xy - xz + xyz;                        // 100
+  w[5] = xz - xyz;                                  // 101
+  w[6] = xy - xyz;                                  // 110
+  w[7] = xyz;                                       // 111
+}
+
+// Builds one state row into s_row (shared, >= ld floats) for the streamline whose points start
+// at P and which has L points.  All 32 lanes of the warp participate.
+__device__ void build_state_row(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
+                                float* s_row, float* s_pts, int ld, int lane) {
+  const float* tip = P + (size_t)(L - 1) * 3;
+  const float tx = tip[0], ty = tip[1], tz = tip[2];
+  const float rad = (float)prm.step_vox;  // env.py:207-213, float32 neighbourhood vectors
+  const int CP4 = v.CP >> 2;
+  const int C = v.C;
+  const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
+
+  // lanes 0-15 take the x-low corners (000..011), lanes 16-31 the x-high corners (100..111)
+  const int half = lane >> 4;
+  const int cl = lane & 15;
+  for (int c4b = 0; c4b < CP4; c4b += 16) {   // warp-uniform trip count: shuffles below need all lanes
+    const bool active = c4b + cl < CP4;
+    const int c4 = active ? c4b + cl : 0;
+    float4 acc[7];
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+      // neighbourhood order env.py:210-213: 0, +x, +y, +z, -x, -y, -z
+      float cx = tx, cy = ty, cz = tz;
+      if (p == 1) cx = __fadd_rn(tx, rad);
+      if (p == 2) cy = __fadd_rn(ty, rad);
+      if (p == 3) cz = __fadd_rn(tz, rad);
+      if (p == 4) cx = __fadd_rn(tx, -rad);
+      if (p == 5) cy = __fadd_rn(ty, -rad);
+      if (p == 6) cz = __fadd_rn(tz, -rad);
+      const TriAxis X = tri_axis(cx, v.X), Y = tri_axis(cy, v.Y), Z = tri_axis(cz, v.Z);
+      float w[8];
+      tri_weights(X.d, Y.d, Z.d, w);
+      const int xi = half ? X.i1 : X.i0;
+      const size_t base_y0 = ((size_t)xi * v.Y + Y.i0) * v.Z;
+      const size_t base_y1 = ((size_t)xi * v.Y + Y.i1) * v.Z;
+      float4 a00 = make_float4(0.f, 0.f, 0.f, 0.f), a01 = a00, a10 = a00, a11 = a00;
+      if (active) {
+        a00 = __ldg(vol4 + (base_y0 + Z.i0) * CP4 + c4);
+        a01 = __ldg(vol4 + (base_y0 + Z.i1) * CP4 + c4);
+        a10 = __ldg(vol4 + (base_y1 + Z.i0) * CP4 + c4);
+        a11 = __ldg(vol4 + (base_y1 + Z.i1) * CP4 + c4);
+      }
+      const float w00 = half ? w[4] : w[0], w01 = half ? w[5] : w[1], w10 = half ? w[6] : w[2],
+                  w11 = half ? w[7] : w[3];
+      float4 s;
+      s.x = a00.x * w00 + a01.x * w01 + a10.x * w10 + a11.x * w11;
+      s.y = a00.y * w00 + a01.y * w01 + a10.y * w10 + a11.y * w11;
+      s.z = a00.z * w00 + a01.z * w01 + a10.z * w10 + a11.z * w11;
+      s.w = a00.w * w00 + a01.w * w01 + a10.w * w10 + a11.w * w11;
+      acc[p] = s;
+    }
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+      acc[p].x += __shfl_down_sync(0xffffffffu, acc[p].x, 16);
+      acc[p].y += __shfl_down_sync(0xffffffffu, acc[p].y, 16);
+      acc[p].z += __shfl_down_sync(0xffffffffu, acc[p].z, 16);
+      acc[p].w += __shfl_down_sync(0xffffffffu, acc[p].w, 16);
+    }
+    if (half == 0 && active) {
+#pragma unroll
+      for (int p = 0; p < 7; ++p) {
+        float* o = s_row + p * C + c4 * 4;
+        const int ch = c4 * 4;
+        if (ch + 0 < C) o[0] = acc[p].x;
+        if (ch + 1 < C) o[1] = acc[p].y;
+        if (ch + 2 < C) o[2] = acc[p].z;
+        if (ch + 3 < C) o[3] = acc[p].w;
+      }
+    }
+  }
+  // previous directions, newest first, zero padded (env.py:549-563)
+  const int S = 7 * C;
+  const int nd = prm.n_dirs;
+  const int npts = min(L, nd + 1);
+  const float* src = P + (size_t)(L - npts) * 3;
+  for (int j = lane; j < npts * 3; j += 32) s_pts[j] = src[j];
+  __syncwarp();
+  for (int j = lane; j < nd * 3; j += 32) {
+    const int k = j / 3, c = j - 3 * k;
+    float val = 0.f;
+    if (k < npts - 1) val = __fsub_rn(s_pts[(npts - 1 - k) * 3 + c], s_pts[(npts - 2 - k) * 3 + c]);
+    s_row[S + j] = val;
+  }
+  for (int j = S + nd * 3 + lane; j < ld; j += 32) s_row[j] = 0.f;
+  __syncwarp();
+}
+
+__device__ __forceinline__ void store_state_row(const float* s_row, float* dst, int ld, int lane) {
+  const float4* s4 = reinterpret_cast<const float4*>(s_row);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int j = lane; j < (ld >> 2); j += 32) d4[j] = s4[j];
+}
+
+__global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volume v, ttl_params prm,
+                                                                       ttl_batch b, int cur,
+                                                                       int count_slot) {
+  __shared__ __align__(16) float s_rows[kStateWarps][kMaxStateLd];
+  __shared__ float s_pts[kStateWarps][kMaxDirPts * 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kStateWarps + warp;
+  const int n_old = b.ctrl[count_slot];
+  if (r >= n_old) return;
+  if (b.stop[r] && !prm.state_stopped) return;
+  const int L = b.ctrl[2];
+  const int i = b.alive[cur][r];
+  const float* P = b.points + (size_t)i * b.max_pts * 3;
+  build_state_row(v, prm, P, L, s_rows[warp], s_pts[warp], b.ld_state, lane);
+  store_state_row(s_rows[warp], b.state[cur ^ 1] + (size_t)b.dest[r] * b.ld_state, b.ld_state, lane);
+}
+
+// reset: alive[0] = identity, dest = identity, state goes to state[0]
+__global__ void __launch_bounds__(kStateWarps * 32) reset_state_kernel(ttl_volume v, ttl_params prm,
+                                                                       ttl_batch b) {
+  __shared__ __align__(16) float s_rows[kStateWarps][kMaxStateLd];
+  __shared__ float s_pts[kStateWarps][kMaxDirPts * 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kStateWarps + warp;
+  if (r >= b.n) return;
+  const float* P = b.points + (size_t)r * b.max_pts * 3;
+  build_state_row(v, prm, P, 1, s_rows[warp], s_pts[warp], b.ld_state, lane);
+  store_state_row(s_rows[warp], b.state[0] + (size_t)r * b.ld_state, b.ld_state, lane);
+}
+
+// stand-alone _format_state for arbitrary streamlines [n][L][3]
+__global__ void __launch_bounds__(kStateWarps * 32) format_state_kernel(ttl_volume v, ttl_params prm,
+                                                                        const float* points, int n,
+                                                                        int L, float* out, int ld_out,
+                                                                        int ld_row) {
+  __shared__ __align__(16) float s_rows[kStateWarps][kMaxStateLd];
+  __shared__ float s_pts[kStateWarps][kMaxDirPts * 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kStateWarps + warp;
+  if (r >= n) return;
+  build_state_row(v, prm, points + (size_t)r * L * 3, L, s_rows[warp], s_pts[warp], ld_row, lane);
+  const int S = 7 * v.C + 3 * prm.n_dirs;
+  for (int j = lane; j < S; j += 32) out[(size_t)r * ld_out + j] = s_rows[warp][j];
+}
+
+__global__ void stopping_flags_kernel(ttl_volume v, ttl_params prm, const float* points, int n, int L,
+                                      int* out_flags, double* out_mask, float* out_reward) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* P = points + (size_t)r * L * 3;
+  double mv;
+  out_flags[r] = stopping_flags(v, prm, P, L, &mv);
+  if (out_mask) out_mask[r] = mv;
+  if (out_reward) {
+    float rew = 1.f;  // local_reward.py:46-48: fewer than 2 points -> ones
+    if (L >= 2 && v.peaks) rew = alignment_reward(v, P, L);
+    out_reward[r] = rew;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src,
+                                                          const int* __restrict__ dest, int n,
+                                                          int ld_src, float* __restrict__ out,
+                                                          int ld_out, int width) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* s = src + (size_t)dest[warp] * ld_src;
+  float* o = out + (size_t)warp * ld_out;
+  for (int j = lane; j < width; j += 32) o[j] = s[j];
+}
+
+__global__ void pad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                    long long n_voxels, int C, int CP) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n_voxels * CP;
+  if (t >= total) return;
+  const long long vx = t / CP;
+  const int c = (int)(t - vx * CP);
+  dst[t] = c < C ? src[vx * C + c] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// get_streamlines: effective lengths -> exclusive scan -> ragged copy
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) offsets_kernel(ttl_batch b, long long* offsets) {
+  __shared__ long long s_sum[1024];
+  const int n = b.n, tid = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int beg = min(n, tid * per), end = min(n, beg + per);
+  long long acc = 0;
+  for (int i = beg; i < end; ++i) {
+    const int cut = (b.flags[i] & (TTL_STOPPING_CURVATURE | TTL_STOPPING_MASK)) ? 1 : 0;
+    acc += b.lengths[i] - cut;
+  }
+  s_sum[tid] = acc;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    long long a = 0;
+    if (tid >= off) a = s_sum[tid - off];
+    __syncthreads();
+    s_sum[tid] += a;
+    __syncthreads();
+  }
+  long long pos = s_sum[tid] - acc;
+  for (int i = beg; i < end; ++i) {
+    offsets[i] = pos;
+    const int cut = (b.flags[i] & (TTL_STOPPING_CURVATURE | TTL_STOPPING_MASK)) ? 1 : 0;
+    pos += b.lengths[i] - cut;
+  }
+  if (tid == 1023) offsets[n] = s_sum[1023];
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(ttl_batch b, const long long* __restrict__ offsets,
+                                                   float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= b.n) return;
+  const long long o = offsets[warp];
+  const int len = (int)(offsets[warp + 1] - o);
+  const float* s = b.points + (size_t)warp * b.max_pts * 3;
+  float* d = out + o * 3;
+  for (int j = lane; j < len * 3; j += 32) d[j] = s[j];
+}
+
+int check_common(const ttl_volume* vol, const ttl_params* prm) {
+  if (!vol || !prm) return TTL_ERR_BAD_ARG;
+  if ((vol->CP & 3) || vol->CP < vol->C || vol->CP > 128) return TTL_ERR_UNSUPPORTED;
+  if (prm->n_dirs + 1 > kMaxDirPts) return TTL_ERR_UNSUPPORTED;
+  if (7 * vol->C + 3 * prm->n_dirs > kMaxStateLd) return TTL_ERR_UNSUPPORTED;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ttl_abi_version(void) { return TTL_ABI_VERSION; }
+int64_t ttl_launch_count(void) { return (int64_t)g_ttl_launches.load(); }
+
+int ttl_pad_channels(const float* src, float* dst, int64_t n_voxels, int32_t C, int32_t CP,
+                     void* stream) {
+  if (!src || !dst || CP < C) return TTL_ERR_BAD_ARG;
+  const long long total = (long long)n_voxels * CP;
+  pad_channels_kernel<<<ttl_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n_voxels, C, CP);
+  TTL_LAUNCHED();
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b,
+                  const double* seeds, void* stream) {
+  int rc = check_common(vol, prm);
+  if (rc) return rc;
+  if (!b || !seeds || b->n > b->capacity || b->ld_state > kMaxStateLd || (b->ld_state & 3) ||
+      b->ld_state < 7 * vol->C + 3 * prm->n_dirs)
+    return TTL_ERR_BAD_ARG;
+  if (b->n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  reset_kernel<<<ttl_div_up(b->n, 256), 256, 0, s>>>(*b, seeds);
+  TTL_LAUNCHED();
+  reset_state_kernel<<<ttl_div_up(b->n, kStateWarps), kStateWarps * 32, 0, s>>>(*vol, *prm, *b);
+  TTL_LAUNCHED();
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                 const float* actions, int32_t lda, const double* noise, int32_t n_upper,
+                 void* stream) {
+  int rc = check_common(vol, prm);
+  if (rc) return rc;
+  if (!b || !actions || lda < 3 || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
+  if (prm->compute_reward && !vol->peaks) return TTL_ERR_BAD_ARG;
+  if (n_upper <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  propagate_stop_kernel<<<ttl_div_up(n_upper, 128), 128, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise);
+  TTL_LAUNCHED();
+  compact_kernel<<<1, kCompactThreads, 0, s>>>(*b, cur);
+  TTL_LAUNCHED();
+  build_state_kernel<<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, 0, s>>>(*vol, *prm, *b, cur, cur);
+  TTL_LAUNCHED();
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_env_gather_step_state(const ttl_batch* b, int32_t cur, int32_t n_rows, float* out,
+                              int32_t ld_out, void* stream) {
+  if (!b || !out) return TTL_ERR_BAD_ARG;
+  if (n_rows <= 0) return 0;
+  gather_rows_kernel<<<ttl_div_up((long long)n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      b->state[cur ^ 1], b->dest, n_rows, b->ld_state, out, ld_out, b->state_size);
+  TTL_LAUNCHED();
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_format_state(const ttl_volume* vol, const ttl_params* prm, const float* points, int32_t n,
+                     int32_t L, float* out, int32_t ld_out, void* stream) {
+  int rc = check_common(vol, prm);
+  if (rc) return rc;
+  if (!points || !out || L < 1) return TTL_ERR_BAD_ARG;
+  if (n <= 0) return 0;
+  const int S = 7 * vol->C + 3 * prm->n_dirs;
+  const int ld_row = (S + 3) & ~3;
+  format_state_kernel<<<ttl_div_up(n, kStateWarps), kStateWarps * 32, 0, (cudaStream_t)stream>>>(
+      *vol, *prm, points, n, L, out, ld_out, ld_row);
+  TTL_LAUNCHED();
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_stopping_flags(const ttl_volume* vol, const ttl_params* prm, const float* points, int32_t n,
+                       int32_t L, int32_t* out_flags, double* out_mask_value, float* out_reward,
+                       void* stream) {
+  int rc = check_common(vol, prm);
+  if (rc) return rc;
+  if (!points || !out_flags || L < 1) return TTL_ERR_BAD_ARG;
+  if (n <= 0) return 0;
+  stopping_flags_kernel<<<ttl_div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(
+      *vol, *prm, points, n, L, out_flags, out_mask_value, out_reward);
+  TTL_LAUNCHED();
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_streamline_offsets(const ttl_batch* b, int64_t* offsets, void* stream) {
+  if (!b || !offsets) return TTL_ERR_BAD_ARG;
+  offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*b, (long long*)offsets);
+  TTL_LAUNCHED();
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_pack_streamlines(const ttl_batch* b, const int64_t* offsets, float* out_points, void* stream) {
+  if (!b || !offsets || !out_points) return TTL_ERR_BAD_ARG;
+  if (b->n == 0) return 0;
+  pack_kernel<<<ttl_div_up((long long)b->n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      *b, (const long long*)offsets, out_points);
+  TTL_LAUNCHED();
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+}  // extern "C"

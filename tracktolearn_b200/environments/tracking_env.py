@@ -1,0 +1,236 @@
+"""TrackingEnvironment on the device (reference: environments/tracking_env.py:13-294).
+
+``reset / nreset / step / harvest / get_streamlines`` keep the reference's signatures and
+return types (state: torch tensor on the env's device; reward / dones / continue_idx: numpy).
+Underneath, everything -- streamline buffer, flags, alive list, state rows -- lives in HBM and
+one ``step`` is three kernel launches through the C ABI (``ttl_env_step``).
+
+Two ways to drive it:
+  * the reference protocol: ``step(actions) -> (state, reward, dones, info)`` then
+    ``harvest() -> (state, not_stopping)``; host arrays are produced on every call, which
+    costs a few small D2H copies per step (what the parity tests use);
+  * the device protocol used by ``Tracker``/``validation_episode`` in this package:
+    ``step_device(actions)`` + ``harvest_device()`` enqueue kernels only and never touch the
+    host; ``n_alive()`` reads the alive count back when the loop wants to know.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from tracktolearn_b200 import _lib
+from tracktolearn_b200.environments.env import BaseEnv
+from tracktolearn_b200.tracking.tractogram import Tractogram
+
+
+class _BatchBuffers(object):
+    """Device buffers of one batch of streamlines (``ttl_batch`` in include/ttl_b200.h)."""
+
+    def __init__(self, capacity, max_pts, state_size, device):
+        self.capacity = capacity
+        self.max_pts = max_pts
+        self.state_size = state_size
+        self.ld_state = (state_size + 3) // 4 * 4
+        i32 = dict(dtype=torch.int32, device=device)
+        pad = capacity + 16          # the compaction kernel reads stop[] 16 bytes at a time
+        self.points = torch.zeros((capacity, max_pts, 3), dtype=torch.float32, device=device)
+        self.flags = torch.zeros((pad,), **i32)
+        self.lengths = torch.zeros((pad,), **i32)
+        self.dones = torch.zeros((pad,), dtype=torch.uint8, device=device)
+        self.alive = [torch.zeros((pad,), **i32), torch.zeros((pad,), **i32)]
+        self.ctrl = torch.zeros((8,), **i32)
+        self.stop = torch.zeros((pad,), dtype=torch.uint8, device=device)
+        self.dest = torch.zeros((pad,), **i32)
+        self.step_flags = torch.zeros((pad,), **i32)
+        self.reward = torch.zeros((pad,), dtype=torch.float32, device=device)
+        self.state = [torch.zeros((capacity, self.ld_state), dtype=torch.float32, device=device),
+                      torch.zeros((capacity, self.ld_state), dtype=torch.float32, device=device)]
+        self.ctrl_host = torch.zeros((8,), dtype=torch.int32).pin_memory()
+
+    def as_struct(self, n):
+        b = _lib.Batch(n=n, capacity=self.capacity, max_pts=self.max_pts, ld_state=self.ld_state,
+                       state_size=self.state_size, points=self.points.data_ptr(),
+                       flags=self.flags.data_ptr(), lengths=self.lengths.data_ptr(),
+                       dones=self.dones.data_ptr(), ctrl=self.ctrl.data_ptr(),
+                       stop=self.stop.data_ptr(), dest=self.dest.data_ptr(),
+                       step_flags=self.step_flags.data_ptr(), reward=self.reward.data_ptr())
+        b.alive[0] = self.alive[0].data_ptr()
+        b.alive[1] = self.alive[1].data_ptr()
+        b.state[0] = self.state[0].data_ptr()
+        b.state[1] = self.state[1].data_ptr()
+        return b
+
+
+class TrackingEnvironment(BaseEnv):
+    """Reference: environments/tracking_env.py:13."""
+
+    # ------------------------------------------------------------------------------ reset
+    def _ensure_buffers(self, n):
+        need_pts = self.max_nb_steps + 1
+        S = self.get_state_size()
+        bb = self._batch
+        if bb is None or bb.capacity < n or bb.max_pts != need_pts or bb.state_size != S:
+            cap = max(n, bb.capacity if bb is not None else 0)
+            self._batch = None
+            bb = _BatchBuffers(cap, need_pts, S, self.device)
+            self._batch = bb
+        return bb
+
+    def _start(self, initial_points):
+        self.initial_points = initial_points
+        N = initial_points.shape[0]
+        bb = self._ensure_buffers(max(N, 1))
+        self._n = N
+        self._b = bb.as_struct(N)
+        self._cur = 0
+        self.length = 1
+        self._n_alive_host = N          # host mirror of the alive count (upper bound between syncs)
+        self._n_prev = N
+        self._continue_idx_cache = np.arange(N)
+        self._pending_harvest = False
+        seeds_dev = torch.from_numpy(np.ascontiguousarray(initial_points, dtype=np.float64)).to(
+            self.device, non_blocking=False)
+        _lib.check(self._lib.ttl_env_reset(ctypes.byref(self._volume), ctypes.byref(self._params),
+                                           ctypes.byref(self._b), _lib.ptr(seeds_dev),
+                                           _lib.stream_ptr(self.device)), 'ttl_env_reset')
+        self._seeds_dev = seeds_dev   # keep alive until the kernel ran
+        return self._state_view(0, N)
+
+    def _state_view(self, which, n):
+        return self._batch.state[which][:n, :self._batch.state_size]
+
+    def reset(self, start, end):
+        """Reference: tracking_env.py:91-133."""
+        return self._start(self.seeds[start:end])
+
+    def nreset(self, n_seeds):
+        """Reference: tracking_env.py:47-89."""
+        replace = n_seeds > len(self.seeds)
+        seeds = np.random.choice(np.arange(len(self.seeds)), size=n_seeds, replace=replace)
+        return self._start(self.seeds[seeds])
+
+    # ------------------------------------------------------------------- device protocol
+    def step_device(self, actions, noise=None):
+        """Enqueue one step for the alive rows.  ``actions``: CUDA float32 tensor
+        [>= n_alive, >= 3] (row stride taken from the tensor).  No host synchronisation."""
+        if self._pending_harvest:
+            raise RuntimeError('step() called twice without harvest()')
+        if actions.dtype != torch.float32 or actions.device != self.device or actions.stride(-1) != 1:
+            actions = actions.to(self.device, dtype=torch.float32).contiguous()
+        lda = actions.stride(0) if actions.dim() == 2 and actions.shape[0] > 1 else actions.shape[-1]
+        _lib.check(self._lib.ttl_env_step(
+            ctypes.byref(self._volume), ctypes.byref(self._params), ctypes.byref(self._b), self._cur,
+            _lib.ptr(actions), int(lda), _lib.ptr(noise), int(self._n_alive_host),
+            _lib.stream_ptr(self.device)), 'ttl_env_step')
+        self._keep = (actions, noise)
+        self.length += 1
+        self._pending_harvest = True
+
+    def harvest_device(self):
+        """The flip that makes the compacted alive list / state rows current (harvest)."""
+        if self._pending_harvest:
+            self._cur ^= 1
+            self._pending_harvest = False
+            self._continue_idx_cache = None
+        return self._batch.state[self._cur]
+
+    def n_alive(self):
+        """Alive count after the last harvest (one 32-byte D2H copy + stream sync)."""
+        bb = self._batch
+        bb.ctrl_host.copy_(bb.ctrl, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._n_alive_host = int(bb.ctrl_host[self._cur])
+        return self._n_alive_host
+
+    def current_state(self):
+        """State rows of the alive set, [n_alive_upper_bound, state_size] view (no sync)."""
+        return self._state_view(self._cur, self._n_alive_host)
+
+    def alive_count_tensor(self):
+        """Device int32 tensor holding the alive count of the current list."""
+        return self._batch.ctrl[self._cur:self._cur + 1]
+
+    # ---------------------------------------------------------------- reference protocol
+    @property
+    def continue_idx(self):
+        if self._continue_idx_cache is None:
+            n = self._n_alive_host
+            self._continue_idx_cache = self._batch.alive[self._cur][:n].cpu().numpy().astype(np.int64)
+        return self._continue_idx_cache
+
+    def _host_actions(self, actions):
+        if isinstance(actions, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32)).to(self.device)
+        return actions
+
+    def step(self, actions):
+        """Reference: tracking_env.py:135-221."""
+        return self._step(self._host_actions(actions), None)
+
+    def _step(self, actions, noise):
+        A = self._n_alive_host
+        ci = self.continue_idx
+        self.step_device(actions, noise)
+        bb = self._batch
+        S = bb.state_size
+        state = torch.empty((A, S), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.ttl_env_gather_step_state(ctypes.byref(self._b), self._cur, A,
+                                                       _lib.ptr(state), S, _lib.stream_ptr(self.device)),
+                   'ttl_env_gather_step_state')
+        stop = bb.stop[:A].cpu().numpy().astype(bool)
+        self.not_stopping = np.logical_not(stop)
+        self.new_continue_idx, self.stopping_idx = ci[~stop], ci[stop]
+        reward_info = {}
+        if self.compute_reward:
+            reward = bb.reward[:A].cpu().numpy().astype(np.float64)
+            reward_info = {'peaks_reward': float(np.mean(reward)) if A else 0.0, 'oracle_reward': 0.0}
+        else:
+            reward = np.zeros(self._n)          # the reference's shape quirk (tracking_env.py:204)
+        self._n_prev = A
+        return state, reward, stop, {'continue_idx': ci, 'reward_info': reward_info}
+
+    def harvest(self):
+        """Reference: tracking_env.py:223-245."""
+        self.harvest_device()
+        n = self.n_alive()
+        self._continue_idx_cache = getattr(self, 'new_continue_idx', None)
+        return self._state_view(self._cur, n), self.not_stopping
+
+    # --------------------------------------------------------------------- results
+    @property
+    def flags(self):
+        return self._batch.flags[:self._n].cpu().numpy().astype(int)
+
+    @property
+    def lengths(self):
+        return self._batch.lengths[:self._n].cpu().numpy()
+
+    @property
+    def dones(self):
+        return self._batch.dones[:self._n].cpu().numpy().astype(bool)
+
+    @property
+    def streamlines(self):
+        """[N, max_nb_steps+1, 3] float32 host copy of the streamline buffer."""
+        return self._batch.points[:self._n].cpu().numpy()
+
+    def get_streamlines_device(self):
+        """Packed streamlines on the device: (points [sum(L),3] fp32, offsets [N+1] int64)."""
+        N = self._n
+        offsets = torch.empty((N + 1,), dtype=torch.int64, device=self.device)
+        sp = _lib.stream_ptr(self.device)
+        _lib.check(self._lib.ttl_streamline_offsets(ctypes.byref(self._b), _lib.ptr(offsets), sp),
+                   'ttl_streamline_offsets')
+        total = int(offsets[N].item())
+        pts = torch.empty((max(total, 1), 3), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.ttl_pack_streamlines(ctypes.byref(self._b), _lib.ptr(offsets), _lib.ptr(pts), sp),
+                   'ttl_pack_streamlines')
+        return pts[:total], offsets
+
+    def get_streamlines(self):
+        """Reference: tracking_env.py:247-294.  The last point is dropped when the CURVATURE or
+        MASK flag stopped the streamline."""
+        pts, offsets = self.get_streamlines_device()
+        return Tractogram(data=pts.cpu().numpy(), offsets=offsets.cpu().numpy(),
+                          data_per_streamline={'seeds': np.asarray(self.initial_points),
+                                               'flags': self.flags})
