@@ -62,27 +62,33 @@ typedef struct ttl_params {
   int32_t compute_reward;   /* 1: alignment reward (reward.py:46-79, local_reward.py:29-107) */
   int32_t state_stopped;    /* 1: also build the state rows of streamlines that stop this step
                                (the reference does, tracking_env.py:214-215); 0: skip them */
+  int32_t refill;           /* 1: streaming tracker -- slots freed by stopped streamlines are given
+                               to the next unseeded rows of the batch in the same step (results per
+                               seed are unchanged at prob = 0; excludes state_stopped) */
 } ttl_params;
 
 /* Per-batch mutable state in HBM (tracking_env.py:91-133 allocates the equivalent). */
 typedef struct ttl_batch {
-  int32_t n;               /* streamlines in this batch */
+  int32_t n;               /* streamlines (seeds) in this batch */
+  int32_t n_slots;         /* streamlines tracked at once (n_actor); == n without refill */
   int32_t capacity;        /* rows allocated in every per-row buffer */
   int32_t max_pts;         /* points per row = max_nb_steps + 1 */
   int32_t ld_state;        /* floats per state row (>= state size, multiple of 4) */
   int32_t state_size;      /* 7*C + 3*n_dirs (615) */
   float* points;           /* [capacity][max_pts][3] fp32 streamline coordinates (voxel space) */
   int32_t* flags;          /* [capacity] StoppingFlags per global row */
-  int32_t* lengths;        /* [capacity] points per global row */
+  int32_t* lengths;        /* [capacity] points per global row, set when the row stops */
+  int32_t* npts;           /* [capacity] running point count of every row (1 after reset) */
   uint8_t* dones;          /* [capacity] */
   int32_t* alive[2];       /* ping-pong lists of alive global rows, ascending */
   int32_t* ctrl;           /* [8] device ints: [0],[1] alive count of alive[0],alive[1];
-                              [2] L = points so far in every alive row */
-  uint8_t* stop;           /* [capacity] per rank (position in the alive list): stopped this step */
-  int32_t* dest;           /* [capacity] per rank: row of state[next] that holds its new state */
-  int32_t* step_flags;     /* [capacity] per rank: flags raised this step */
-  float* reward;           /* [capacity] per rank */
-  float* state[2];         /* ping-pong [capacity][ld_state] fp32 state rows.  state[cur] rows
+                              [2] steps taken; [3] alive count before the last step;
+                              [4],[5] int64 streamline-steps so far; [6] next unseeded row */
+  uint8_t* stop;           /* [n_slots+16] per rank (position in the alive list): stopped this step */
+  int32_t* dest;           /* [n_slots] per rank: row of state[next] that holds its new state */
+  int32_t* step_flags;     /* [n_slots] per rank: flags raised this step */
+  float* reward;           /* [n_slots] per rank */
+  float* state[2];         /* ping-pong [n_slots][ld_state] fp32 state rows.  state[cur] rows
                               [0, n_alive) are the states of alive[cur] in order. */
 } ttl_batch;
 
@@ -96,8 +102,8 @@ int ttl_pad_channels(const float* src, float* dst, int64_t n_voxels, int32_t C, 
 /* ---- TrackingEnvironment ------------------------------------------------------------------ */
 
 /* TrackingEnvironment.reset / nreset (tracking_env.py:47-133): seeds [n][3] float64 voxel
- * coordinates -> first points, zeroed flags, lengths 1, alive = 0..n-1, L = 1 and the initial
- * state rows in state[0].  After this call cur = 0. */
+ * coordinates -> first points, zeroed flags, lengths 1, alive = 0..min(n,n_slots)-1 and the
+ * initial state rows in state[0].  After this call cur = 0. */
 int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b,
                   const double* seeds, void* stream);
 
@@ -106,7 +112,8 @@ int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch*
  * `noise` [n_alive][3] f64 added first.  Normalise+scale (env.py:493-502), first-step flip,
  * grow, stopping flags (env.py:567-603, utils.py:127-173, stopping_criteria.py:38-82), reward,
  * ordered compaction into alive[cur^1] / ctrl[cur^1], new state rows into state[cur^1]
- * (survivors first, in order; then stopped rows if prm->state_stopped), L += 1.
+ * (survivors first, in order; then refilled rows if prm->refill, or stopped rows if
+ * prm->state_stopped).
  * `n_upper` >= current alive count bounds the launch (the kernels read the true count from
  * ctrl[cur] on the device, so no host sync is needed between steps).
  * The caller flips cur afterwards: that flip is TrackingEnvironment.harvest (:223-245). */
@@ -211,6 +218,11 @@ int ttl_oracle_forward(const ttl_oracle_weights* w, const float* dirs, int32_t n
 int ttl_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t ttl_launch_count(void);
+/* Per-kernel device timing: when enabled every launch is bracketed by CUDA events on its
+ * stream; ttl_prof_report waits for them, writes {"kernel": [launches, total_ms], ...} (JSON)
+ * into buf_host and clears the record.  Returns the bytes the full report needs. */
+void ttl_prof_enable(int32_t on);
+int32_t ttl_prof_report(char* buf_host, int32_t buflen);
 
 #ifdef __cplusplus
 }

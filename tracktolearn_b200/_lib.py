@@ -23,13 +23,13 @@ class Volume(ctypes.Structure):
 class Params(ctypes.Structure):
     _fields_ = [('step_vox', c_f64), ('mask_threshold', c_f64), ('alignment_weighting', c_f64),
                 ('theta_rad', c_f32), ('max_nb_steps', c_i32), ('n_dirs', c_i32), ('dir_f64', c_i32),
-                ('compute_reward', c_i32), ('state_stopped', c_i32)]
+                ('compute_reward', c_i32), ('state_stopped', c_i32), ('refill', c_i32)]
 
 
 class Batch(ctypes.Structure):
-    _fields_ = [('n', c_i32), ('capacity', c_i32), ('max_pts', c_i32), ('ld_state', c_i32),
+    _fields_ = [('n', c_i32), ('n_slots', c_i32), ('capacity', c_i32), ('max_pts', c_i32), ('ld_state', c_i32),
                 ('state_size', c_i32), ('points', c_vp), ('flags', c_vp), ('lengths', c_vp),
-                ('dones', c_vp), ('alive', c_vp * 2), ('ctrl', c_vp), ('stop', c_vp), ('dest', c_vp),
+                ('npts', c_vp), ('dones', c_vp), ('alive', c_vp * 2), ('ctrl', c_vp), ('stop', c_vp), ('dest', c_vp),
                 ('step_flags', c_vp), ('reward', c_vp), ('state', c_vp * 2)]
 
 
@@ -51,6 +51,8 @@ P = ctypes.POINTER
 SIGNATURES = {
     'ttl_abi_version': (c_i32, []),
     'ttl_launch_count': (c_i64, []),
+    'ttl_prof_enable': (None, [c_i32]),
+    'ttl_prof_report': (c_i32, [ctypes.c_char_p, c_i32]),
     'ttl_pad_channels': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
     'ttl_env_reset': (c_i32, [P(Volume), P(Params), P(Batch), c_vp, c_vp]),
     'ttl_env_step': (c_i32, [P(Volume), P(Params), P(Batch), c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]),
@@ -95,6 +97,15 @@ def load():
 def check(rc, what):
     if rc != 0:
         raise TTLError('%s failed with code %d' % (what, rc))
+
+
+def prof_report():
+    """Per-kernel {name: (launches, total_ms)} since the last report (see ttl_prof_enable)."""
+    import json
+    lib = load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.ttl_prof_report(buf, len(buf))
+    return {k: (int(v[0]), float(v[1])) for k, v in json.loads(buf.value.decode()).items()}
 
 
 def ptr(t):

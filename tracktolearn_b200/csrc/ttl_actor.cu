@@ -482,9 +482,8 @@ int launch_dense_bf16(const CUtensorMap& ta, const CUtensorMap& tb, const float*
   const int tiles = ttl_div_up(m_max, BM) * ttl_div_up(n_pad, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid <= 0) return 0;
-  dense_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ta, tb, bias, C, ldc, m_dev, m_max, n_pad,
-                                                         k_pad, relu);
-  TTL_LAUNCHED();
+  TTL_LAUNCH("dense_bf16_kernel", s, dense_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ta, tb, bias, C, ldc, m_dev, m_max, n_pad,
+                                                         k_pad, relu));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -574,12 +573,10 @@ int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int3
     p->wq[i] = reinterpret_cast<__nv_bfloat16*>(ws + L.off_w[i]);
     p->bq[i] = reinterpret_cast<float*>(ws + L.off_b[i]);
     const long long tot = (long long)L.n_pad[i] * L.k_pad[i];
-    pack_weight_bf16_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(w->w[i], p->wq[i], w->out_dim[i],
-                                                                w->in_dim[i], L.n_pad[i], L.k_pad[i]);
-    TTL_LAUNCHED();
+    TTL_LAUNCH("pack_weight_bf16_kernel", s, pack_weight_bf16_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(w->w[i], p->wq[i], w->out_dim[i],
+                                                                w->in_dim[i], L.n_pad[i], L.k_pad[i]));
     const int bp = round_up(L.n_pad[i], BN);
-    pack_bias_kernel<<<ttl_div_up(bp, 256), 256, 0, s>>>(w->b[i], p->bq[i], w->out_dim[i], bp);
-    TTL_LAUNCHED();
+    TTL_LAUNCH("pack_bias_kernel", s, pack_bias_kernel<<<ttl_div_up(bp, 256), 256, 0, s>>>(w->b[i], p->bq[i], w->out_dim[i], bp));
     rc = make_tmap(&p->map_w[i], p->wq[i], (uint64_t)L.n_pad[i], (uint64_t)L.k_pad[i], BN);
     if (rc) { delete p; return rc; }
     // A operand of layer i lives in act[i & 1] with row pitch k_pad[i]
@@ -614,19 +611,17 @@ int ttl_actor_forward(ttl_actor_plan* p, const float* state, int32_t ld_state, c
       head_attr = true;
     }
     const long long tot = (long long)n_rows_max * (p->k_pad[0] >> 3);
-    pack_state_bf16_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(state, ld_state, w.in_dim[0], n_rows_dev,
-                                                              n_rows_max, p->act[0], p->k_pad[0]);
-    TTL_LAUNCHED();
+    TTL_LAUNCH("pack_state_bf16_kernel", s, pack_state_bf16_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(state, ld_state, w.in_dim[0], n_rows_dev,
+                                                              n_rows_max, p->act[0], p->k_pad[0]));
     for (int i = 0; i < nl - 1; ++i) {
       // layer i: act[i&1] (pitch k_pad[i]) -> act[(i+1)&1] (pitch k_pad[i+1] = n_pad[i])
       int rc = launch_dense_bf16(p->map_a[i], p->map_w[i], p->bq[i], p->act[(i + 1) & 1], p->n_pad[i],
                                  n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1, s);
       if (rc) return rc;
     }
-    head_kernel<__nv_bfloat16><<<head_grid, 256, head_smem, s>>>(
+    TTL_LAUNCH("head_kernel_bf16", s, head_kernel<__nv_bfloat16><<<head_grid, 256, head_smem, s>>>(
         p->act[(nl - 1) & 1], p->k_pad[nl - 1], k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
-        n_rows_max, probabilistic, eps, action, logp, pre);
-    TTL_LAUNCHED();
+        n_rows_max, probabilistic, eps, action, logp, pre));
     TTL_CHECK_LAST();
     return 0;
   }
@@ -653,17 +648,15 @@ int ttl_actor_forward(ttl_actor_plan* p, const float* state, int32_t ld_state, c
       for (int i = 0; i < nl - 1; ++i) {
         float* o = p->f32[i & 1];
         dim3 grid(ttl_div_up(w.out_dim[i], SG_T), ttl_div_up(m, SG_T));
-        dense_f32_kernel<<<grid, 256, 0, s>>>(in, ld_in, w.w[i], w.b[i], o, p->max_width, m, w.out_dim[i],
-                                              w.in_dim[i], 1);
-        TTL_LAUNCHED();
+        TTL_LAUNCH("dense_f32_kernel", s, dense_f32_kernel<<<grid, 256, 0, s>>>(in, ld_in, w.w[i], w.b[i], o, p->max_width, m, w.out_dim[i],
+                                              w.in_dim[i], 1));
         in = o;
         ld_in = p->max_width;
       }
-      head_kernel<float><<<head_grid, 256, head_smem, s>>>(
+      TTL_LAUNCH("head_kernel_f32", s, head_kernel<float><<<head_grid, 256, head_smem, s>>>(
           in, ld_in, k_last, w.w[nl - 1], w.b[nl - 1], n_out, nullptr, m, probabilistic,
           eps ? eps + (size_t)r0 * A : nullptr, action + (size_t)r0 * A, logp ? logp + r0 : nullptr,
-          pre ? pre + (size_t)r0 * n_out : nullptr);
-      TTL_LAUNCHED();
+          pre ? pre + (size_t)r0 * n_out : nullptr));
     }
     TTL_CHECK_LAST();
     return 0;

@@ -15,6 +15,20 @@ extern std::atomic<long long> g_ttl_launches;
 
 #define TTL_LAUNCHED() (g_ttl_launches.fetch_add(1, std::memory_order_relaxed))
 
+// Optional per-kernel timing with CUDA events on the launching stream (ttl_prof_enable).
+void ttl_prof_begin(const char* name, cudaStream_t s);
+void ttl_prof_end(cudaStream_t s);
+
+// Every kernel launch of the library goes through this macro: it counts the launch and, when
+// profiling is on, brackets it with a pair of events.
+#define TTL_LAUNCH(name, stream, ...)    \
+  do {                                   \
+    ttl_prof_begin(name, stream);        \
+    __VA_ARGS__;                         \
+    ttl_prof_end(stream);                \
+    TTL_LAUNCHED();                      \
+  } while (0)
+
 #define TTL_CHECK_LAST()                     \
   do {                                       \
     cudaError_t e__ = cudaGetLastError();    \

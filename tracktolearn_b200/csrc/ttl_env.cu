@@ -188,10 +188,22 @@ __device__ float alignment_reward(const ttl_volume& v, const float* P, int L) {
 // ------------------------------------------------------------------------------------------
 __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n0 = min(b.n, b.n_slots);
   if (i == 0) {
-    b.ctrl[0] = b.n;
+    b.ctrl[0] = n0;
     b.ctrl[1] = 0;
-    b.ctrl[2] = 1;
+    b.ctrl[2] = 0;
+    b.ctrl[3] = 0;
+    b.ctrl[4] = 0;
+    b.ctrl[5] = 0;
+    b.ctrl[6] = n0;  // next unseeded row
+  }
+  if (i < b.n_slots) {
+    b.dest[i] = i;
+    b.stop[i] = 0;
+    b.step_flags[i] = 0;
+    b.reward[i] = 0.f;
+    if (i < n0) b.alive[0][i] = i;
   }
   if (i >= b.n) return;
   float* P = b.points + (size_t)i * b.max_pts * 3;
@@ -200,12 +212,8 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
   P[2] = (float)seeds[3 * i + 2];
   b.flags[i] = 0;
   b.lengths[i] = 1;
+  b.npts[i] = 1;
   b.dones[i] = 0;
-  b.alive[0][i] = i;
-  b.dest[i] = i;
-  b.stop[i] = 0;
-  b.step_flags[i] = 0;
-  b.reward[i] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -217,8 +225,8 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_alive = b.ctrl[cur];
   if (r >= n_alive) return;
-  const int L = b.ctrl[2];  // points so far
   const int i = b.alive[cur][r];
+  const int L = b.npts[i];  // points so far in this row
   float* P = b.points + (size_t)i * b.max_pts * 3;
   const float px = P[(L - 1) * 3 + 0], py = P[(L - 1) * 3 + 1], pz = P[(L - 1) * 3 + 2];
   const float ax = actions[(size_t)r * lda + 0], ay = actions[(size_t)r * lda + 1],
@@ -265,6 +273,7 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
   P[L * 3 + 0] = qx; P[L * 3 + 1] = qy; P[L * 3 + 2] = qz;
   const int Ln = L + 1;
   const int f = stopping_flags(v, prm, P, Ln, nullptr);
+  b.npts[i] = Ln;
   b.step_flags[r] = f;
   b.stop[r] = f != 0;
   if (f) {
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
 // ------------------------------------------------------------------------------------------
 constexpr int kCompactThreads = 1024;
 
-__global__ void __launch_bounds__(kCompactThreads) compact_kernel(ttl_batch b, int cur) {
+__global__ void __launch_bounds__(kCompactThreads) compact_kernel(ttl_batch b, int cur, int refill) {
   __shared__ int s_keep[kCompactThreads];
   __shared__ int s_stop[kCompactThreads];
   const int n = b.ctrl[cur];
@@ -330,10 +339,23 @@ __global__ void __launch_bounds__(kCompactThreads) compact_kernel(ttl_batch b, i
       alive_next[kpos++] = alive_cur[r];
     }
   }
+  // streaming refill: freed slots take the next unseeded rows (their state rows are built
+  // by build_state_kernel with L = 1)
+  int n_new = 0;
+  const int cursor = b.ctrl[6];
+  if (refill) {
+    n_new = min(b.n_slots - total_keep, b.n - cursor);
+    n_new = max(n_new, 0);
+    for (int j = tid; j < n_new; j += kCompactThreads) alive_next[total_keep + j] = cursor + j;
+  }
+  __syncthreads();
   if (tid == 0) {
-    b.ctrl[cur ^ 1] = total_keep;
+    b.ctrl[cur ^ 1] = total_keep + n_new;
     b.ctrl[2] = b.ctrl[2] + 1;
     b.ctrl[3] = n;
+    b.ctrl[6] = cursor + n_new;
+    long long* total = reinterpret_cast<long long*>(b.ctrl + 4);
+    *total += n;
   }
 }
 
@@ -466,21 +488,30 @@ __device__ __forceinline__ void store_state_row(const float* s_row, float* dst, 
   for (int j = lane; j < (ld >> 2); j += 32) d4[j] = s4[j];
 }
 
+// Warps [0, u_new) build the rows of the NEW alive list (survivors in order, then refilled
+// rows): rank r' -> state[next][r'].  Warps [u_new, u_new + u_old) exist only in parity mode
+// (state_stopped) and build the rows of streamlines that stopped this step at dest[r].
 __global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volume v, ttl_params prm,
-                                                                       ttl_batch b, int cur,
-                                                                       int count_slot) {
+                                                                       ttl_batch b, int cur, int u_new) {
   __shared__ __align__(16) float s_rows[kStateWarps][kMaxStateLd];
   __shared__ float s_pts[kStateWarps][kMaxDirPts * 3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * kStateWarps + warp;
-  const int n_old = b.ctrl[count_slot];
-  if (r >= n_old) return;
-  if (b.stop[r] && !prm.state_stopped) return;
-  const int L = b.ctrl[2];
-  const int i = b.alive[cur][r];
-  const float* P = b.points + (size_t)i * b.max_pts * 3;
+  const int w = blockIdx.x * kStateWarps + warp;
+  int row, dst;
+  if (w < u_new) {
+    if (w >= b.ctrl[cur ^ 1]) return;
+    row = b.alive[cur ^ 1][w];
+    dst = w;
+  } else {
+    const int r = w - u_new;
+    if (r >= b.ctrl[cur] || !b.stop[r]) return;
+    row = b.alive[cur][r];
+    dst = b.dest[r];
+  }
+  const int L = b.npts[row];
+  const float* P = b.points + (size_t)row * b.max_pts * 3;
   build_state_row(v, prm, P, L, s_rows[warp], s_pts[warp], b.ld_state, lane);
-  store_state_row(s_rows[warp], b.state[cur ^ 1] + (size_t)b.dest[r] * b.ld_state, b.ld_state, lane);
+  store_state_row(s_rows[warp], b.state[cur ^ 1] + (size_t)dst * b.ld_state, b.ld_state, lane);
 }
 
 // reset: alive[0] = identity, dest = identity, state goes to state[0]
@@ -490,7 +521,7 @@ __global__ void __launch_bounds__(kStateWarps * 32) reset_state_kernel(ttl_volum
   __shared__ float s_pts[kStateWarps][kMaxDirPts * 3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * kStateWarps + warp;
-  if (r >= b.n) return;
+  if (r >= min(b.n, b.n_slots)) return;
   const float* P = b.points + (size_t)r * b.max_pts * 3;
   build_state_row(v, prm, P, 1, s_rows[warp], s_pts[warp], b.ld_state, lane);
   store_state_row(s_rows[warp], b.state[0] + (size_t)r * b.ld_state, b.ld_state, lane);
@@ -608,8 +639,7 @@ int ttl_pad_channels(const float* src, float* dst, int64_t n_voxels, int32_t C, 
                      void* stream) {
   if (!src || !dst || CP < C) return TTL_ERR_BAD_ARG;
   const long long total = (long long)n_voxels * CP;
-  pad_channels_kernel<<<ttl_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n_voxels, C, CP);
-  TTL_LAUNCHED();
+  TTL_LAUNCH("pad_channels_kernel", (cudaStream_t)stream, pad_channels_kernel<<<ttl_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n_voxels, C, CP));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -619,14 +649,14 @@ int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch*
   int rc = check_common(vol, prm);
   if (rc) return rc;
   if (!b || !seeds || b->n > b->capacity || b->ld_state > kMaxStateLd || (b->ld_state & 3) ||
-      b->ld_state < 7 * vol->C + 3 * prm->n_dirs)
+      b->ld_state < 7 * vol->C + 3 * prm->n_dirs || b->n_slots <= 0)
     return TTL_ERR_BAD_ARG;
   if (b->n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  reset_kernel<<<ttl_div_up(b->n, 256), 256, 0, s>>>(*b, seeds);
-  TTL_LAUNCHED();
-  reset_state_kernel<<<ttl_div_up(b->n, kStateWarps), kStateWarps * 32, 0, s>>>(*vol, *prm, *b);
-  TTL_LAUNCHED();
+  const int n_init = b->n > b->n_slots ? b->n : b->n_slots;
+  TTL_LAUNCH("reset_kernel", s, reset_kernel<<<ttl_div_up(n_init, 256), 256, 0, s>>>(*b, seeds));
+  const int n0 = b->n < b->n_slots ? b->n : b->n_slots;
+  TTL_LAUNCH("reset_state_kernel", s, reset_state_kernel<<<ttl_div_up(n0, kStateWarps), kStateWarps * 32, 0, s>>>(*vol, *prm, *b));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -638,14 +668,16 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   if (rc) return rc;
   if (!b || !actions || lda < 3 || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
   if (prm->compute_reward && !vol->peaks) return TTL_ERR_BAD_ARG;
+  if (prm->refill && prm->state_stopped) return TTL_ERR_BAD_ARG;
   if (n_upper <= 0) return 0;
+  if (n_upper > b->n_slots) n_upper = b->n_slots;
   cudaStream_t s = (cudaStream_t)stream;
-  propagate_stop_kernel<<<ttl_div_up(n_upper, 128), 128, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise);
-  TTL_LAUNCHED();
-  compact_kernel<<<1, kCompactThreads, 0, s>>>(*b, cur);
-  TTL_LAUNCHED();
-  build_state_kernel<<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, 0, s>>>(*vol, *prm, *b, cur, cur);
-  TTL_LAUNCHED();
+  TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<<<ttl_div_up(n_upper, 128), 128, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise));
+  TTL_LAUNCH("compact_kernel", s, compact_kernel<<<1, kCompactThreads, 0, s>>>(*b, cur, prm->refill));
+  const int u_new = prm->refill ? b->n_slots : n_upper;
+  const int u_old = prm->state_stopped ? n_upper : 0;
+  TTL_LAUNCH("build_state_kernel", s, build_state_kernel<<<ttl_div_up(u_new + u_old, kStateWarps), kStateWarps * 32, 0, s>>>(*vol, *prm, *b, cur,
+                                                                                       u_new));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -654,9 +686,8 @@ int ttl_env_gather_step_state(const ttl_batch* b, int32_t cur, int32_t n_rows, f
                               int32_t ld_out, void* stream) {
   if (!b || !out) return TTL_ERR_BAD_ARG;
   if (n_rows <= 0) return 0;
-  gather_rows_kernel<<<ttl_div_up((long long)n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      b->state[cur ^ 1], b->dest, n_rows, b->ld_state, out, ld_out, b->state_size);
-  TTL_LAUNCHED();
+  TTL_LAUNCH("gather_rows_kernel", (cudaStream_t)stream, gather_rows_kernel<<<ttl_div_up((long long)n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      b->state[cur ^ 1], b->dest, n_rows, b->ld_state, out, ld_out, b->state_size));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -669,9 +700,8 @@ int ttl_format_state(const ttl_volume* vol, const ttl_params* prm, const float* 
   if (n <= 0) return 0;
   const int S = 7 * vol->C + 3 * prm->n_dirs;
   const int ld_row = (S + 3) & ~3;
-  format_state_kernel<<<ttl_div_up(n, kStateWarps), kStateWarps * 32, 0, (cudaStream_t)stream>>>(
-      *vol, *prm, points, n, L, out, ld_out, ld_row);
-  TTL_LAUNCHED();
+  TTL_LAUNCH("format_state_kernel", (cudaStream_t)stream, format_state_kernel<<<ttl_div_up(n, kStateWarps), kStateWarps * 32, 0, (cudaStream_t)stream>>>(
+      *vol, *prm, points, n, L, out, ld_out, ld_row));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -683,17 +713,15 @@ int ttl_stopping_flags(const ttl_volume* vol, const ttl_params* prm, const float
   if (rc) return rc;
   if (!points || !out_flags || L < 1) return TTL_ERR_BAD_ARG;
   if (n <= 0) return 0;
-  stopping_flags_kernel<<<ttl_div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(
-      *vol, *prm, points, n, L, out_flags, out_mask_value, out_reward);
-  TTL_LAUNCHED();
+  TTL_LAUNCH("stopping_flags_kernel", (cudaStream_t)stream, stopping_flags_kernel<<<ttl_div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(
+      *vol, *prm, points, n, L, out_flags, out_mask_value, out_reward));
   TTL_CHECK_LAST();
   return 0;
 }
 
 int ttl_streamline_offsets(const ttl_batch* b, int64_t* offsets, void* stream) {
   if (!b || !offsets) return TTL_ERR_BAD_ARG;
-  offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*b, (long long*)offsets);
-  TTL_LAUNCHED();
+  TTL_LAUNCH("offsets_kernel", (cudaStream_t)stream, offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*b, (long long*)offsets));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -701,9 +729,8 @@ int ttl_streamline_offsets(const ttl_batch* b, int64_t* offsets, void* stream) {
 int ttl_pack_streamlines(const ttl_batch* b, const int64_t* offsets, float* out_points, void* stream) {
   if (!b || !offsets || !out_points) return TTL_ERR_BAD_ARG;
   if (b->n == 0) return 0;
-  pack_kernel<<<ttl_div_up((long long)b->n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      *b, (const long long*)offsets, out_points);
-  TTL_LAUNCHED();
+  TTL_LAUNCH("pack_kernel", (cudaStream_t)stream, pack_kernel<<<ttl_div_up((long long)b->n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      *b, (const long long*)offsets, out_points));
   TTL_CHECK_LAST();
   return 0;
 }

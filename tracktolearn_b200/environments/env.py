@@ -79,7 +79,10 @@ class BaseEnv(object):
 
         self.tracking_mask = tracking_mask
         self.peaks = peaks
-        self.seeding_data = np.asarray(seeding_mask.data).astype(np.uint8)
+        sd = seeding_mask.data
+        if isinstance(sd, torch.Tensor):
+            sd = sd.cpu().numpy()
+        self.seeding_data = np.asarray(sd).astype(np.uint8)
 
         if not self._uploaded:
             self._upload_volumes(input_volume, tracking_mask, peaks)
@@ -109,12 +112,14 @@ class BaseEnv(object):
 
     def _upload_volumes(self, input_volume, tracking_mask, peaks):
         lib = self._lib
-        data = np.asarray(input_volume.data)
-        if data.ndim != 4:
+        data = input_volume.data
+        if not isinstance(data, torch.Tensor):
+            data = torch.as_tensor(np.asarray(data))
+        if data.dim() != 4:
             raise ValueError('input volume must be [X,Y,Z,C]')
         X, Y, Z, C = data.shape
         CP = (C + self.CHANNEL_ALIGN - 1) // self.CHANNEL_ALIGN * self.CHANNEL_ALIGN
-        raw = torch.as_tensor(data).to(self.device, dtype=torch.float32).contiguous()
+        raw = data.to(self.device, dtype=torch.float32).contiguous()
         self._sh = torch.empty((X, Y, Z, CP), dtype=torch.float32, device=self.device)
         _lib.check(lib.ttl_pad_channels(_lib.ptr(raw), _lib.ptr(self._sh), X * Y * Z, C, CP,
                                         _lib.stream_ptr(self.device)), 'ttl_pad_channels')
@@ -122,13 +127,18 @@ class BaseEnv(object):
         del raw
         self._n_coefs = C
         # stopping_criteria.py:58-59: cubic B-spline coefficients of the mask, float64
-        mask_data = np.asarray(tracking_mask.data).astype(np.uint8)
+        mask_data = tracking_mask.data
+        if isinstance(mask_data, torch.Tensor):
+            mask_data = mask_data.cpu().numpy()
+        mask_data = np.asarray(mask_data).astype(np.uint8)
         coef = spline_filter(np.ascontiguousarray(mask_data, dtype=float), order=3)
         self._mask_coef = torch.from_numpy(coef).to(self.device)
         self._peaks = None
         if peaks is not None and self.compute_reward:
-            pk = np.asarray(peaks.data, dtype=np.float32)
-            self._peaks = torch.from_numpy(np.ascontiguousarray(pk)).to(self.device)
+            pk = peaks.data
+            if not isinstance(pk, torch.Tensor):
+                pk = torch.from_numpy(np.ascontiguousarray(np.asarray(pk, dtype=np.float32)))
+            self._peaks = pk.to(self.device, dtype=torch.float32).contiguous()
         pshape = tuple(self._peaks.shape[:3]) if self._peaks is not None else (0, 0, 0)
         self._volume = _lib.Volume(
             sh=self._sh.data_ptr(), X=X, Y=Y, Z=Z, C=C, CP=CP,

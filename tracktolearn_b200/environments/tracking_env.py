@@ -24,33 +24,39 @@ from tracktolearn_b200.tracking.tractogram import Tractogram
 
 
 class _BatchBuffers(object):
-    """Device buffers of one batch of streamlines (``ttl_batch`` in include/ttl_b200.h)."""
+    """Device buffers of one batch of streamlines (``ttl_batch`` in include/ttl_b200.h).
 
-    def __init__(self, capacity, max_pts, state_size, device):
-        self.capacity = capacity
+    ``rows``: seeds held by the batch (one streamline buffer row each); ``slots``: streamlines
+    tracked at once (== rows unless the streaming tracker refills freed slots)."""
+
+    def __init__(self, rows, slots, max_pts, state_size, device):
+        self.rows = rows
+        self.slots = slots
         self.max_pts = max_pts
         self.state_size = state_size
         self.ld_state = (state_size + 3) // 4 * 4
         i32 = dict(dtype=torch.int32, device=device)
-        pad = capacity + 16          # the compaction kernel reads stop[] 16 bytes at a time
-        self.points = torch.zeros((capacity, max_pts, 3), dtype=torch.float32, device=device)
-        self.flags = torch.zeros((pad,), **i32)
-        self.lengths = torch.zeros((pad,), **i32)
-        self.dones = torch.zeros((pad,), dtype=torch.uint8, device=device)
+        pad = slots + 16             # the compaction kernel reads stop[] 16 bytes at a time
+        self.points = torch.zeros((rows, max_pts, 3), dtype=torch.float32, device=device)
+        self.flags = torch.zeros((rows,), **i32)
+        self.lengths = torch.zeros((rows,), **i32)
+        self.npts = torch.zeros((rows,), **i32)
+        self.dones = torch.zeros((rows,), dtype=torch.uint8, device=device)
         self.alive = [torch.zeros((pad,), **i32), torch.zeros((pad,), **i32)]
         self.ctrl = torch.zeros((8,), **i32)
         self.stop = torch.zeros((pad,), dtype=torch.uint8, device=device)
         self.dest = torch.zeros((pad,), **i32)
         self.step_flags = torch.zeros((pad,), **i32)
         self.reward = torch.zeros((pad,), dtype=torch.float32, device=device)
-        self.state = [torch.zeros((capacity, self.ld_state), dtype=torch.float32, device=device),
-                      torch.zeros((capacity, self.ld_state), dtype=torch.float32, device=device)]
+        self.state = [torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device),
+                      torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device)]
         self.ctrl_host = torch.zeros((8,), dtype=torch.int32).pin_memory()
 
-    def as_struct(self, n):
-        b = _lib.Batch(n=n, capacity=self.capacity, max_pts=self.max_pts, ld_state=self.ld_state,
-                       state_size=self.state_size, points=self.points.data_ptr(),
-                       flags=self.flags.data_ptr(), lengths=self.lengths.data_ptr(),
+    def as_struct(self, n, n_slots):
+        b = _lib.Batch(n=n, n_slots=n_slots, capacity=self.rows, max_pts=self.max_pts,
+                       ld_state=self.ld_state, state_size=self.state_size,
+                       points=self.points.data_ptr(), flags=self.flags.data_ptr(),
+                       lengths=self.lengths.data_ptr(), npts=self.npts.data_ptr(),
                        dones=self.dones.data_ptr(), ctrl=self.ctrl.data_ptr(),
                        stop=self.stop.data_ptr(), dest=self.dest.data_ptr(),
                        step_flags=self.step_flags.data_ptr(), reward=self.reward.data_ptr())
@@ -65,36 +71,46 @@ class TrackingEnvironment(BaseEnv):
     """Reference: environments/tracking_env.py:13."""
 
     # ------------------------------------------------------------------------------ reset
-    def _ensure_buffers(self, n):
+    def _ensure_buffers(self, rows, slots):
         need_pts = self.max_nb_steps + 1
         S = self.get_state_size()
         bb = self._batch
-        if bb is None or bb.capacity < n or bb.max_pts != need_pts or bb.state_size != S:
-            cap = max(n, bb.capacity if bb is not None else 0)
+        if (bb is None or bb.rows < rows or bb.slots < slots or bb.max_pts != need_pts
+                or bb.state_size != S):
+            rows = max(rows, bb.rows if bb is not None else 0)
+            slots = max(slots, bb.slots if bb is not None else 0)
             self._batch = None
-            bb = _BatchBuffers(cap, need_pts, S, self.device)
+            bb = _BatchBuffers(rows, slots, need_pts, S, self.device)
             self._batch = bb
         return bb
 
-    def _start(self, initial_points):
+    def _start(self, initial_points, n_slots=None):
+        """``n_slots`` < N turns on the streaming tracker: only n_slots streamlines are alive
+        at once and slots freed by stopped ones take the next seeds in the same step."""
         self.initial_points = initial_points
         N = initial_points.shape[0]
-        bb = self._ensure_buffers(max(N, 1))
+        streaming = n_slots is not None and n_slots < N
+        slots = n_slots if streaming else max(N, 1)
+        bb = self._ensure_buffers(max(N, 1), slots)
         self._n = N
-        self._b = bb.as_struct(N)
+        self._b = bb.as_struct(N, slots)
+        self._params.refill = int(streaming)
+        self._params.state_stopped = int(bool(self.state_of_stopped) and not streaming)
         self._cur = 0
         self.length = 1
-        self._n_alive_host = N          # host mirror of the alive count (upper bound between syncs)
-        self._n_prev = N
-        self._continue_idx_cache = np.arange(N)
+        self._n_alive_host = min(N, slots)   # host mirror of the alive count (upper bound between syncs)
+        self._n_prev = self._n_alive_host
+        self._continue_idx_cache = np.arange(self._n_alive_host)
         self._pending_harvest = False
-        seeds_dev = torch.from_numpy(np.ascontiguousarray(initial_points, dtype=np.float64)).to(
-            self.device, non_blocking=False)
+        seeds_host = np.ascontiguousarray(initial_points, dtype=np.float64)
+        seeds_dev = (torch.from_numpy(seeds_host).pin_memory().to(self.device, non_blocking=True)
+                     if not isinstance(initial_points, torch.Tensor)
+                     else initial_points.to(self.device, dtype=torch.float64, non_blocking=True))
         _lib.check(self._lib.ttl_env_reset(ctypes.byref(self._volume), ctypes.byref(self._params),
                                            ctypes.byref(self._b), _lib.ptr(seeds_dev),
                                            _lib.stream_ptr(self.device)), 'ttl_env_reset')
         self._seeds_dev = seeds_dev   # keep alive until the kernel ran
-        return self._state_view(0, N)
+        return self._state_view(0, self._n_alive_host)
 
     def _state_view(self, which, n):
         return self._batch.state[which][:n, :self._batch.state_size]
@@ -102,6 +118,11 @@ class TrackingEnvironment(BaseEnv):
     def reset(self, start, end):
         """Reference: tracking_env.py:91-133."""
         return self._start(self.seeds[start:end])
+
+    def reset_streaming(self, start, end, n_slots):
+        """Like ``reset`` but at most ``n_slots`` streamlines are tracked at once; the others
+        wait in the batch and take over slots as streamlines stop (device-side refill)."""
+        return self._start(self.seeds[start:end], n_slots=n_slots)
 
     def nreset(self, n_seeds):
         """Reference: tracking_env.py:47-89."""
@@ -139,8 +160,18 @@ class TrackingEnvironment(BaseEnv):
         bb = self._batch
         bb.ctrl_host.copy_(bb.ctrl, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        self._n_alive_host = int(bb.ctrl_host[self._cur])
-        return self._n_alive_host
+        n = int(bb.ctrl_host[self._cur])
+        if self._params.refill and int(bb.ctrl_host[6]) < self._n:
+            # seeds are still waiting: later steps can have up to n_slots rows again
+            self._n_alive_host = self._b.n_slots
+        else:
+            self._n_alive_host = n
+        return n
+
+    def streamline_steps(self):
+        """Total streamline-steps taken since reset (device counter, valid after n_alive())."""
+        h = self._batch.ctrl_host
+        return (int(h[4]) & 0xffffffff) | (int(h[5]) << 32)
 
     def current_state(self):
         """State rows of the alive set, [n_alive_upper_bound, state_size] view (no sync)."""

@@ -202,13 +202,14 @@ def actor_state_dict(input_size=615, hidden_dims='1024-1024-1024', action_size=3
         sd['layers.%d.bias' % (2 * li)] = b
     if kind == 'tracking':
         n_sig = input_size - 300 if input_size > 300 else 0
-        # Shrink the random part, then wire relu(+x) - relu(-x) carry units through
-        # every hidden layer for the most recent direction (state[n_sig:n_sig+3])
-        # and for a fixed readout of the centre SH coefficients (first step).
+        # Shrink the random part, then wire relu(+x) / relu(-x) carry units through every
+        # hidden layer for the most recent direction (state[n_sig:n_sig+3]) and for a fixed
+        # readout of three centre-point SH coefficients (gives the first step a direction and
+        # later steps a gentle curvature).  The output gain keeps |mu| <= ~0.35 so tanh stays
+        # near-linear and the direction is carried almost unchanged.
         for li in range(len(dims) - 1):
-            sd['layers.%d.weight' % (2 * li)] *= 0.05
-            sd['layers.%d.bias' % (2 * li)] *= 0.05
-        gain = 4.0
+            sd['layers.%d.weight' % (2 * li)] *= 0.02
+            sd['layers.%d.bias' % (2 * li)] *= 0.02
         w0 = sd['layers.0.weight']
         for a in range(3):
             for s, sign in enumerate((1.0, -1.0)):
@@ -216,10 +217,9 @@ def actor_state_dict(input_size=615, hidden_dims='1024-1024-1024', action_size=3
                 w0[u, :] = 0
                 sd['layers.0.bias'][u] = 0
                 if n_sig:
-                    w0[u, n_sig + a] = sign * gain
-                    # l=2 coefficients of the centre point give a weak first-step cue
-                    w0[u, 1 + a] = sign * 0.5
-        for li in (1, 2):
+                    w0[u, n_sig + a] = sign
+                    w0[u, 1 + a] = sign * 0.125
+        for li in range(1, len(dims) - 2):
             w = sd['layers.%d.weight' % (2 * li)]
             for u in range(6):
                 w[u, :] = 0
@@ -229,8 +229,8 @@ def actor_state_dict(input_size=615, hidden_dims='1024-1024-1024', action_size=3
         wl = sd['layers.%d.weight' % (2 * (len(dims) - 2))]
         for a in range(3):
             wl[a, :6] = 0
-            wl[a, 2 * a] = 1.0
-            wl[a, 2 * a + 1] = -1.0
+            wl[a, 2 * a] = 0.4375
+            wl[a, 2 * a + 1] = -0.4375
     return sd
 
 

@@ -1,0 +1,117 @@
+"""Tracker (reference: tracking/tracker.py:18-259).
+
+``track`` keeps the reference's generator contract -- shuffle seeds, track batch after batch,
+keep streamlines whose length is within [min_length, max_length] mm, move them to TRK or TCK
+space, yield ``TractogramItem`` -- but by default it drives the env as a *streaming* tracker:
+``n_actor`` streamlines are alive at once and slots freed by stopped streamlines take the next
+seeds on the device, so the GPU stays full while the tail of long streamlines finishes.
+At ``prob = 0`` every streamline depends only on its own seed, so the output is the same as
+batch-by-batch tracking (tests/test_tracker_gpu.py).
+"""
+import numpy as np
+import torch
+
+from tracktolearn_b200.tracking.tractogram import Tractogram, TractogramItem
+
+
+def streamline_lengths(data, offsets):
+    """dipy ``length`` for every packed streamline: sum of segment norms, in double."""
+    n = len(offsets) - 1
+    out = np.zeros(n, dtype=np.float64)
+    if len(data) < 2 or n == 0:
+        return out
+    d = np.diff(data.astype(np.float64), axis=0)
+    seg = np.sqrt((d * d).sum(-1))
+    cs = np.concatenate(([0.0], np.cumsum(seg)))
+    first, last = offsets[:-1], offsets[1:] - 1
+    ok = last > first
+    out[ok] = cs[last[ok]] - cs[first[ok]]
+    return out
+
+
+class Tracker(object):
+
+    def __init__(self, alg, n_actor, prob=0., compress=0.0, min_length=20, max_length=200,
+                 save_seeds=False, streaming=True, rows_per_pass=None):
+        self.alg = alg
+        self.n_actor = n_actor
+        self.prob = prob
+        self.compress = compress
+        self.min_length = min_length
+        self.max_length = max_length
+        self.save_seeds = save_seeds
+        self.streaming = streaming
+        self.rows_per_pass = rows_per_pass
+        if compress:
+            raise NotImplementedError('--compress (dipy compress_streamlines) is a next-row item, '
+                                      'see DESIGN.md')
+
+    # ----------------------------------------------------------------------------------
+    def _passes(self, env):
+        n_seeds = len(env.seeds)
+        if not self.streaming or self.prob != 0.:
+            for start in range(0, n_seeds, self.n_actor):
+                yield start, min(start + self.n_actor, n_seeds), None
+            return
+        rows = self.rows_per_pass
+        if rows is None:
+            # streamline buffer budget: rows * (max_nb_steps+1) * 12 bytes <= ~6 GB
+            rows = max(self.n_actor, int(6e9 // ((env.max_nb_steps + 1) * 12)))
+        for start in range(0, n_seeds, rows):
+            yield start, min(start + rows, n_seeds), self.n_actor
+
+    def track_packed(self, env):
+        """Yields (Tractogram with voxel-space packed streamlines, seeds, flags) per pass;
+        no length filter, no space change."""
+        self.alg.agent.eval()
+        for start, end, slots in self._passes(env):
+            if slots is None or slots >= end - start:
+                state = env.reset(start, end)
+            else:
+                state = env.reset_streaming(start, end, slots)
+            self.alg.validation_episode(state, env, self.prob)
+            yield env.get_streamlines()
+
+    def track(self, env, tracts_format='trk'):
+        """Reference: tracking/tracker.py:62-150.  ``tracts_format``: 'trk' / 'tck' (or the
+        nibabel TrkFile / TckFile classes).  Returns a generator of TractogramItem."""
+        affine = env.affine_vox2rasmm
+        np.random.shuffle(env.seeds)      # tracker.py:94
+        is_trk = 'trk' in str(tracts_format).lower()
+
+        def tracking_generator():
+            vox_size = np.mean(np.abs(affine)[np.diag_indices(4)][:3])
+            scaled_min_length = self.min_length / vox_size
+            scaled_max_length = self.max_length / vox_size
+            for batch in self.track_packed(env):
+                lens = streamline_lengths(batch.data, batch.offsets)
+                keep = (scaled_min_length <= lens) & (lens <= scaled_max_length)
+                seeds = batch.data_per_streamline['seeds']
+                for i in np.nonzero(keep)[0]:
+                    s = np.array(batch.data[batch.offsets[i]:batch.offsets[i + 1]])
+                    if is_trk:
+                        s += 0.5
+                        s *= vox_size
+                    else:
+                        s = np.dot(s, affine[:3, :3]) + affine[:3, 3]
+                    seed_dict = {'seeds': seeds[i] - 0.5} if self.save_seeds else {}
+                    yield TractogramItem(s, seed_dict, {})
+
+        return tracking_generator()
+
+    def track_and_validate(self, env):
+        """Reference: tracking/tracker.py:204-259 (batch by batch, with rewards)."""
+        self.alg.agent.eval()
+        tractogram = None
+        cummulative_reward = 0
+        for start in range(0, len(env.seeds), self.n_actor):
+            end = min(start + self.n_actor, len(env.seeds))
+            state = env.reset(start, end)
+            reward = self.alg.validation_episode(state, env, self.prob)
+            t = env.get_streamlines()
+            if tractogram is None and len(t) > 0:
+                tractogram = t
+            elif len(t) > 0:
+                tractogram += t
+            cummulative_reward += reward
+        return tractogram, cummulative_reward
