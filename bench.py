@@ -332,15 +332,19 @@ def main_gpu(args):
         n, ms = prof.get(name, (0, 0.0))
         return ms / n if n else None
 
-    dense_ms = avg_ms('dense_bf16_kernel')
+    # the three tcgen05 layers of one step (the last one carries the fused head)
+    dn = [prof.get(k, (0, 0.0)) for k in ('dense_bf16_kernel', 'dense_bf16_head_kernel')]
+    dense_launches = sum(n for n, _ in dn)
+    dense_total_ms = sum(ms for _, ms in dn)
     roofline = None
-    if dense_ms:
-        per_launch_flop = DENSE_FLOP_PER_ROW / 3.0 * rows_prof      # three launches share the FLOPs
-        # use the true per-layer figure: average over the three layers of one step
-        achieved = per_launch_flop / (dense_ms * 1e-3) / 1e12
-        roofline = {'kernel': 'dense_bf16_kernel (tcgen05 actor layers, 3 launches/step)', 'bound': 'tensor',
-                    'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
+    if dense_launches:
+        steps_prof = dense_launches / 3.0
+        achieved = DENSE_FLOP_PER_ROW * rows_prof * steps_prof / (dense_total_ms * 1e-3) / 1e12
+        roofline = {'kernel': 'dense_bf16_kernel (tcgen05 actor layers, 3 launches/step, last one with fused head)',
+                    'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'],
+                    'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
+                    'avg_launch_us': 1000.0 * dense_total_ms / dense_launches,
+                    'flop_per_launch': DENSE_FLOP_PER_ROW * rows_prof / 3.0,
                     'peak_source': pk['source'] + ', sustained bf16 figure (kernel timed inside a long step)'}
     kernels = {}
     for name, (n, ms) in sorted(prof.items()):

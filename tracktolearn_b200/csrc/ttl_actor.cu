@@ -126,10 +126,21 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// HEAD_OUT > 0 fuses the network's last (HEAD_OUT-wide) linear layer into this layer's epilogue:
+// instead of storing relu(A.W^T+b) the epilogue threads (one accumulator row each) contract their
+// fp32 activations with head_w [HEAD_OUT][n] held in shared memory and write one partial result
+// per (row, n-tile) to head_partial [m][n_tiles][8]; head_finish_kernel sums the partials in a
+// fixed order, so results are deterministic.
+constexpr int EXTRA_SMEM_BIAS = 4096;           // bias vector staged for n_pad <= 1024
+constexpr int HEAD_OUT_FUSED = 6;               // SAC actor: 3 means + 3 log-stds
+constexpr int HEAD_SMEM_MAX = HEAD_OUT_FUSED * 1024 * 4;
+
+template <int HEAD_OUT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dense_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ C, int ldc,
-                  const int* __restrict__ m_dev, int m_max, int n_pad, int k_pad, int relu) {
+                  const int* __restrict__ m_dev, int m_max, int n_pad, int k_pad, int relu,
+                  const float* __restrict__ head_w, int head_k, float* __restrict__ head_partial) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ttl_smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -163,6 +174,18 @@ dense_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                  "r"((uint32_t)TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // bias (and the fused head's weights) staged once per CTA
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - raw));
+  float* s_head = s_bias + EXTRA_SMEM_BIAS / 4;
+  const bool bias_in_smem = n_pad <= EXTRA_SMEM_BIAS / 4;
+  if (bias_in_smem)
+    for (int t = threadIdx.x; t < n_pad; t += GEMM_THREADS) s_bias[t] = bias[t];
+  if (HEAD_OUT > 0) {
+    for (int t = threadIdx.x; t < HEAD_OUT * n_pad; t += GEMM_THREADS) {
+      const int o = t / n_pad, c = t - o * n_pad;
+      s_head[t] = c < head_k ? head_w[(size_t)o * head_k + c] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -223,21 +246,52 @@ dense_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < m;
       __nv_bfloat16* crow = C + (size_t)row * ldc;
+      float hp[HEAD_OUT > 0 ? HEAD_OUT : 1];
+#pragma unroll
+      for (int o = 0; o < (HEAD_OUT > 0 ? HEAD_OUT : 1); ++o) hp[o] = 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         const int col0 = n_blk * BN + ch * 32;
-        if (col0 >= ldc) break;  // warp-uniform
+        if (col0 >= n_pad) break;  // warp-uniform
         uint32_t v[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
         tc_wait_ld();
-        if (row_ok) {
+        float x[32];
+        if (bias_in_smem) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j);
+            x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+            x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+            x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __ldg(bias + col0 + j);
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
+        if (HEAD_OUT > 0) {
+#pragma unroll
+          for (int o = 0; o < HEAD_OUT; ++o) {
+            const float* wrow = s_head + o * n_pad + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wrow + 4 * j);
+              hp[o] = fmaf(x[4 * j + 0], w4.x, hp[o]);
+              hp[o] = fmaf(x[4 * j + 1], w4.y, hp[o]);
+              hp[o] = fmaf(x[4 * j + 2], w4.z, hp[o]);
+              hp[o] = fmaf(x[4 * j + 3], w4.w, hp[o]);
+            }
+          }
+        } else if (row_ok) {
           uint32_t packed[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float x0 = __uint_as_float(v[2 * j]) + __ldg(bias + col0 + 2 * j);
-            float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + col0 + 2 * j + 1);
-            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+            __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
             packed[j] = *reinterpret_cast<uint32_t*>(&h);
           }
           uint4* dst = reinterpret_cast<uint4*>(crow + col0);
@@ -245,6 +299,14 @@ dense_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           for (int j = 0; j < 4; ++j)
             dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
         }
+      }
+      if (HEAD_OUT > 0 && row_ok) {
+        float o8[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) o8[o] = o < HEAD_OUT ? hp[o < HEAD_OUT ? o : 0] : 0.f;
+        float4* dst = reinterpret_cast<float4*>(head_partial + ((size_t)row * n_n + n_blk) * 8);
+        dst[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+        dst[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
       }
       tc_fence_before();
       __syncwarp();
@@ -376,6 +438,57 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ h, int 
   }
 }
 
+// Sums the per-n-tile partials of the fused head in tile order, adds the bias and applies the
+// policy head.  One thread per row.
+__global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ partial, int n_tiles,
+                                                          const float* __restrict__ b, int n_out,
+                                                          const int* __restrict__ n_dev, int n_max,
+                                                          float prob, const float* __restrict__ eps,
+                                                          float* __restrict__ action,
+                                                          float* __restrict__ logp, float* __restrict__ pre) {
+  int n = n_dev ? *n_dev : n_max;
+  n = min(n, n_max);
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+  for (int t = 0; t < n_tiles; ++t) {
+    const float4* p = reinterpret_cast<const float4*>(partial + ((size_t)r * n_tiles + t) * 8);
+    const float4 a = p[0], c = p[1];
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += c.x; acc[5] += c.y; acc[6] += c.z; acc[7] += c.w;
+  }
+  const int A = n_out >> 1;
+  float lp = 0.f;
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+    if (o < n_out) {
+      acc[o] += b[o];
+      if (pre) pre[(size_t)r * n_out + o] = acc[o];
+    }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (a >= A) break;
+    const float mu = acc[a];
+    float ls = 0.f;
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o == A + a) ls = acc[o];
+    const float log_std = fminf(fmaxf(ls, -20.f), 2.f);
+    const float std = expf(log_std) * prob;
+    const float e = eps ? eps[(size_t)r * A + a] : 0.f;
+    const float pi = eps ? fmaf(std, e, mu) : mu;
+    if (logp) {
+      const float z = pi - mu;
+      lp += -(z * z) / (2.f * std * std) - logf(std) - 0.9189385332046727f;
+      lp -= 2.f * (0.6931471805599453f - pi - softplus_f(-2.f * pi));
+    }
+    action[(size_t)r * A + a] = tanhf(pi);
+  }
+  if (logp) logp[r] = lp;
+}
+
 // ==========================================================================================
 // fp32 tier: plain tiled SGEMM on CUDA cores (reference precision)
 // ==========================================================================================
@@ -471,19 +584,31 @@ int num_sms() {
 
 int launch_dense_bf16(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, __nv_bfloat16* C,
                       int ldc, const int* m_dev, int m_max, int n_pad, int k_pad, int relu,
-                      cudaStream_t s) {
+                      cudaStream_t s, const float* head_w = nullptr, int head_k = 0,
+                      float* head_partial = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dense_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GEMM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(dense_bf16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GEMM_SMEM + EXTRA_SMEM_BIAS);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(dense_bf16_kernel<HEAD_OUT_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             GEMM_SMEM + EXTRA_SMEM_BIAS + HEAD_SMEM_MAX);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int tiles = ttl_div_up(m_max, BM) * ttl_div_up(n_pad, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid <= 0) return 0;
-  TTL_LAUNCH("dense_bf16_kernel", s, dense_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ta, tb, bias, C, ldc, m_dev, m_max, n_pad,
-                                                         k_pad, relu));
+  if (head_w) {
+    TTL_LAUNCH("dense_bf16_head_kernel", s,
+               dense_bf16_kernel<HEAD_OUT_FUSED><<<grid, GEMM_THREADS,
+                                                   GEMM_SMEM + EXTRA_SMEM_BIAS + HEAD_OUT_FUSED * n_pad * 4, s>>>(
+                   ta, tb, bias, C, ldc, m_dev, m_max, n_pad, k_pad, relu, head_w, head_k, head_partial));
+  } else {
+    TTL_LAUNCH("dense_bf16_kernel", s,
+               dense_bf16_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM + EXTRA_SMEM_BIAS, s>>>(
+                   ta, tb, bias, C, ldc, m_dev, m_max, n_pad, k_pad, relu, nullptr, 0, nullptr));
+  }
   TTL_CHECK_LAST();
   return 0;
 }
@@ -499,6 +624,8 @@ struct ttl_actor_plan {
   float* bq[TTL_ACTOR_MAX_LAYERS];
   __nv_bfloat16* act[2];             // ping-pong activations [max_rows][max_kpad]
   float* f32[2];                     // fp32-tier scratch [F32_CHUNK][max_width]
+  float* head_partial;               // fused head partials [max_rows][4][8]
+  bool fuse_head;
   int max_kpad, max_width;
   CUtensorMap map_w[TTL_ACTOR_MAX_LAYERS];
   CUtensorMap map_a[TTL_ACTOR_MAX_LAYERS];  // A operand of layer i
@@ -509,7 +636,7 @@ constexpr int F32_CHUNK = 8192;
 
 struct Layout {
   int64_t total;
-  int64_t off_w[TTL_ACTOR_MAX_LAYERS], off_b[TTL_ACTOR_MAX_LAYERS], off_act[2], off_f32[2];
+  int64_t off_w[TTL_ACTOR_MAX_LAYERS], off_b[TTL_ACTOR_MAX_LAYERS], off_act[2], off_f32[2], off_hp;
   int k_pad[TTL_ACTOR_MAX_LAYERS], n_pad[TTL_ACTOR_MAX_LAYERS];
   int max_kpad, max_width;
 };
@@ -535,6 +662,7 @@ int plan_layout(const ttl_actor_weights* w, int max_rows, Layout* L) {
   }
   for (int j = 0; j < 2; ++j) L->off_act[j] = take((int64_t)max_rows * L->max_kpad * 2);
   for (int j = 0; j < 2; ++j) L->off_f32[j] = take((int64_t)F32_CHUNK * L->max_width * 4);
+  L->off_hp = take((int64_t)max_rows * 4 * 8 * 4);
   L->total = off;
   return 0;
 }
@@ -569,6 +697,9 @@ int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int3
   }
   const int nl = w->n_layers;
   for (int i = 0; i < nl; ++i) { p->k_pad[i] = L.k_pad[i]; p->n_pad[i] = L.n_pad[i]; }
+  p->head_partial = reinterpret_cast<float*>(ws + L.off_hp);
+  // the last hidden layer can carry the head when it is 6 wide and the layer fits 4 n-tiles
+  p->fuse_head = w->out_dim[nl - 1] == HEAD_OUT_FUSED && L.n_pad[nl - 2] <= 1024;
   for (int i = 0; i < nl - 1; ++i) {  // hidden layers run on tensor cores
     p->wq[i] = reinterpret_cast<__nv_bfloat16*>(ws + L.off_w[i]);
     p->bq[i] = reinterpret_cast<float*>(ws + L.off_b[i]);
@@ -615,13 +746,22 @@ int ttl_actor_forward(ttl_actor_plan* p, const float* state, int32_t ld_state, c
                                                               n_rows_max, p->act[0], p->k_pad[0]));
     for (int i = 0; i < nl - 1; ++i) {
       // layer i: act[i&1] (pitch k_pad[i]) -> act[(i+1)&1] (pitch k_pad[i+1] = n_pad[i])
+      const bool fused = p->fuse_head && i == nl - 2;
       int rc = launch_dense_bf16(p->map_a[i], p->map_w[i], p->bq[i], p->act[(i + 1) & 1], p->n_pad[i],
-                                 n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1, s);
+                                 n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1, s,
+                                 fused ? w.w[nl - 1] : nullptr, k_last, fused ? p->head_partial : nullptr);
       if (rc) return rc;
     }
-    TTL_LAUNCH("head_kernel_bf16", s, head_kernel<__nv_bfloat16><<<head_grid, 256, head_smem, s>>>(
-        p->act[(nl - 1) & 1], p->k_pad[nl - 1], k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
-        n_rows_max, probabilistic, eps, action, logp, pre));
+    if (p->fuse_head) {
+      TTL_LAUNCH("head_finish_kernel", s,
+                 head_finish_kernel<<<ttl_div_up(n_rows_max, 256), 256, 0, s>>>(
+                     p->head_partial, ttl_div_up(p->n_pad[nl - 2], BN), w.b[nl - 1], n_out, n_rows_dev,
+                     n_rows_max, probabilistic, eps, action, logp, pre));
+    } else {
+      TTL_LAUNCH("head_kernel_bf16", s, head_kernel<__nv_bfloat16><<<head_grid, 256, head_smem, s>>>(
+          p->act[(nl - 1) & 1], p->k_pad[nl - 1], k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
+          n_rows_max, probabilistic, eps, action, logp, pre));
+    }
     TTL_CHECK_LAST();
     return 0;
   }
