@@ -8,8 +8,9 @@ descoteaux07 fODF, npv 20 on the mask shell (~1M seeds per GPU), n_actor 50 000,
 NoisyTrackingEnvironment with noise 0 (what ttl_track.py always runs), SAC actor
 615-1024-1024-1024-6 with a synthetic "tracking-like" checkpoint.  One bench STEP = one pass of
 the hot path over the batch of n_actor alive streamlines: actor forward (state pack, three
-tcgen05 dense layers, fp32 head) + env step (propagate/stop, ordered compaction with slot
-refill, state gather) -- 8 kernel launches, no host involvement.
+tcgen05 dense layers with the head fused into the last, head finish) + env step (propagate/stop
+with ordered-compaction bookkeeping and slot refill, state gather) -- 6 kernel launches, no host
+involvement.
 
 The JSON line follows the driver contract; see DESIGN.md section "Measurement" for how every
 field is produced.  `--impl reference` times the CPU restatement of the reference path
@@ -248,7 +249,7 @@ def main_gpu(args):
     def one_step(action_buf):
         state = env.current_state()
         actor.forward_device(state, 0.0, n_rows_dev=env.alive_count_tensor(), n_rows=state.shape[0],
-                             want_logp=False, out_action=action_buf)
+                             want_logp=False, out_action=action_buf, state_bf16=env.current_state_bf16())
         env.step_device(action_buf)
         env.harvest_device()
 
@@ -350,7 +351,7 @@ def main_gpu(args):
     for name, (n, ms) in sorted(prof.items()):
         kernels[name] = {'launches': n, 'avg_us': 1000.0 * ms / n}
     state_ms = avg_ms('build_state_kernel')
-    step_ms = sum(avg_ms(k) or 0.0 for k in ('propagate_stop_kernel', 'compact_kernel', 'build_state_kernel'))
+    step_ms = sum(avg_ms(k) or 0.0 for k in ('propagate_stop_kernel', 'build_state_kernel'))
     roofline_step = None
     if state_ms and step_ms:
         a_state = STATE_KERNEL_BYTES_PER_ROW * rows_prof / (state_ms * 1e-3) / 1e9
@@ -359,7 +360,7 @@ def main_gpu(args):
             'build_state_kernel': {'bound': 'hbm', 'achieved': a_state, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                                    'frac': a_state / pk['hbm_gbs'], 'traffic': None,
                                    'bytes_per_row': STATE_KERNEL_BYTES_PER_ROW},
-            'env_step (propagate_stop+compact+build_state)': {
+            'env_step (propagate_stop+build_state)': {
                 'bound': 'hbm', 'achieved': a_step, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                 'frac': a_step / pk['hbm_gbs'], 'traffic': None, 'bytes_per_row': STEP_BYTES_PER_ROW},
             'peak_source': pk['source']}

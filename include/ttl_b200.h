@@ -83,13 +83,22 @@ typedef struct ttl_batch {
   int32_t* alive[2];       /* ping-pong lists of alive global rows, ascending */
   int32_t* ctrl;           /* [8] device ints: [0],[1] alive count of alive[0],alive[1];
                               [2] steps taken; [3] alive count before the last step;
-                              [4],[5] int64 streamline-steps so far; [6] next unseeded row */
+                              [4],[5] int64 streamline-steps so far; [6] next unseeded row;
+                              [7] block ticket; [8] survivors of the last step; [9] rows refilled in
+                              the last step; [10] first row refilled in the last step  (16 ints) */
   uint8_t* stop;           /* [n_slots+16] per rank (position in the alive list): stopped this step */
   int32_t* dest;           /* [n_slots] per rank: row of state[next] that holds its new state */
   int32_t* step_flags;     /* [n_slots] per rank: flags raised this step */
   float* reward;           /* [n_slots] per rank */
   float* state[2];         /* ping-pong [n_slots][ld_state] fp32 state rows.  state[cur] rows
                               [0, n_alive) are the states of alive[cur] in order. */
+  void* state_bf16[2];     /* ping-pong [n_slots][ld_bf16] bf16 copies of the state rows, zero padded
+                              to ld_bf16 = round_up(state_size, 64): the actor's first-layer TMA
+                              operand, written by the same kernel that writes state[] */
+  int32_t ld_bf16;
+  int32_t max_groups;      /* entries in grp_stops / grp_prefix: ceil(n_slots / 128) + 1 */
+  int32_t* grp_stops;      /* [max_groups] streamlines stopped this step per group of 128 ranks */
+  int32_t* grp_prefix;     /* [max_groups] exclusive prefix of survivors per group */
 } ttl_batch;
 
 /* ---- one-time / load-time helpers ------------------------------------------------------ */
@@ -177,6 +186,13 @@ int ttl_actor_forward(ttl_actor_plan* plan, const float* state, int32_t ld_state
                       const int32_t* n_rows_dev, int32_t n_rows_max, float probabilistic,
                       const float* eps, float* action, float* logp, float* pre,
                       int32_t precision, void* stream);
+/* Same (bf16 tier only) when the caller already holds the bf16, zero-padded copy of the states
+ * that ttl_env_step / ttl_env_reset write (ttl_batch.state_bf16): state_bf16 [rows_alloc][ld]
+ * with ld == round_up(in_dim, 64).  Skips the packing pass. */
+int ttl_actor_forward_packed(ttl_actor_plan* plan, const void* state_bf16, int32_t ld,
+                             int32_t rows_alloc, const int32_t* n_rows_dev, int32_t n_rows_max,
+                             float probabilistic, const float* eps, float* action, float* logp,
+                             float* pre, void* stream);
 
 /* Stand-alone dense layer used by the actor and exposed for tests:
  * C[m][ldc] (bf16) = act(A[m][k] (bf16) . W[n][k]^T (bf16) + bias[n]), tcgen05/TMEM/TMA. */

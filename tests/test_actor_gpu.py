@@ -113,3 +113,15 @@ def test_actor_full_size_both_tiers(kind):
     out = torch.full((5000, 3), 9.0, device='cuda')
     ac16.actor.forward_device(buf[:, :615], 0.0, n_rows_dev=n_dev, out_action=out, want_logp=False)
     assert torch.equal(out[:1234], a16[:1234]) and (out[1234:] == 9.0).all()
+
+
+def test_actor_packed_bf16_state_matches_packing_path():
+    """ttl_actor_forward_packed (bf16 rows supplied by the env) == ttl_actor_forward (packs fp32)."""
+    ac16, _ = _actor('1024-1024-1024', 1111, 'bf16', 'tracking')
+    rs = np.random.RandomState(1)
+    st = torch.from_numpy(rs.normal(size=(3000, 615)).astype(np.float32)).cuda()
+    sb = torch.zeros((3000, 640), dtype=torch.bfloat16, device='cuda')
+    sb[:, :615] = st.to(torch.bfloat16)
+    a1, _, p1 = ac16.actor.forward_device(st, 0.0, want_pre=True)
+    a2, _, p2 = ac16.actor.forward_device(st, 0.0, want_pre=True, state_bf16=sb)
+    assert torch.equal(p1, p2) and torch.equal(a1, a2)

@@ -30,7 +30,9 @@ class Batch(ctypes.Structure):
     _fields_ = [('n', c_i32), ('n_slots', c_i32), ('capacity', c_i32), ('max_pts', c_i32), ('ld_state', c_i32),
                 ('state_size', c_i32), ('points', c_vp), ('flags', c_vp), ('lengths', c_vp),
                 ('npts', c_vp), ('dones', c_vp), ('alive', c_vp * 2), ('ctrl', c_vp), ('stop', c_vp), ('dest', c_vp),
-                ('step_flags', c_vp), ('reward', c_vp), ('state', c_vp * 2)]
+                ('step_flags', c_vp), ('reward', c_vp), ('state', c_vp * 2),
+                ('state_bf16', c_vp * 2), ('ld_bf16', c_i32), ('max_groups', c_i32), ('grp_stops', c_vp),
+                ('grp_prefix', c_vp)]
 
 
 class ActorWeights(ctypes.Structure):
@@ -65,6 +67,7 @@ SIGNATURES = {
     'ttl_actor_plan_create': (c_i32, [P(c_vp), P(ActorWeights), c_i32, c_vp, c_i64, c_vp]),
     'ttl_actor_plan_destroy': (None, [c_vp]),
     'ttl_actor_forward': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
+    'ttl_actor_forward_packed': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ttl_gemm_bf16': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'ttl_oracle_features': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
     'ttl_oracle_forward': (c_i32, [P(OracleWeights), c_vp, c_i32, c_vp, c_vp]),

@@ -44,7 +44,8 @@ class RLAlgorithm(object):
             state = env.current_state()
             rows = state.shape[0]
             actor.forward_device(state, prob, n_rows_dev=env.alive_count_tensor(), n_rows=rows,
-                                 want_logp=False, out_action=action_buf)
+                                 want_logp=False, out_action=action_buf,
+                                 state_bf16=env.current_state_bf16())
             env.step_device(action_buf)
             if env.compute_reward:
                 r = env._batch.reward[:rows].sum(dtype=torch.float64)

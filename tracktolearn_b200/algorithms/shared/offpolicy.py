@@ -115,9 +115,11 @@ class MaxEntropyActor(object):
         self._w_struct = w
 
     def forward_device(self, state, probabilistic, n_rows_dev=None, n_rows=None, eps=None,
-                       want_logp=True, want_pre=False, out_action=None):
+                       want_logp=True, want_pre=False, out_action=None, state_bf16=None):
         """state: CUDA fp32 [rows, >= state_dim] (row stride free).  ``n_rows_dev``: optional
-        device int32 tensor with the live row count (no host sync).  Returns
+        device int32 tensor with the live row count (no host sync).  ``state_bf16``: the env's
+        bf16 zero-padded copy of the same rows ([rows_alloc, round_up(state_dim, 64)]); with it
+        the bf16 tier skips its packing pass.  Returns
         (action [rows,3], logp [rows] or None, pre [rows,6] or None)."""
         if state.dim() < 2:
             state = state[None, :]
@@ -135,6 +137,13 @@ class MaxEntropyActor(object):
             eps = torch.randn((rows, A), dtype=torch.float32, device=self.device)
         self._ensure_plan(rows)
         prec = _lib.PRECISION_BF16 if self.precision == 'bf16' else _lib.PRECISION_FP32
+        if prec == _lib.PRECISION_BF16 and state_bf16 is not None:
+            _lib.check(self._lib.ttl_actor_forward_packed(
+                self._plan, _lib.ptr(state_bf16), int(state_bf16.stride(0)), int(state_bf16.shape[0]),
+                _lib.ptr(n_rows_dev), rows, float(probabilistic), _lib.ptr(eps), _lib.ptr(action),
+                _lib.ptr(logp), _lib.ptr(pre), _lib.stream_ptr(self.device)), 'ttl_actor_forward_packed')
+            self._keep = (state_bf16, eps)
+            return action, logp, pre
         ld = state.stride(0) if state.shape[0] > 1 else state.shape[1]
         _lib.check(self._lib.ttl_actor_forward(
             self._plan, _lib.ptr(state), int(ld), _lib.ptr(n_rows_dev), rows, float(probabilistic),

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "ttl_common.cuh"
 
@@ -629,6 +630,9 @@ struct ttl_actor_plan {
   int max_kpad, max_width;
   CUtensorMap map_w[TTL_ACTOR_MAX_LAYERS];
   CUtensorMap map_a[TTL_ACTOR_MAX_LAYERS];  // A operand of layer i
+  // first-layer operand maps for caller-owned bf16 state buffers (ttl_actor_forward_packed)
+  struct ExtMap { const void* ptr; int rows; CUtensorMap map; };
+  std::vector<ExtMap> ext_maps;
 };
 
 namespace {
@@ -664,6 +668,45 @@ int plan_layout(const ttl_actor_weights* w, int max_rows, Layout* L) {
   for (int j = 0; j < 2; ++j) L->off_f32[j] = take((int64_t)F32_CHUNK * L->max_width * 4);
   L->off_hp = take((int64_t)max_rows * 4 * 8 * 4);
   L->total = off;
+  return 0;
+}
+}  // namespace
+
+namespace {
+// Hidden layers on tensor cores (the last one carries the fused head when possible) + head.
+// map_a0: TMA map of the first layer's bf16 operand [rows][k_pad[0]].
+int run_bf16_layers(ttl_actor_plan* p, const CUtensorMap& map_a0, const int32_t* n_rows_dev,
+                    int32_t n_rows_max, float probabilistic, const float* eps, float* action, float* logp,
+                    float* pre, cudaStream_t s) {
+  const ttl_actor_weights& w = p->w;
+  const int nl = w.n_layers;
+  const int n_out = w.out_dim[nl - 1], k_last = w.in_dim[nl - 1];
+  const size_t head_smem = (size_t)n_out * k_last * sizeof(float);
+  const int head_grid = num_sms() * 2;
+  static bool head_attr = false;
+  if (!head_attr && head_smem > 48 * 1024) {
+    cudaFuncSetAttribute(head_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    head_attr = true;
+  }
+  for (int i = 0; i < nl - 1; ++i) {
+    // layer i: act[i&1] (pitch k_pad[i]) -> act[(i+1)&1] (pitch k_pad[i+1] = n_pad[i])
+    const bool fused = p->fuse_head && i == nl - 2;
+    int rc = launch_dense_bf16(i == 0 ? map_a0 : p->map_a[i], p->map_w[i], p->bq[i], p->act[(i + 1) & 1],
+                               p->n_pad[i], n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1, s,
+                               fused ? w.w[nl - 1] : nullptr, k_last, fused ? p->head_partial : nullptr);
+    if (rc) return rc;
+  }
+  if (p->fuse_head) {
+    TTL_LAUNCH("head_finish_kernel", s,
+               head_finish_kernel<<<ttl_div_up(n_rows_max, 256), 256, 0, s>>>(
+                   p->head_partial, ttl_div_up(p->n_pad[nl - 2], BN), w.b[nl - 1], n_out, n_rows_dev,
+                   n_rows_max, probabilistic, eps, action, logp, pre));
+  } else {
+    TTL_LAUNCH("head_kernel_bf16", s, head_kernel<__nv_bfloat16><<<head_grid, 256, head_smem, s>>>(
+        p->act[(nl - 1) & 1], p->k_pad[nl - 1], k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
+        n_rows_max, probabilistic, eps, action, logp, pre));
+  }
+  TTL_CHECK_LAST();
   return 0;
 }
 }  // namespace
@@ -736,34 +779,10 @@ int ttl_actor_forward(ttl_actor_plan* p, const float* state, int32_t ld_state, c
   const int head_grid = num_sms() * 2;
 
   if (precision == TTL_PRECISION_BF16) {
-    static bool head_attr = false;
-    if (!head_attr && head_smem > 48 * 1024) {
-      cudaFuncSetAttribute(head_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      head_attr = true;
-    }
     const long long tot = (long long)n_rows_max * (p->k_pad[0] >> 3);
     TTL_LAUNCH("pack_state_bf16_kernel", s, pack_state_bf16_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(state, ld_state, w.in_dim[0], n_rows_dev,
                                                               n_rows_max, p->act[0], p->k_pad[0]));
-    for (int i = 0; i < nl - 1; ++i) {
-      // layer i: act[i&1] (pitch k_pad[i]) -> act[(i+1)&1] (pitch k_pad[i+1] = n_pad[i])
-      const bool fused = p->fuse_head && i == nl - 2;
-      int rc = launch_dense_bf16(p->map_a[i], p->map_w[i], p->bq[i], p->act[(i + 1) & 1], p->n_pad[i],
-                                 n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1, s,
-                                 fused ? w.w[nl - 1] : nullptr, k_last, fused ? p->head_partial : nullptr);
-      if (rc) return rc;
-    }
-    if (p->fuse_head) {
-      TTL_LAUNCH("head_finish_kernel", s,
-                 head_finish_kernel<<<ttl_div_up(n_rows_max, 256), 256, 0, s>>>(
-                     p->head_partial, ttl_div_up(p->n_pad[nl - 2], BN), w.b[nl - 1], n_out, n_rows_dev,
-                     n_rows_max, probabilistic, eps, action, logp, pre));
-    } else {
-      TTL_LAUNCH("head_kernel_bf16", s, head_kernel<__nv_bfloat16><<<head_grid, 256, head_smem, s>>>(
-          p->act[(nl - 1) & 1], p->k_pad[nl - 1], k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
-          n_rows_max, probabilistic, eps, action, logp, pre));
-    }
-    TTL_CHECK_LAST();
-    return 0;
+    return run_bf16_layers(p, p->map_a[0], n_rows_dev, n_rows_max, probabilistic, eps, action, logp, pre, s);
   }
   if (precision == TTL_PRECISION_FP32) {
     // Reference-precision tier; needs the row count on the host.
@@ -802,6 +821,30 @@ int ttl_actor_forward(ttl_actor_plan* p, const float* state, int32_t ld_state, c
     return 0;
   }
   return TTL_ERR_UNSUPPORTED;
+}
+
+int ttl_actor_forward_packed(ttl_actor_plan* p, const void* state_bf16, int32_t ld, int32_t rows_alloc,
+                             const int32_t* n_rows_dev, int32_t n_rows_max, float probabilistic,
+                             const float* eps, float* action, float* logp, float* pre, void* stream) {
+  if (!p || !state_bf16 || !action || n_rows_max > p->max_rows || n_rows_max > rows_alloc) return TTL_ERR_BAD_ARG;
+  if (ld != p->k_pad[0] || (reinterpret_cast<uintptr_t>(state_bf16) & 15)) return TTL_ERR_BAD_ARG;
+  if (probabilistic != 0.f && !eps) return TTL_ERR_BAD_ARG;
+  if (n_rows_max <= 0) return 0;
+  const CUtensorMap* map = nullptr;
+  for (auto& e : p->ext_maps)
+    if (e.ptr == state_bf16 && e.rows == rows_alloc) map = &e.map;
+  if (!map) {
+    if (p->ext_maps.size() >= 16) p->ext_maps.clear();
+    ttl_actor_plan::ExtMap e;
+    e.ptr = state_bf16;
+    e.rows = rows_alloc;
+    int rc = make_tmap(&e.map, state_bf16, (uint64_t)rows_alloc, (uint64_t)ld, BM);
+    if (rc) return rc;
+    p->ext_maps.push_back(e);
+    map = &p->ext_maps.back().map;
+  }
+  return run_bf16_layers(p, *map, n_rows_dev, n_rows_max, probabilistic, eps, action, logp, pre,
+                         (cudaStream_t)stream);
 }
 
 int ttl_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t m, int32_t n,

@@ -16,18 +16,26 @@
 // are one contiguous 384 B run; streamline points [row][max_pts][3] fp32; state rows
 // [rank][ld_state=616] fp32 so rows start 16-byte aligned.
 //
-// Three launches per step, none of which needs the host:
-//   propagate_stop  one thread per alive streamline (byte/flag work, 64 fp64 spline taps)
-//   compact         one CTA, ordered stream compaction of the alive list (keeps the
-//                   reference's ascending continue_idx order)
-//   build_state     one warp per streamline: float4 gathers of the 7x8 trilinear corners
-//                   (unique footprint ~26 voxels, duplicates hit L1), row staged in shared
-//                   memory and written with coalesced 16-byte stores.
+// Two launches per step, none of which needs the host:
+//   propagate_stop  one thread per alive streamline (byte/flag work, 64 fp64 spline taps); each
+//                   CTA publishes how many of its 128 ranks stopped and the last CTA to finish
+//                   scans those counts (ordered compaction bookkeeping, slot refill, counters)
+//   build_state     one warp per rank: derives its position in the compacted alive list from
+//                   the group prefix + a ballot over its group's stop flags (keeps the
+//                   reference's ascending continue_idx order), stages the 7x8 trilinear corner
+//                   voxels (192 B each) into shared memory with cp.async (all ~10 KB in flight
+//                   at once, duplicates of the ~26-voxel footprint hit L1), then every lane
+//                   produces consecutive state elements so fp32 and bf16 rows are written with
+//                   fully coalesced stores.
+#include <cuda_bf16.h>
+
 #include "ttl_common.cuh"
 
 std::atomic<long long> g_ttl_launches{0};
 
 namespace {
+
+constexpr int kGroup = 128;   // ranks per compaction group == propagate_stop block size
 
 // ------------------------------------------------------------------------------------------
 // float helpers that refuse FMA contraction, so sums of products round like numpy's
@@ -197,6 +205,10 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
     b.ctrl[4] = 0;
     b.ctrl[5] = 0;
     b.ctrl[6] = n0;  // next unseeded row
+    b.ctrl[7] = 0;
+    b.ctrl[8] = 0;
+    b.ctrl[9] = 0;
+    b.ctrl[10] = 0;
   }
   if (i < b.n_slots) {
     b.dest[i] = i;
@@ -224,7 +236,8 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
     int lda, const double* __restrict__ noise) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_alive = b.ctrl[cur];
-  if (r >= n_alive) return;
+  int stopped = 0;
+  if (r < n_alive) {
   const int i = b.alive[cur][r];
   const int L = b.npts[i];  // points so far in this row
   float* P = b.points + (size_t)i * b.max_pts * 3;
@@ -276,6 +289,7 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
   b.npts[i] = Ln;
   b.step_flags[r] = f;
   b.stop[r] = f != 0;
+  stopped = f != 0;
   if (f) {
     b.flags[i] = f;
     b.dones[i] = 1;
@@ -285,86 +299,72 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
     // reward.py:63-67: w * f(...) stays float32 (weak python scalar)
     b.reward[r] = __fmul_rn((float)prm.alignment_weighting, alignment_reward(v, P, Ln));
   }
-}
+  }  // r < n_alive
 
-// ------------------------------------------------------------------------------------------
-// K2: ordered compaction of the alive list, one CTA.
-// Survivors keep their relative order (the reference's continue_idx[~stopping]); rank r gets
-// dest[r] = its row in state[next]: survivors first, stopped rows after them.
-// ------------------------------------------------------------------------------------------
-constexpr int kCompactThreads = 1024;
-
-__global__ void __launch_bounds__(kCompactThreads) compact_kernel(ttl_batch b, int cur, int refill) {
-  __shared__ int s_keep[kCompactThreads];
-  __shared__ int s_stop[kCompactThreads];
-  const int n = b.ctrl[cur];
-  const int tid = threadIdx.x;
-  int per = (n + kCompactThreads - 1) / kCompactThreads;
-  per = (per + 15) & ~15;  // whole uint4 of flags per thread; stop[] is cudaMalloc-aligned
-  const int beg = min(n, tid * per), end = min(n, beg + per);
-  int n_stop = 0;
-  for (int r = beg; r < end; r += 16) {
-    const uint4 q = *reinterpret_cast<const uint4*>(b.stop + r);
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int left = end - (r + 4 * k);
-      uint32_t x = w[k];
-      if (left < 4) x &= left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left)));
-      n_stop += __popc(x & 0x01010101u);
-    }
-  }
-  s_keep[tid] = (end - beg) - n_stop;
-  s_stop[tid] = n_stop;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (int off = 1; off < kCompactThreads; off <<= 1) {
-    int a = 0, c = 0;
-    if (tid >= off) { a = s_keep[tid - off]; c = s_stop[tid - off]; }
-    __syncthreads();
-    s_keep[tid] += a;
-    s_stop[tid] += c;
-    __syncthreads();
-  }
-  const int total_keep = s_keep[kCompactThreads - 1];
-  int kpos = s_keep[tid] - ((end - beg) - n_stop);
-  int spos = total_keep + s_stop[tid] - n_stop;
-  const int* alive_cur = b.alive[cur];
-  int* alive_next = b.alive[cur ^ 1];
-  for (int r = beg; r < end; ++r) {
-    if (b.stop[r]) {
-      b.dest[r] = spos++;
-    } else {
-      b.dest[r] = kpos;
-      alive_next[kpos++] = alive_cur[r];
-    }
-  }
-  // streaming refill: freed slots take the next unseeded rows (their state rows are built
-  // by build_state_kernel with L = 1)
-  int n_new = 0;
-  const int cursor = b.ctrl[6];
-  if (refill) {
-    n_new = min(b.n_slots - total_keep, b.n - cursor);
-    n_new = max(n_new, 0);
-    for (int j = tid; j < n_new; j += kCompactThreads) alive_next[total_keep + j] = cursor + j;
+  // ---- ordered-compaction bookkeeping: stops per group of kGroup ranks; the last CTA scans ----
+  __shared__ int s_is_last;
+  __shared__ int s_part[kGroup];
+  const int grp_stops = __syncthreads_count(stopped);
+  if (threadIdx.x == 0) {
+    b.grp_stops[blockIdx.x] = grp_stops;
+    __threadfence();
+    const int ticket = atomicAdd(b.ctrl + 7, 1);
+    s_is_last = ticket == (int)gridDim.x - 1;
   }
   __syncthreads();
-  if (tid == 0) {
-    b.ctrl[cur ^ 1] = total_keep + n_new;
+  if (!s_is_last) return;
+  __threadfence();
+  const int ngrp = gridDim.x;
+  const int per = (ngrp + kGroup - 1) / kGroup;
+  const int g0 = min(ngrp, (int)threadIdx.x * per), g1 = min(ngrp, g0 + per);
+  int keep = 0;
+  for (int g = g0; g < g1; ++g) {
+    const int rows = max(0, min(kGroup, n_alive - g * kGroup));
+    keep += rows - __ldcg(b.grp_stops + g);
+  }
+  s_part[threadIdx.x] = keep;
+  __syncthreads();
+  for (int off = 1; off < kGroup; off <<= 1) {
+    int a = 0;
+    if ((int)threadIdx.x >= off) a = s_part[threadIdx.x - off];
+    __syncthreads();
+    s_part[threadIdx.x] += a;
+    __syncthreads();
+  }
+  int pos = s_part[threadIdx.x] - keep;
+  for (int g = g0; g < g1; ++g) {
+    b.grp_prefix[g] = pos;
+    const int rows = max(0, min(kGroup, n_alive - g * kGroup));
+    pos += rows - __ldcg(b.grp_stops + g);
+  }
+  if (threadIdx.x == kGroup - 1) {
+    const int total_keep = s_part[kGroup - 1];
+    const int cursor = b.ctrl[6];
+    int n_new = 0;
+    if (prm.refill) n_new = max(0, min(b.n_slots - total_keep, b.n - cursor));
+    b.ctrl[cur ^ 1] = total_keep + n_new;   // alive count of the next list
     b.ctrl[2] = b.ctrl[2] + 1;
-    b.ctrl[3] = n;
+    b.ctrl[3] = n_alive;
     b.ctrl[6] = cursor + n_new;
+    b.ctrl[7] = 0;
+    b.ctrl[8] = total_keep;
+    b.ctrl[9] = n_new;
+    b.ctrl[10] = cursor;
     long long* total = reinterpret_cast<long long*>(b.ctrl + 4);
-    *total += n;
+    *total += n_alive;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: state rows.  One warp per streamline.
+// K3: state rows.  One warp per rank of the OLD alive list.
 // ------------------------------------------------------------------------------------------
-constexpr int kStateWarps = 8;
-constexpr int kMaxStateLd = 640;   // floats staged per row (>= ld_state)
+constexpr int kStateWarps = 4;
+constexpr int kMaxStateLd = 640;   // floats per state row (>= ld_state)
 constexpr int kMaxDirPts = 104;    // n_dirs + 1 points staged (n_dirs <= 103)
+constexpr int kMaxCP = 48;         // padded channels staged per corner voxel
+constexpr int kCornerFloats = 56 * kMaxCP;                 // 7 points x 8 corners
+constexpr int kWarpSmemFloats = kCornerFloats + 64 + 64 + kMaxDirPts * 3 + 8;   // corners, weights, voxel ids, points
+constexpr int kWarpSmemBytes = ((kWarpSmemFloats * 4 + 127) / 128) * 128;
 
 struct TriAxis {  // one axis of one neighbourhood point
   int i0, i1;     // clamped lower / upper lattice index
@@ -396,150 +396,179 @@ __device__ __forceinline__ void tri_weights(float dx, float dy, float dz, float 
   w[7] = xyz;                                       // 111
 }
 
-// Builds one state row into s_row (shared, >= ld floats) for the streamline whose points start
-// at P and which has L points.  All 32 lanes of the warp participate.
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// Builds one state row for the streamline whose points start at P (L points) and writes
+//   out_f32 [0, n_f32)   fp32: 7*C SH values | 3*n_dirs previous directions | zero padding
+//   out_bf16 [0, n_bf16) the same values rounded to bf16 (actor operand), zero padded
+// smem_f: this warp's private staging area (kWarpSmemBytes).  All 32 lanes participate.
 __device__ void build_state_row(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
-                                float* s_row, float* s_pts, int ld, int lane) {
+                                float* __restrict__ out_f32, int n_f32,
+                                __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f, int lane) {
+  float* s_corner = smem_f;                       // [56][CP]
+  float* s_w = smem_f + kCornerFloats;            // [56] trilinear weights
+  int* s_vox = reinterpret_cast<int*>(s_w + 64);  // [56] voxel index
+  float* s_pts = s_w + 128;                       // [(n_dirs+1)*3]
+  const int C = v.C, CP = v.CP, CP4 = CP >> 2;
   const float* tip = P + (size_t)(L - 1) * 3;
   const float tx = tip[0], ty = tip[1], tz = tip[2];
   const float rad = (float)prm.step_vox;  // env.py:207-213, float32 neighbourhood vectors
-  const int CP4 = v.CP >> 2;
-  const int C = v.C;
-  const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
 
-  // lanes 0-15 take the x-low corners (000..011), lanes 16-31 the x-high corners (100..111)
-  const int half = lane >> 4;
-  const int cl = lane & 15;
-  for (int c4b = 0; c4b < CP4; c4b += 16) {   // warp-uniform trip count: shuffles below need all lanes
-    const bool active = c4b + cl < CP4;
-    const int c4 = active ? c4b + cl : 0;
-    float4 acc[7];
+  // phase 0: lane i (and i+32) owns corner i = 8*p + c: voxel index and weight
+  for (int i = lane; i < 56; i += 32) {
+    const int p = i >> 3, c = i & 7;
+    // neighbourhood order env.py:210-213: 0, +x, +y, +z, -x, -y, -z
+    float cx = tx, cy = ty, cz = tz;
+    if (p == 1) cx = __fadd_rn(tx, rad);
+    if (p == 2) cy = __fadd_rn(ty, rad);
+    if (p == 3) cz = __fadd_rn(tz, rad);
+    if (p == 4) cx = __fadd_rn(tx, -rad);
+    if (p == 5) cy = __fadd_rn(ty, -rad);
+    if (p == 6) cz = __fadd_rn(tz, -rad);
+    const TriAxis X = tri_axis(cx, v.X), Y = tri_axis(cy, v.Y), Z = tri_axis(cz, v.Z);
+    float w[8];
+    tri_weights(X.d, Y.d, Z.d, w);
+    float wc = w[0];
 #pragma unroll
-    for (int p = 0; p < 7; ++p) {
-      // neighbourhood order env.py:210-213: 0, +x, +y, +z, -x, -y, -z
-      float cx = tx, cy = ty, cz = tz;
-      if (p == 1) cx = __fadd_rn(tx, rad);
-      if (p == 2) cy = __fadd_rn(ty, rad);
-      if (p == 3) cz = __fadd_rn(tz, rad);
-      if (p == 4) cx = __fadd_rn(tx, -rad);
-      if (p == 5) cy = __fadd_rn(ty, -rad);
-      if (p == 6) cz = __fadd_rn(tz, -rad);
-      const TriAxis X = tri_axis(cx, v.X), Y = tri_axis(cy, v.Y), Z = tri_axis(cz, v.Z);
-      float w[8];
-      tri_weights(X.d, Y.d, Z.d, w);
-      const int xi = half ? X.i1 : X.i0;
-      const size_t base_y0 = ((size_t)xi * v.Y + Y.i0) * v.Z;
-      const size_t base_y1 = ((size_t)xi * v.Y + Y.i1) * v.Z;
-      float4 a00 = make_float4(0.f, 0.f, 0.f, 0.f), a01 = a00, a10 = a00, a11 = a00;
-      if (active) {
-        a00 = __ldg(vol4 + (base_y0 + Z.i0) * CP4 + c4);
-        a01 = __ldg(vol4 + (base_y0 + Z.i1) * CP4 + c4);
-        a10 = __ldg(vol4 + (base_y1 + Z.i0) * CP4 + c4);
-        a11 = __ldg(vol4 + (base_y1 + Z.i1) * CP4 + c4);
-      }
-      const float w00 = half ? w[4] : w[0], w01 = half ? w[5] : w[1], w10 = half ? w[6] : w[2],
-                  w11 = half ? w[7] : w[3];
-      float4 s;
-      s.x = a00.x * w00 + a01.x * w01 + a10.x * w10 + a11.x * w11;
-      s.y = a00.y * w00 + a01.y * w01 + a10.y * w10 + a11.y * w11;
-      s.z = a00.z * w00 + a01.z * w01 + a10.z * w10 + a11.z * w11;
-      s.w = a00.w * w00 + a01.w * w01 + a10.w * w10 + a11.w * w11;
-      acc[p] = s;
-    }
-#pragma unroll
-    for (int p = 0; p < 7; ++p) {
-      acc[p].x += __shfl_down_sync(0xffffffffu, acc[p].x, 16);
-      acc[p].y += __shfl_down_sync(0xffffffffu, acc[p].y, 16);
-      acc[p].z += __shfl_down_sync(0xffffffffu, acc[p].z, 16);
-      acc[p].w += __shfl_down_sync(0xffffffffu, acc[p].w, 16);
-    }
-    if (half == 0 && active) {
-#pragma unroll
-      for (int p = 0; p < 7; ++p) {
-        float* o = s_row + p * C + c4 * 4;
-        const int ch = c4 * 4;
-        if (ch + 0 < C) o[0] = acc[p].x;
-        if (ch + 1 < C) o[1] = acc[p].y;
-        if (ch + 2 < C) o[2] = acc[p].z;
-        if (ch + 3 < C) o[3] = acc[p].w;
-      }
-    }
+    for (int k = 1; k < 8; ++k) wc = (c == k) ? w[k] : wc;
+    const int xi = (c & 4) ? X.i1 : X.i0, yi = (c & 2) ? Y.i1 : Y.i0, zi = (c & 1) ? Z.i1 : Z.i0;
+    s_w[i] = wc;
+    s_vox[i] = (xi * v.Y + yi) * v.Z + zi;
   }
-  // previous directions, newest first, zero padded (env.py:549-563)
-  const int S = 7 * C;
+  __syncwarp();
+
+  // phase 1: every (corner, 16-byte chunk) goes straight from the volume into shared memory
+  const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
+  const uint32_t s_corner_u32 = ttl_smem_u32(s_corner);
+  const int n_items = 56 * CP4;
+  for (int it = lane; it < n_items; it += 32) {
+    const int corner = it / CP4, chunk = it - corner * CP4;
+    cp_async16(s_corner_u32 + (uint32_t)(corner * CP + chunk * 4) * 4u,
+               vol4 + (size_t)s_vox[corner] * CP4 + chunk);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // previous points (needed for the direction part) while the gather is in flight
   const int nd = prm.n_dirs;
   const int npts = min(L, nd + 1);
   const float* src = P + (size_t)(L - npts) * 3;
   for (int j = lane; j < npts * 3; j += 32) s_pts[j] = src[j];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
-  for (int j = lane; j < nd * 3; j += 32) {
-    const int k = j / 3, c = j - 3 * k;
+
+  // phase 2: lane l produces elements l, l+32, ... of the row
+  const int S = 7 * C;
+  const int n_out = max(n_f32, n_bf16);
+  for (int o0 = 0; o0 < n_out; o0 += 32) {
+    const int o = o0 + lane;
     float val = 0.f;
-    if (k < npts - 1) val = __fsub_rn(s_pts[(npts - 1 - k) * 3 + c], s_pts[(npts - 2 - k) * 3 + c]);
-    s_row[S + j] = val;
+    if (o < S) {
+      const int p = o / C, ch = o - p * C;
+      const float* cw = s_w + p * 8;
+      const float* cv = s_corner + p * 8 * CP + ch;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) val = fmaf(cw[k], cv[k * CP], val);
+    } else if (o < S + nd * 3) {
+      // previous directions, newest first, zero padded (env.py:549-563)
+      const int j = o - S;
+      const int k = j / 3, c = j - 3 * k;
+      if (k < npts - 1) val = __fsub_rn(s_pts[(npts - 1 - k) * 3 + c], s_pts[(npts - 2 - k) * 3 + c]);
+    }
+    if (out_f32 && o < n_f32) out_f32[o] = val;
+    if (out_bf16) {
+      const float nxt = __shfl_down_sync(0xffffffffu, val, 1);
+      if (!(lane & 1) && o < n_bf16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(val, nxt);
+        *reinterpret_cast<__nv_bfloat162*>(out_bf16 + o) = h;
+      }
+    }
   }
-  for (int j = S + nd * 3 + lane; j < ld; j += 32) s_row[j] = 0.f;
   __syncwarp();
 }
 
-__device__ __forceinline__ void store_state_row(const float* s_row, float* dst, int ld, int lane) {
-  const float4* s4 = reinterpret_cast<const float4*>(s_row);
-  float4* d4 = reinterpret_cast<float4*>(dst);
-  for (int j = lane; j < (ld >> 2); j += 32) d4[j] = s4[j];
-}
-
-// Warps [0, u_new) build the rows of the NEW alive list (survivors in order, then refilled
-// rows): rank r' -> state[next][r'].  Warps [u_new, u_new + u_old) exist only in parity mode
-// (state_stopped) and build the rows of streamlines that stopped this step at dest[r].
-__global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volume v, ttl_params prm,
-                                                                       ttl_batch b, int cur, int u_new) {
-  __shared__ __align__(16) float s_rows[kStateWarps][kMaxStateLd];
-  __shared__ float s_pts[kStateWarps][kMaxDirPts * 3];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w = blockIdx.x * kStateWarps + warp;
-  int row, dst;
-  if (w < u_new) {
-    if (w >= b.ctrl[cur ^ 1]) return;
-    row = b.alive[cur ^ 1][w];
-    dst = w;
-  } else {
-    const int r = w - u_new;
-    if (r >= b.ctrl[cur] || !b.stop[r]) return;
-    row = b.alive[cur][r];
-    dst = b.dest[r];
+// rank r of the old alive list -> (number of survivors before r); all lanes return the value.
+__device__ __forceinline__ int survivors_before(const ttl_batch& b, int r, int n_old, int lane) {
+  const int g = r / kGroup, base = g * kGroup, pos = r - base;
+  // 128 stop bytes of the group, 4 per lane
+  const uint32_t word = *reinterpret_cast<const uint32_t*>(b.stop + base + 4 * lane);
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int q = 4 * lane + k;
+    const bool stopped = (word >> (8 * k)) & 1u;
+    cnt += (q < pos && base + q < n_old && !stopped) ? 1 : 0;
   }
-  const int L = b.npts[row];
-  const float* P = b.points + (size_t)row * b.max_pts * 3;
-  build_state_row(v, prm, P, L, s_rows[warp], s_pts[warp], b.ld_state, lane);
-  store_state_row(s_rows[warp], b.state[cur ^ 1] + (size_t)dst * b.ld_state, b.ld_state, lane);
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  return b.grp_prefix[g] + cnt;
 }
 
-// reset: alive[0] = identity, dest = identity, state goes to state[0]
+__global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volume v, ttl_params prm,
+                                                                       ttl_batch b, int cur) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * kWarpSmemBytes);
+  const int r = blockIdx.x * kStateWarps + warp;
+  const int n_old = b.ctrl[3];
+  if (r >= n_old) return;
+  const int keep_before = survivors_before(b, r, n_old, lane);
+  const bool stopped = b.stop[r] != 0;
+  int row, dst, L;
+  if (!stopped) {
+    row = b.alive[cur][r];
+    dst = keep_before;
+    L = b.npts[row];
+    if (lane == 0) { b.alive[cur ^ 1][dst] = row; b.dest[r] = dst; }
+  } else {
+    const int total_keep = b.ctrl[8];
+    const int j = r - keep_before;        // how many stopped before this rank
+    dst = total_keep + j;
+    if (lane == 0) b.dest[r] = dst;
+    if (j < b.ctrl[9]) {                  // streaming refill: this freed slot takes a fresh seed
+      row = b.ctrl[10] + j;
+      L = 1;
+      if (lane == 0) b.alive[cur ^ 1][dst] = row;
+    } else if (prm.state_stopped) {       // parity mode: state of the streamline that just stopped
+      row = b.alive[cur][r];
+      L = b.npts[row];
+    } else {
+      return;
+    }
+  }
+  const float* P = b.points + (size_t)row * b.max_pts * 3;
+  __nv_bfloat16* o16 = b.state_bf16[cur ^ 1]
+                           ? reinterpret_cast<__nv_bfloat16*>(b.state_bf16[cur ^ 1]) + (size_t)dst * b.ld_bf16
+                           : nullptr;
+  build_state_row(v, prm, P, L, b.state[cur ^ 1] + (size_t)dst * b.ld_state, b.ld_state, o16, b.ld_bf16,
+                  smem_f, lane);
+}
+
+// reset: alive[0] = identity, state goes to state[0]
 __global__ void __launch_bounds__(kStateWarps * 32) reset_state_kernel(ttl_volume v, ttl_params prm,
                                                                        ttl_batch b) {
-  __shared__ __align__(16) float s_rows[kStateWarps][kMaxStateLd];
-  __shared__ float s_pts[kStateWarps][kMaxDirPts * 3];
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * kWarpSmemBytes);
   const int r = blockIdx.x * kStateWarps + warp;
   if (r >= min(b.n, b.n_slots)) return;
   const float* P = b.points + (size_t)r * b.max_pts * 3;
-  build_state_row(v, prm, P, 1, s_rows[warp], s_pts[warp], b.ld_state, lane);
-  store_state_row(s_rows[warp], b.state[0] + (size_t)r * b.ld_state, b.ld_state, lane);
+  __nv_bfloat16* o16 = b.state_bf16[0]
+                           ? reinterpret_cast<__nv_bfloat16*>(b.state_bf16[0]) + (size_t)r * b.ld_bf16
+                           : nullptr;
+  build_state_row(v, prm, P, 1, b.state[0] + (size_t)r * b.ld_state, b.ld_state, o16, b.ld_bf16, smem_f, lane);
 }
 
 // stand-alone _format_state for arbitrary streamlines [n][L][3]
 __global__ void __launch_bounds__(kStateWarps * 32) format_state_kernel(ttl_volume v, ttl_params prm,
                                                                         const float* points, int n,
-                                                                        int L, float* out, int ld_out,
-                                                                        int ld_row) {
-  __shared__ __align__(16) float s_rows[kStateWarps][kMaxStateLd];
-  __shared__ float s_pts[kStateWarps][kMaxDirPts * 3];
+                                                                        int L, float* out, int ld_out) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * kWarpSmemBytes);
   const int r = blockIdx.x * kStateWarps + warp;
   if (r >= n) return;
-  build_state_row(v, prm, points + (size_t)r * L * 3, L, s_rows[warp], s_pts[warp], ld_row, lane);
   const int S = 7 * v.C + 3 * prm.n_dirs;
-  for (int j = lane; j < S; j += 32) out[(size_t)r * ld_out + j] = s_rows[warp][j];
+  build_state_row(v, prm, points + (size_t)r * L * 3, L, out + (size_t)r * ld_out, S, nullptr, 0, smem_f, lane);
 }
 
 __global__ void stopping_flags_kernel(ttl_volume v, ttl_params prm, const float* points, int n, int L,
@@ -620,9 +649,24 @@ __global__ void __launch_bounds__(256) pack_kernel(ttl_batch b, const long long*
   for (int j = lane; j < len * 3; j += 32) d[j] = s[j];
 }
 
+constexpr int kStateSmem = kStateWarps * kWarpSmemBytes;
+
+int state_kernels_ready() {
+  static bool done = false;
+  if (done) return 0;
+  cudaError_t e = cudaFuncSetAttribute(build_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(reset_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(format_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  if (e != cudaSuccess) return (int)e;
+  done = true;
+  return 0;
+}
+
 int check_common(const ttl_volume* vol, const ttl_params* prm) {
   if (!vol || !prm) return TTL_ERR_BAD_ARG;
-  if ((vol->CP & 3) || vol->CP < vol->C || vol->CP > 128) return TTL_ERR_UNSUPPORTED;
+  if ((vol->CP & 3) || vol->CP < vol->C || vol->CP > kMaxCP) return TTL_ERR_UNSUPPORTED;
   if (prm->n_dirs + 1 > kMaxDirPts) return TTL_ERR_UNSUPPORTED;
   if (7 * vol->C + 3 * prm->n_dirs > kMaxStateLd) return TTL_ERR_UNSUPPORTED;
   return 0;
@@ -656,7 +700,10 @@ int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch*
   const int n_init = b->n > b->n_slots ? b->n : b->n_slots;
   TTL_LAUNCH("reset_kernel", s, reset_kernel<<<ttl_div_up(n_init, 256), 256, 0, s>>>(*b, seeds));
   const int n0 = b->n < b->n_slots ? b->n : b->n_slots;
-  TTL_LAUNCH("reset_state_kernel", s, reset_state_kernel<<<ttl_div_up(n0, kStateWarps), kStateWarps * 32, 0, s>>>(*vol, *prm, *b));
+  rc = state_kernels_ready();
+  if (rc) return rc;
+  TTL_LAUNCH("reset_state_kernel", s,
+             reset_state_kernel<<<ttl_div_up(n0, kStateWarps), kStateWarps * 32, kStateSmem, s>>>(*vol, *prm, *b));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -671,13 +718,14 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   if (prm->refill && prm->state_stopped) return TTL_ERR_BAD_ARG;
   if (n_upper <= 0) return 0;
   if (n_upper > b->n_slots) n_upper = b->n_slots;
+  if (ttl_div_up(n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->grp_prefix) return TTL_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<<<ttl_div_up(n_upper, 128), 128, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise));
-  TTL_LAUNCH("compact_kernel", s, compact_kernel<<<1, kCompactThreads, 0, s>>>(*b, cur, prm->refill));
-  const int u_new = prm->refill ? b->n_slots : n_upper;
-  const int u_old = prm->state_stopped ? n_upper : 0;
-  TTL_LAUNCH("build_state_kernel", s, build_state_kernel<<<ttl_div_up(u_new + u_old, kStateWarps), kStateWarps * 32, 0, s>>>(*vol, *prm, *b, cur,
-                                                                                       u_new));
+  rc = state_kernels_ready();
+  if (rc) return rc;
+  TTL_LAUNCH("build_state_kernel", s,
+             build_state_kernel<<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateSmem, s>>>(*vol, *prm, *b,
+                                                                                                     cur));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -698,10 +746,11 @@ int ttl_format_state(const ttl_volume* vol, const ttl_params* prm, const float* 
   if (rc) return rc;
   if (!points || !out || L < 1) return TTL_ERR_BAD_ARG;
   if (n <= 0) return 0;
-  const int S = 7 * vol->C + 3 * prm->n_dirs;
-  const int ld_row = (S + 3) & ~3;
-  TTL_LAUNCH("format_state_kernel", (cudaStream_t)stream, format_state_kernel<<<ttl_div_up(n, kStateWarps), kStateWarps * 32, 0, (cudaStream_t)stream>>>(
-      *vol, *prm, points, n, L, out, ld_out, ld_row));
+  rc = state_kernels_ready();
+  if (rc) return rc;
+  TTL_LAUNCH("format_state_kernel", (cudaStream_t)stream,
+             format_state_kernel<<<ttl_div_up(n, kStateWarps), kStateWarps * 32, kStateSmem, (cudaStream_t)stream>>>(
+                 *vol, *prm, points, n, L, out, ld_out));
   TTL_CHECK_LAST();
   return 0;
 }

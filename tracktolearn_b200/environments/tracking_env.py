@@ -36,21 +36,28 @@ class _BatchBuffers(object):
         self.state_size = state_size
         self.ld_state = (state_size + 3) // 4 * 4
         i32 = dict(dtype=torch.int32, device=device)
-        pad = slots + 16             # the compaction kernel reads stop[] 16 bytes at a time
+        pad = (slots + 127) // 128 * 128 + 16   # stop[] is read in whole 128-rank groups
         self.points = torch.zeros((rows, max_pts, 3), dtype=torch.float32, device=device)
         self.flags = torch.zeros((rows,), **i32)
         self.lengths = torch.zeros((rows,), **i32)
         self.npts = torch.zeros((rows,), **i32)
         self.dones = torch.zeros((rows,), dtype=torch.uint8, device=device)
         self.alive = [torch.zeros((pad,), **i32), torch.zeros((pad,), **i32)]
-        self.ctrl = torch.zeros((8,), **i32)
+        self.ctrl = torch.zeros((16,), **i32)
         self.stop = torch.zeros((pad,), dtype=torch.uint8, device=device)
         self.dest = torch.zeros((pad,), **i32)
         self.step_flags = torch.zeros((pad,), **i32)
         self.reward = torch.zeros((pad,), dtype=torch.float32, device=device)
         self.state = [torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device),
                       torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device)]
-        self.ctrl_host = torch.zeros((8,), dtype=torch.int32).pin_memory()
+        self.ctrl_host = torch.zeros((16,), dtype=torch.int32).pin_memory()
+        # bf16 copy of the state rows, zero padded to a multiple of 64: the actor's TMA operand
+        self.ld_bf16 = (state_size + 63) // 64 * 64
+        self.state_bf16 = [torch.zeros((slots, self.ld_bf16), dtype=torch.bfloat16, device=device),
+                           torch.zeros((slots, self.ld_bf16), dtype=torch.bfloat16, device=device)]
+        self.max_groups = (slots + 127) // 128 + 1
+        self.grp_stops = torch.zeros((self.max_groups,), **i32)
+        self.grp_prefix = torch.zeros((self.max_groups,), **i32)
 
     def as_struct(self, n, n_slots):
         b = _lib.Batch(n=n, n_slots=n_slots, capacity=self.rows, max_pts=self.max_pts,
@@ -59,7 +66,11 @@ class _BatchBuffers(object):
                        lengths=self.lengths.data_ptr(), npts=self.npts.data_ptr(),
                        dones=self.dones.data_ptr(), ctrl=self.ctrl.data_ptr(),
                        stop=self.stop.data_ptr(), dest=self.dest.data_ptr(),
-                       step_flags=self.step_flags.data_ptr(), reward=self.reward.data_ptr())
+                       step_flags=self.step_flags.data_ptr(), reward=self.reward.data_ptr(),
+                       ld_bf16=self.ld_bf16, max_groups=self.max_groups,
+                       grp_stops=self.grp_stops.data_ptr(), grp_prefix=self.grp_prefix.data_ptr())
+        b.state_bf16[0] = self.state_bf16[0].data_ptr()
+        b.state_bf16[1] = self.state_bf16[1].data_ptr()
         b.alive[0] = self.alive[0].data_ptr()
         b.alive[1] = self.alive[1].data_ptr()
         b.state[0] = self.state[0].data_ptr()
@@ -176,6 +187,11 @@ class TrackingEnvironment(BaseEnv):
     def current_state(self):
         """State rows of the alive set, [n_alive_upper_bound, state_size] view (no sync)."""
         return self._state_view(self._cur, self._n_alive_host)
+
+    def current_state_bf16(self):
+        """bf16, zero-padded copy of ``current_state()`` ([slots, round_up(state_size, 64)]) that
+        the step kernel writes alongside the fp32 rows; the actor's first layer reads it by TMA."""
+        return self._batch.state_bf16[self._cur]
 
     def alive_count_tensor(self):
         """Device int32 tensor holding the alive count of the current list."""
