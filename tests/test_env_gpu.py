@@ -155,3 +155,36 @@ def test_device_protocol_equals_reference_protocol():
     np.testing.assert_array_equal(envA.flags, envB.flags)
     np.testing.assert_array_equal(envA.lengths, envB.lengths)
     np.testing.assert_array_equal(envA.get_streamlines().data, envB.get_streamlines().data)
+
+
+def test_format_state_generic_channel_count():
+    """Order-6 volume (28 coefficients): exercises the non-specialised state path."""
+    from tracktolearn_b200.datasets.utils import MRIDataVolume
+    from tracktolearn_b200.environments import TrackingEnvironment
+    rs = np.random.RandomState(4)
+    shape = (10, 11, 12)
+    sh = rs.normal(size=shape + (28,)).astype(np.float32)
+    mask = np.ones(shape, dtype=np.uint8)
+    affine = np.eye(4)
+    dto = {'n_dirs': 100, 'theta': 30.0, 'npv': 1, 'binary_stopping_threshold': 0.1, 'step_size': 0.6,
+           'min_length': 1.0, 'max_length': 12.0, 'oracle_checkpoint': None,
+           'oracle_stopping_criterion': False, 'scoring_data': None, 'compute_reward': False,
+           'alignment_weighting': 0.0, 'oracle_bonus': 0.0, 'rng': np.random.RandomState(0),
+           'device': torch.device('cuda:0'), 'target_sh_order': 6, 'noise': 0.0, 'fa_map': None}
+    env = TrackingEnvironment((MRIDataVolume(sh, affine), MRIDataVolume(mask, affine),
+                               MRIDataVolume(mask, affine), None, affine), 'testing', dto)
+    assert env.get_state_size() == 7 * 28 + 300
+    pts = (rs.uniform(-1.0, 12.0, size=(200, 1, 3)) + np.cumsum(rs.normal(scale=0.4, size=(200, 9, 3)), 1)).astype(np.float32)
+    ref = O.format_state(sh, pts, O.neighborhood_directions(0.6), 100)
+    got = env._format_state(pts).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=STATE_TOL)
+    # and through reset/step with the oracle env
+    seeds = rs.uniform(2, 8, size=(64, 3))
+    env.seeds = seeds
+    renv = O.OracleEnv(sh, mask, seeds, 1.0, 0.6, max_length_mm=12.0, noisy=False)
+    np.testing.assert_allclose(env.reset(0, 64).cpu().numpy(), renv.reset(0, 64), rtol=0, atol=STATE_TOL)
+    act = rs.normal(size=(64, 3)).astype(np.float32)
+    sg, _, dg, _ = env.step(act)
+    sr, _, dr, _ = renv.step(act)
+    np.testing.assert_array_equal(dg, dr)
+    np.testing.assert_allclose(sg.cpu().numpy(), sr, rtol=0, atol=STATE_TOL)

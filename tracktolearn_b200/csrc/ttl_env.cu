@@ -404,7 +404,7 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) 
 //   out_f32 [0, n_f32)   fp32: 7*C SH values | 3*n_dirs previous directions | zero padding
 //   out_bf16 [0, n_bf16) the same values rounded to bf16 (actor operand), zero padded
 // smem_f: this warp's private staging area (kWarpSmemBytes).  All 32 lanes participate.
-__device__ void build_state_row(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
+__device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
                                 float* __restrict__ out_f32, int n_f32,
                                 __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f, int lane) {
   float* s_corner = smem_f;                       // [56][CP]
@@ -485,6 +485,148 @@ __device__ void build_state_row(const ttl_volume& v, const ttl_params& prm, cons
     }
   }
   __syncwarp();
+}
+
+
+// Fast path for the order-8 volume (C = 45 coefficients padded to CP = 48): every offset is a
+// compile-time constant, the gather is issued as 28 x (LDS + IMAD.WIDE + LDGSTS.128) per lane,
+// the interpolation runs on float4 (84 work items per row) and the row leaves through shared
+// memory as 16-byte stores.  ~900 warp instructions per row instead of ~2300.
+__device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
+                                    float* __restrict__ out_f32, int n_f32,
+                                    __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f, int lane) {
+  constexpr int C = 45, CP = 48, CP4 = 12, S = 7 * C;
+  float* s_corner = smem_f;                       // [56][48]; reused as the output row afterwards
+  float* s_w = smem_f + kCornerFloats;            // [56] trilinear weights
+  int* s_vox = reinterpret_cast<int*>(s_w + 64);  // [56] voxel index
+  float* s_pts = s_w + 128;                       // [(n_dirs+1)*3]
+  const float* tip = P + (size_t)(L - 1) * 3;
+  const float tx = tip[0], ty = tip[1], tz = tip[2];
+  const float rad = (float)prm.step_vox;
+
+  // phase 0: lane i (and i+32) owns corner i = 8*p + c: voxel index and weight
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int i = lane + 32 * rep;
+    if (i < 56) {
+      const int p = i >> 3, c = i & 7;
+      float cx = tx, cy = ty, cz = tz;
+      if (p == 1) cx = __fadd_rn(tx, rad);
+      if (p == 2) cy = __fadd_rn(ty, rad);
+      if (p == 3) cz = __fadd_rn(tz, rad);
+      if (p == 4) cx = __fadd_rn(tx, -rad);
+      if (p == 5) cy = __fadd_rn(ty, -rad);
+      if (p == 6) cz = __fadd_rn(tz, -rad);
+      const TriAxis X = tri_axis(cx, v.X), Y = tri_axis(cy, v.Y), Z = tri_axis(cz, v.Z);
+      float w[8];
+      tri_weights(X.d, Y.d, Z.d, w);
+      float wc = w[0];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) wc = (c == k) ? w[k] : wc;
+      const int xi = (c & 4) ? X.i1 : X.i0, yi = (c & 2) ? Y.i1 : Y.i0, zi = (c & 1) ? Z.i1 : Z.i0;
+      s_w[i] = wc;
+      s_vox[i] = (xi * v.Y + yi) * v.Z + zi;
+    }
+  }
+  __syncwarp();
+
+  // phase 1: lanes 0-11 / 12-23 stream the 12 chunks of corner 2k / 2k+1, k = 0..27
+  const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
+  if (lane < 24) {
+    const int sub = lane >= 12 ? 1 : 0, chunk = lane - 12 * sub;
+    const uint32_t dst0 = ttl_smem_u32(s_corner) + (uint32_t)(sub * CP + chunk * 4) * 4u;
+    const float4* src0 = vol4 + chunk;
+    const int* vx = s_vox + sub;
+#pragma unroll
+    for (int k = 0; k < 28; ++k)
+      cp_async16(dst0 + (uint32_t)(k * 2 * CP * 4), src0 + (size_t)vx[2 * k] * CP4);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int nd = prm.n_dirs;
+  const int npts = min(L, nd + 1);
+  const float* src = P + (size_t)(L - npts) * 3;
+  for (int j = lane; j < npts * 3; j += 32) s_pts[j] = src[j];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  // phase 2: work item = (point p, chunk ck): 8 corners x float4
+  float4 res[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int item = lane + 32 * t;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (item < 7 * CP4) {
+      const int p = item / CP4, ck = item - p * CP4;
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + p * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + p * 8 + 4);
+      const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float4* cv = reinterpret_cast<const float4*>(s_corner + p * 8 * CP) + ck;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 a = cv[k * CP4];
+        acc.x = fmaf(wk[k], a.x, acc.x);
+        acc.y = fmaf(wk[k], a.y, acc.y);
+        acc.z = fmaf(wk[k], a.z, acc.z);
+        acc.w = fmaf(wk[k], a.w, acc.w);
+      }
+    }
+    res[t] = acc;
+  }
+  __syncwarp();   // every lane is done reading the corners: the region becomes the output row
+  float* s_row = s_corner;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int item = lane + 32 * t;
+    if (item < 7 * CP4) {
+      const int p = item / CP4, ck = item - p * CP4;
+      float* o = s_row + p * C + ck * 4;
+      o[0] = res[t].x;                       // channel 44 is the only valid one of chunk 11
+      if (ck < CP4 - 1) { o[1] = res[t].y; o[2] = res[t].z; o[3] = res[t].w; }
+    }
+  }
+  // previous directions, newest first, zero padded (env.py:549-563), then the row padding
+  for (int j = lane; j < nd * 3; j += 32) {
+    const int k = j / 3, c = j - 3 * k;
+    float val = 0.f;
+    if (k < npts - 1) val = __fsub_rn(s_pts[(npts - 1 - k) * 3 + c], s_pts[(npts - 2 - k) * 3 + c]);
+    s_row[S + j] = val;
+  }
+  const int n_pad = max(n_f32, n_bf16);
+  for (int j = S + nd * 3 + lane; j < n_pad; j += 32) s_row[j] = 0.f;
+  __syncwarp();
+
+  // copy-out
+  if (out_f32) {
+    if (((n_f32 & 3) == 0) && ((reinterpret_cast<uintptr_t>(out_f32) & 15) == 0)) {
+      const float4* s4 = reinterpret_cast<const float4*>(s_row);
+      float4* d4 = reinterpret_cast<float4*>(out_f32);
+      for (int q = lane; q < (n_f32 >> 2); q += 32) d4[q] = s4[q];
+    } else {
+      for (int q = lane; q < n_f32; q += 32) out_f32[q] = s_row[q];
+    }
+  }
+  if (out_bf16) {
+    uint4* d8 = reinterpret_cast<uint4*>(out_bf16);     // rows are 128-byte aligned (ld multiple of 64)
+    for (int q = lane; q < (n_bf16 >> 3); q += 32) {
+      const float4 a = *reinterpret_cast<const float4*>(s_row + 8 * q);
+      const float4 c = *reinterpret_cast<const float4*>(s_row + 8 * q + 4);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
+      d8[q] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                         *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void build_state_row(const ttl_volume& v, const ttl_params& prm, const float* P,
+                                                int L, float* __restrict__ out_f32, int n_f32,
+                                                __nv_bfloat16* __restrict__ out_bf16, int n_bf16,
+                                                float* smem_f, int lane) {
+  if (v.C == 45 && v.CP == 48 && max(n_f32, n_bf16) <= kMaxStateLd)
+    build_state_row_c45(v, prm, P, L, out_f32, n_f32, out_bf16, n_bf16, smem_f, lane);
+  else
+    build_state_row_generic(v, prm, P, L, out_f32, n_f32, out_bf16, n_bf16, smem_f, lane);
 }
 
 // rank r of the old alive list -> (number of survivors before r); all lanes return the value.
