@@ -358,12 +358,12 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
 // ------------------------------------------------------------------------------------------
 // K3: state rows.  One warp per rank of the OLD alive list.
 // ------------------------------------------------------------------------------------------
-constexpr int kStateWarps = 4;
+constexpr int kStateWarps = 8;
 constexpr int kMaxStateLd = 640;   // floats per state row (>= ld_state)
 constexpr int kMaxDirPts = 104;    // n_dirs + 1 points staged (n_dirs <= 103)
-constexpr int kMaxCP = 48;         // padded channels staged per corner voxel
-constexpr int kCornerFloats = 56 * kMaxCP;                 // 7 points x 8 corners
-constexpr int kWarpSmemFloats = kCornerFloats + 64 + 64 + kMaxDirPts * 3 + 8;   // corners, weights, voxel ids, points
+constexpr int kMaxCP = 128;        // padded channels per voxel
+// per-warp shared memory: 56 weights, 56 voxel ids, staged points, the output row
+constexpr int kWarpSmemFloats = 64 + 64 + kMaxDirPts * 3 + kMaxStateLd;
 constexpr int kWarpSmemBytes = ((kWarpSmemFloats * 4 + 127) / 128) * 128;
 
 struct TriAxis {  // one axis of one neighbourhood point
@@ -396,115 +396,12 @@ __device__ __forceinline__ void tri_weights(float dx, float dy, float dz, float 
   w[7] = xyz;                                       // 111
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-
-// Builds one state row for the streamline whose points start at P (L points) and writes
-//   out_f32 [0, n_f32)   fp32: 7*C SH values | 3*n_dirs previous directions | zero padding
-//   out_bf16 [0, n_bf16) the same values rounded to bf16 (actor operand), zero padded
-// smem_f: this warp's private staging area (kWarpSmemBytes).  All 32 lanes participate.
-__device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
-                                float* __restrict__ out_f32, int n_f32,
-                                __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f, int lane) {
-  float* s_corner = smem_f;                       // [56][CP]
-  float* s_w = smem_f + kCornerFloats;            // [56] trilinear weights
-  int* s_vox = reinterpret_cast<int*>(s_w + 64);  // [56] voxel index
-  float* s_pts = s_w + 128;                       // [(n_dirs+1)*3]
-  const int C = v.C, CP = v.CP, CP4 = CP >> 2;
-  const float* tip = P + (size_t)(L - 1) * 3;
+// phase 0 shared by both paths: lane i (and i+32) owns corner i = 8*p + c of the 7-point
+// neighbourhood (order env.py:210-213: 0, +x, +y, +z, -x, -y, -z): voxel index and weight.
+__device__ __forceinline__ void corner_table(const ttl_volume& v, const ttl_params& prm, const float* tip,
+                                             float* s_w, int* s_vox, int lane) {
   const float tx = tip[0], ty = tip[1], tz = tip[2];
   const float rad = (float)prm.step_vox;  // env.py:207-213, float32 neighbourhood vectors
-
-  // phase 0: lane i (and i+32) owns corner i = 8*p + c: voxel index and weight
-  for (int i = lane; i < 56; i += 32) {
-    const int p = i >> 3, c = i & 7;
-    // neighbourhood order env.py:210-213: 0, +x, +y, +z, -x, -y, -z
-    float cx = tx, cy = ty, cz = tz;
-    if (p == 1) cx = __fadd_rn(tx, rad);
-    if (p == 2) cy = __fadd_rn(ty, rad);
-    if (p == 3) cz = __fadd_rn(tz, rad);
-    if (p == 4) cx = __fadd_rn(tx, -rad);
-    if (p == 5) cy = __fadd_rn(ty, -rad);
-    if (p == 6) cz = __fadd_rn(tz, -rad);
-    const TriAxis X = tri_axis(cx, v.X), Y = tri_axis(cy, v.Y), Z = tri_axis(cz, v.Z);
-    float w[8];
-    tri_weights(X.d, Y.d, Z.d, w);
-    float wc = w[0];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) wc = (c == k) ? w[k] : wc;
-    const int xi = (c & 4) ? X.i1 : X.i0, yi = (c & 2) ? Y.i1 : Y.i0, zi = (c & 1) ? Z.i1 : Z.i0;
-    s_w[i] = wc;
-    s_vox[i] = (xi * v.Y + yi) * v.Z + zi;
-  }
-  __syncwarp();
-
-  // phase 1: every (corner, 16-byte chunk) goes straight from the volume into shared memory
-  const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
-  const uint32_t s_corner_u32 = ttl_smem_u32(s_corner);
-  const int n_items = 56 * CP4;
-  for (int it = lane; it < n_items; it += 32) {
-    const int corner = it / CP4, chunk = it - corner * CP4;
-    cp_async16(s_corner_u32 + (uint32_t)(corner * CP + chunk * 4) * 4u,
-               vol4 + (size_t)s_vox[corner] * CP4 + chunk);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  // previous points (needed for the direction part) while the gather is in flight
-  const int nd = prm.n_dirs;
-  const int npts = min(L, nd + 1);
-  const float* src = P + (size_t)(L - npts) * 3;
-  for (int j = lane; j < npts * 3; j += 32) s_pts[j] = src[j];
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
-
-  // phase 2: lane l produces elements l, l+32, ... of the row
-  const int S = 7 * C;
-  const int n_out = max(n_f32, n_bf16);
-  for (int o0 = 0; o0 < n_out; o0 += 32) {
-    const int o = o0 + lane;
-    float val = 0.f;
-    if (o < S) {
-      const int p = o / C, ch = o - p * C;
-      const float* cw = s_w + p * 8;
-      const float* cv = s_corner + p * 8 * CP + ch;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) val = fmaf(cw[k], cv[k * CP], val);
-    } else if (o < S + nd * 3) {
-      // previous directions, newest first, zero padded (env.py:549-563)
-      const int j = o - S;
-      const int k = j / 3, c = j - 3 * k;
-      if (k < npts - 1) val = __fsub_rn(s_pts[(npts - 1 - k) * 3 + c], s_pts[(npts - 2 - k) * 3 + c]);
-    }
-    if (out_f32 && o < n_f32) out_f32[o] = val;
-    if (out_bf16) {
-      const float nxt = __shfl_down_sync(0xffffffffu, val, 1);
-      if (!(lane & 1) && o < n_bf16) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(val, nxt);
-        *reinterpret_cast<__nv_bfloat162*>(out_bf16 + o) = h;
-      }
-    }
-  }
-  __syncwarp();
-}
-
-
-// Fast path for the order-8 volume (C = 45 coefficients padded to CP = 48): every offset is a
-// compile-time constant, the gather is issued as 28 x (LDS + IMAD.WIDE + LDGSTS.128) per lane,
-// the interpolation runs on float4 (84 work items per row) and the row leaves through shared
-// memory as 16-byte stores.  ~900 warp instructions per row instead of ~2300.
-__device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
-                                    float* __restrict__ out_f32, int n_f32,
-                                    __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f, int lane) {
-  constexpr int C = 45, CP = 48, CP4 = 12, S = 7 * C;
-  float* s_corner = smem_f;                       // [56][48]; reused as the output row afterwards
-  float* s_w = smem_f + kCornerFloats;            // [56] trilinear weights
-  int* s_vox = reinterpret_cast<int*>(s_w + 64);  // [56] voxel index
-  float* s_pts = s_w + 128;                       // [(n_dirs+1)*3]
-  const float* tip = P + (size_t)(L - 1) * 3;
-  const float tx = tip[0], ty = tip[1], tz = tip[2];
-  const float rad = (float)prm.step_vox;
-
-  // phase 0: lane i (and i+32) owns corner i = 8*p + c: voxel index and weight
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
     const int i = lane + 32 * rep;
@@ -528,60 +425,103 @@ __device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, 
       s_vox[i] = (xi * v.Y + yi) * v.Z + zi;
     }
   }
-  __syncwarp();
+}
 
-  // phase 1: lanes 0-11 / 12-23 stream the 12 chunks of corner 2k / 2k+1, k = 0..27
-  const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
-  if (lane < 24) {
-    const int sub = lane >= 12 ? 1 : 0, chunk = lane - 12 * sub;
-    const uint32_t dst0 = ttl_smem_u32(s_corner) + (uint32_t)(sub * CP + chunk * 4) * 4u;
-    const float4* src0 = vol4 + chunk;
-    const int* vx = s_vox + sub;
-#pragma unroll
-    for (int k = 0; k < 28; ++k)
-      cp_async16(dst0 + (uint32_t)(k * 2 * CP * 4), src0 + (size_t)vx[2 * k] * CP4);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
+// Builds one state row for the streamline whose points start at P (L points) and writes
+//   out_f32 [0, n_f32)   fp32: 7*C SH values | 3*n_dirs previous directions | zero padding
+//   out_bf16 [0, n_bf16) the same values rounded to bf16 (actor operand), zero padded
+// smem_f: this warp's private staging area (kWarpSmemBytes).  All 32 lanes participate.
+// Generic channel count: lane l produces elements l, l+32, ... with scalar gathers.
+__device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
+                                        float* __restrict__ out_f32, int n_f32,
+                                        __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f,
+                                        int lane) {
+  float* s_w = smem_f;
+  int* s_vox = reinterpret_cast<int*>(smem_f + 64);
+  float* s_pts = smem_f + 128;
+  const int C = v.C, CP = v.CP;
+  corner_table(v, prm, P + (size_t)(L - 1) * 3, s_w, s_vox, lane);
   const int nd = prm.n_dirs;
   const int npts = min(L, nd + 1);
   const float* src = P + (size_t)(L - npts) * 3;
   for (int j = lane; j < npts * 3; j += 32) s_pts[j] = src[j];
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  const int S = 7 * C;
+  const int n_out = max(n_f32, n_bf16);
+  for (int o0 = 0; o0 < n_out; o0 += 32) {
+    const int o = o0 + lane;
+    float val = 0.f;
+    if (o < S) {
+      const int p = o / C, ch = o - p * C;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        val = fmaf(s_w[p * 8 + k], __ldg(v.sh + (size_t)s_vox[p * 8 + k] * CP + ch), val);
+    } else if (o < S + nd * 3) {
+      const int j = o - S;
+      const int k = j / 3, c = j - 3 * k;
+      if (k < npts - 1) val = __fsub_rn(s_pts[(npts - 1 - k) * 3 + c], s_pts[(npts - 2 - k) * 3 + c]);
+    }
+    if (out_f32 && o < n_f32) out_f32[o] = val;
+    if (out_bf16) {
+      const float nxt = __shfl_down_sync(0xffffffffu, val, 1);
+      if (!(lane & 1) && o < n_bf16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(val, nxt);
+        *reinterpret_cast<__nv_bfloat162*>(out_bf16 + o) = h;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Fast path for the order-8 volume (C = 45 coefficients padded to CP = 48 floats = 12 float4).
+// Work item = (neighbourhood point p, float4 chunk ck): 84 items per row, three per lane; each
+// item gathers its 8 trilinear corners with LDG.128 straight into registers (8 independent
+// 16-byte loads in flight per lane; corners shared between the 7 points hit L1), so a row needs
+// only 4.3 KB of shared memory (weights, voxel ids, previous points, the output row) and ~32
+// warps fit on an SM.  The finished row leaves through shared memory as 16-byte stores.
+// (A cp.async-staged variant that parked all 56 corner voxels in shared memory first was
+// measured at 172 us/step at 50 000 rows: 12.5 KB/warp capped the SM at 16 warps.)
+__device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
+                                    float* __restrict__ out_f32, int n_f32,
+                                    __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f, int lane) {
+  constexpr int C = 45, CP4 = 12, S = 7 * C;
+  float* s_w = smem_f;                                  // [56] trilinear weights
+  int* s_vox = reinterpret_cast<int*>(smem_f + 64);     // [56] voxel index
+  float* s_pts = smem_f + 128;                          // [(n_dirs+1)*3]
+  float* s_row = smem_f + 128 + kMaxDirPts * 3;         // [640] output row
+  corner_table(v, prm, P + (size_t)(L - 1) * 3, s_w, s_vox, lane);
+  const int nd = prm.n_dirs;
+  const int npts = min(L, nd + 1);
+  const float* src = P + (size_t)(L - npts) * 3;
+  for (int j = lane; j < npts * 3; j += 32) s_pts[j] = src[j];
   __syncwarp();
 
-  // phase 2: work item = (point p, chunk ck): 8 corners x float4
-  float4 res[3];
+  const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
     const int item = lane + 32 * t;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (item < 7 * CP4) {
       const int p = item / CP4, ck = item - p * CP4;
+      const int4 v0 = *reinterpret_cast<const int4*>(s_vox + p * 8);
+      const int4 v1 = *reinterpret_cast<const int4*>(s_vox + p * 8 + 4);
+      const int vx[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float4 a[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = __ldg(vol4 + (size_t)vx[k] * CP4 + ck);
       const float4 w0 = *reinterpret_cast<const float4*>(s_w + p * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(s_w + p * 8 + 4);
       const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      const float4* cv = reinterpret_cast<const float4*>(s_corner + p * 8 * CP) + ck;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float4 a = cv[k * CP4];
-        acc.x = fmaf(wk[k], a.x, acc.x);
-        acc.y = fmaf(wk[k], a.y, acc.y);
-        acc.z = fmaf(wk[k], a.z, acc.z);
-        acc.w = fmaf(wk[k], a.w, acc.w);
+        acc.x = fmaf(wk[k], a[k].x, acc.x);
+        acc.y = fmaf(wk[k], a[k].y, acc.y);
+        acc.z = fmaf(wk[k], a[k].z, acc.z);
+        acc.w = fmaf(wk[k], a[k].w, acc.w);
       }
-    }
-    res[t] = acc;
-  }
-  __syncwarp();   // every lane is done reading the corners: the region becomes the output row
-  float* s_row = s_corner;
-#pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    const int item = lane + 32 * t;
-    if (item < 7 * CP4) {
-      const int p = item / CP4, ck = item - p * CP4;
       float* o = s_row + p * C + ck * 4;
-      o[0] = res[t].x;                       // channel 44 is the only valid one of chunk 11
-      if (ck < CP4 - 1) { o[1] = res[t].y; o[2] = res[t].z; o[3] = res[t].w; }
+      o[0] = acc.x;                          // channel 44 is the only valid one of chunk 11
+      if (ck < CP4 - 1) { o[1] = acc.y; o[2] = acc.z; o[3] = acc.w; }
     }
   }
   // previous directions, newest first, zero padded (env.py:549-563), then the row padding
