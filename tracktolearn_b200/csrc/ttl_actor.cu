@@ -41,10 +41,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  uint64_t t0 = 0;
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 28); ++it) {
+  for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -53,8 +59,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
+    if ((it & 1023u) == 1023u) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();   // 2 s
+    }
   }
-  __trap();
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1) {
@@ -325,6 +335,271 @@ dense_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
 }
 
+
+// ==========================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.
+// Each CTA stages ITS 128 rows of A and ITS 128 of the 256 W rows per k-block (32 KB instead
+// of 48 KB), the leader CTA's elected thread issues tcgen05.mma.cta_group::2 (M = 256), each
+// CTA's tensor core accumulates its own 128 rows into its own TMEM, and each CTA's epilogue
+// warps drain their half.  Shared-memory traffic per SM drops from 96+96 to 64+64 bytes/clk
+// at full MMA rate, which is what holds the 1-CTA kernel to ~58 % tensor-pipe utilisation.
+//
+// Barrier protocol (same smem offsets in both CTAs):
+//   full[s]    lives in the leader; its producer arms it with arrive.expect_tx for BOTH CTAs'
+//              bytes (64 KB); all four TMA loads complete_tx on it (cp.async.bulk.tensor ...
+//              .cta_group::2 with the leader's barrier address).  The peer's bytes may land
+//              before the leader arms the phase: the tx-count goes transiently negative, which
+//              mbarrier permits, and the phase cannot complete before the leader's arrival.
+//   empty[s]   one per CTA, released by tcgen05.commit ... multicast to both CTAs
+//   tfull[a]   one per CTA, signalled by the same multicast commit after the last k-block
+//   tempty[a]  lives in the leader; 8 arrivals (4 epilogue warps x 2 CTAs, the peer's remotely)
+// ==========================================================================================
+constexpr int STAGES2 = 6;
+constexpr int B2_BYTES = (BN / 2) * BK * 2;        // 16 KB: this CTA's half of the W tile
+constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;   // 32 KB
+constexpr int GEMM2_SMEM = STAGES2 * STAGE2_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Remote arrive with the default (cta-scope) release: a cluster-scope release compiles to
+// MEMBAR.ALL.GPU, which was measured to serialise the pipeline.  The data this barrier guards is
+// TMEM drained by tcgen05.wait::ld + tcgen05.fence, not generic-proxy memory.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Instruction descriptor for the pair: D=f32, A=B=bf16, K-major, M=256, N=256.
+__device__ __forceinline__ constexpr uint32_t umma_idesc_2cta() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+}
+
+template <int HEAD_OUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ C, int ldc,
+                       const int* __restrict__ m_dev, int m_max, int n_pad, int k_pad, int relu,
+                       const float* __restrict__ head_w, int head_k, float* __restrict__ head_partial) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ttl_smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar0 = base + STAGES2 * STAGE2_BYTES;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (STAGES2 + s); };
+  auto tfull = [&](int s) { return bar0 + 8u * (2 * STAGES2 + s); };
+  auto tempty = [&](int s) { return bar0 + 8u * (2 * STAGES2 + ACC_STAGES + s); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES2 + 2 * ACC_STAGES);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();       // 0 = leader
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  int m = m_dev ? *m_dev : m_max;
+  m = min(m, m_max);
+  const int n_m = (m + 2 * BM - 1) / (2 * BM), n_n = (n_pad + BN - 1) / BN;
+  const int total = n_m * n_n, kblocks = k_pad / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - raw));
+  float* s_head = s_bias + EXTRA_SMEM_BIAS / 4;
+  const bool bias_in_smem = n_pad <= EXTRA_SMEM_BIAS / 4;
+  if (bias_in_smem)
+    for (int t = threadIdx.x; t < n_pad; t += GEMM_THREADS) s_bias[t] = bias[t];
+  if (HEAD_OUT > 0) {
+    for (int t = threadIdx.x; t < HEAD_OUT * n_pad; t += GEMM_THREADS) {
+      const int o = t / n_pad, c = t - o * n_pad;
+      s_head[t] = c < head_k ? head_w[(size_t)o * head_k + c] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total; tile += n_clusters) {
+        const int m_blk = tile / n_n, n_blk = tile - m_blk * n_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          const uint32_t leader_full = mapa_shared(full(stage), 0);
+          if (cta == 0) mbar_arrive_expect_tx(full(stage), 2 * STAGE2_BYTES);
+          const uint32_t sa = base + stage * STAGE2_BYTES;
+          tma_load_2d_2cta(sa, &tma_a, leader_full, kb * BK, m_blk * 2 * BM + (int)cta * BM);
+          tma_load_2d_2cta(sa + A_BYTES, &tma_b, leader_full, kb * BK, n_blk * BN + (int)cta * (BN / 2));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cta == 0) {  // ===== MMA issuer (leader only) =====
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      constexpr uint32_t idesc = umma_idesc_2cta();
+      for (int tile = cluster_id; tile < total; tile += n_clusters) {
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * STAGE2_BYTES;
+          const uint64_t da = umma_desc(sa), db = umma_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                             (uint32_t)((kb | k) != 0));
+          tc_commit_2cta(empty(stage));   // frees this stage in BOTH CTAs
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_2cta(tfull(acc));       // accumulators complete in both CTAs
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {  // ===== epilogue (both CTAs, own 128 rows) =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total; tile += n_clusters) {
+      const int m_blk = tile / n_n, n_blk = tile - m_blk * n_n;
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 2 * BM + (int)cta * BM + q * 32 + lane;
+      const bool row_ok = row < m;
+      __nv_bfloat16* crow = C + (size_t)row * ldc;
+      float hp[HEAD_OUT > 0 ? HEAD_OUT : 1];
+#pragma unroll
+      for (int o = 0; o < (HEAD_OUT > 0 ? HEAD_OUT : 1); ++o) hp[o] = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col0 = n_blk * BN + ch * 32;
+        if (col0 >= n_pad) break;  // warp-uniform
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+        tc_wait_ld();
+        float x[32];
+        if (bias_in_smem) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j);
+            x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+            x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+            x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __ldg(bias + col0 + j);
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
+        if (HEAD_OUT > 0) {
+#pragma unroll
+          for (int o = 0; o < HEAD_OUT; ++o) {
+            const float* wrow = s_head + o * n_pad + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wrow + 4 * j);
+              hp[o] = fmaf(x[4 * j + 0], w4.x, hp[o]);
+              hp[o] = fmaf(x[4 * j + 1], w4.y, hp[o]);
+              hp[o] = fmaf(x[4 * j + 2], w4.z, hp[o]);
+              hp[o] = fmaf(x[4 * j + 3], w4.w, hp[o]);
+            }
+          }
+        } else if (row_ok) {
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      }
+      if (HEAD_OUT > 0 && row_ok) {
+        float o8[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) o8[o] = o < HEAD_OUT ? hp[o < HEAD_OUT ? o : 0] : 0.f;
+        float4* dst = reinterpret_cast<float4*>(head_partial + ((size_t)row * n_n + n_blk) * 8);
+        dst[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+        dst[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta == 0) mbar_arrive(tempty(acc));
+        else mbar_arrive_remote(mapa_shared(tempty(acc), 0));
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // neither CTA leaves (or frees TMEM) while its peer can still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ==========================================================================================
 // Packing kernels
 // ==========================================================================================
@@ -583,19 +858,55 @@ int num_sms() {
   return g_num_sms;
 }
 
-int launch_dense_bf16(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, __nv_bfloat16* C,
-                      int ldc, const int* m_dev, int m_max, int n_pad, int k_pad, int relu,
+bool use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TTL_DENSE_1CTA");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// tb2: TMA map of W with a 128-row box (2-CTA kernel); tb: 256-row box (1-CTA kernel)
+int launch_dense_bf16(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb2, const float* bias,
+                      __nv_bfloat16* C, int ldc, const int* m_dev, int m_max, int n_pad, int k_pad, int relu,
                       cudaStream_t s, const float* head_w = nullptr, int head_k = 0,
                       float* head_partial = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(dense_bf16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GEMM_SMEM + EXTRA_SMEM_BIAS);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(dense_bf16_kernel<HEAD_OUT_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             GEMM_SMEM + EXTRA_SMEM_BIAS + HEAD_SMEM_MAX);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_bf16_kernel<HEAD_OUT_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GEMM_SMEM + EXTRA_SMEM_BIAS + HEAD_SMEM_MAX);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_bf16_2cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GEMM2_SMEM + EXTRA_SMEM_BIAS);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_bf16_2cta_kernel<HEAD_OUT_FUSED>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GEMM2_SMEM + EXTRA_SMEM_BIAS + HEAD_SMEM_MAX);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
+  }
+  if (use_2cta()) {
+    const int tiles = ttl_div_up(m_max, 2 * BM) * ttl_div_up(n_pad, BN);
+    int clusters = num_sms() / 2;
+    if (tiles < clusters) clusters = tiles;
+    if (clusters <= 0) return 0;
+    const int grid = 2 * clusters;
+    if (head_w) {
+      TTL_LAUNCH("dense_bf16_head_kernel", s,
+                 dense_bf16_2cta_kernel<HEAD_OUT_FUSED><<<grid, GEMM_THREADS,
+                                                          GEMM2_SMEM + EXTRA_SMEM_BIAS + HEAD_OUT_FUSED * n_pad * 4, s>>>(
+                     ta, tb2, bias, C, ldc, m_dev, m_max, n_pad, k_pad, relu, head_w, head_k, head_partial));
+    } else {
+      TTL_LAUNCH("dense_bf16_kernel", s,
+                 dense_bf16_2cta_kernel<0><<<grid, GEMM_THREADS, GEMM2_SMEM + EXTRA_SMEM_BIAS, s>>>(
+                     ta, tb2, bias, C, ldc, m_dev, m_max, n_pad, k_pad, relu, nullptr, 0, nullptr));
+    }
+    TTL_CHECK_LAST();
+    return 0;
   }
   const int tiles = ttl_div_up(m_max, BM) * ttl_div_up(n_pad, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -629,6 +940,7 @@ struct ttl_actor_plan {
   bool fuse_head;
   int max_kpad, max_width;
   CUtensorMap map_w[TTL_ACTOR_MAX_LAYERS];
+  CUtensorMap map_w2[TTL_ACTOR_MAX_LAYERS];  // 128-row box for the 2-CTA kernel
   CUtensorMap map_a[TTL_ACTOR_MAX_LAYERS];  // A operand of layer i
   // first-layer operand maps for caller-owned bf16 state buffers (ttl_actor_forward_packed)
   struct ExtMap { const void* ptr; int rows; CUtensorMap map; };
@@ -691,7 +1003,7 @@ int run_bf16_layers(ttl_actor_plan* p, const CUtensorMap& map_a0, const int32_t*
   for (int i = 0; i < nl - 1; ++i) {
     // layer i: act[i&1] (pitch k_pad[i]) -> act[(i+1)&1] (pitch k_pad[i+1] = n_pad[i])
     const bool fused = p->fuse_head && i == nl - 2;
-    int rc = launch_dense_bf16(i == 0 ? map_a0 : p->map_a[i], p->map_w[i], p->bq[i], p->act[(i + 1) & 1],
+    int rc = launch_dense_bf16(i == 0 ? map_a0 : p->map_a[i], p->map_w[i], p->map_w2[i], p->bq[i], p->act[(i + 1) & 1],
                                p->n_pad[i], n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1, s,
                                fused ? w.w[nl - 1] : nullptr, k_last, fused ? p->head_partial : nullptr);
     if (rc) return rc;
@@ -752,6 +1064,8 @@ int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int3
     const int bp = round_up(L.n_pad[i], BN);
     TTL_LAUNCH("pack_bias_kernel", s, pack_bias_kernel<<<ttl_div_up(bp, 256), 256, 0, s>>>(w->b[i], p->bq[i], w->out_dim[i], bp));
     rc = make_tmap(&p->map_w[i], p->wq[i], (uint64_t)L.n_pad[i], (uint64_t)L.k_pad[i], BN);
+    if (rc) { delete p; return rc; }
+    rc = make_tmap(&p->map_w2[i], p->wq[i], (uint64_t)L.n_pad[i], (uint64_t)L.k_pad[i], BN / 2);
     if (rc) { delete p; return rc; }
     // A operand of layer i lives in act[i & 1] with row pitch k_pad[i]
     rc = make_tmap(&p->map_a[i], p->act[i & 1], (uint64_t)max_rows, (uint64_t)L.k_pad[i], BM);
@@ -851,13 +1165,15 @@ int ttl_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int3
                   int32_t k, int32_t ldc, int32_t relu, const int32_t* m_dev, void* stream) {
   if (!A || !W || !bias || !C || (k % BK) || (n % BK) || ldc < n || (ldc % 8)) return TTL_ERR_BAD_ARG;
   if (m <= 0) return 0;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tb2;
   int rc = make_tmap(&ta, A, (uint64_t)m, (uint64_t)k, BM);
   if (rc) return rc;
   rc = make_tmap(&tb, W, (uint64_t)n, (uint64_t)k, BN);
   if (rc) return rc;
+  rc = make_tmap(&tb2, W, (uint64_t)n, (uint64_t)k, BN / 2);
+  if (rc) return rc;
   // bias must be readable up to the tile edge: caller pads it to a multiple of 256 floats
-  return launch_dense_bf16(ta, tb, bias, static_cast<__nv_bfloat16*>(C), ldc, m_dev, m, n, k, relu,
+  return launch_dense_bf16(ta, tb, tb2, bias, static_cast<__nv_bfloat16*>(C), ldc, m_dev, m, n, k, relu,
                            (cudaStream_t)stream);
 }
 
