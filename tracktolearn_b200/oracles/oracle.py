@@ -1,0 +1,123 @@
+"""TractOracle-Net scorer (reference: oracles/oracle.py:11-89, transformer_oracle.py:37-118).
+
+``OracleSingleton(checkpoint, device).predict(streamlines) -> np.ndarray[N]`` like the reference;
+the resampling to 128 points (dipy ``set_number_of_points``), the ``np.diff`` and the transformer
+all run on the device (``ttl_oracle_features`` / ``ttl_oracle_forward``).  Scores are computed in
+fp32.  Every streamline is scored: the reference's own loop drops a trailing partial batch when
+N > 4096; we follow ``experiment/oracle_validator.py:40-47``'s chunked semantics.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from tracktolearn_b200 import _lib
+
+
+class TransformerOracleWeights(object):
+    """Device copy of a TransformerOracle checkpoint
+    ({'hyper_parameters': {...}, 'state_dict': {...}}, transformer_oracle.py:95-118)."""
+
+    def __init__(self, checkpoint, device):
+        hp = checkpoint['hyper_parameters']
+        if hp.get('name', 'TransformerOracle') != 'TransformerOracle':
+            raise ValueError('unsupported oracle model %r' % (hp.get('name'),))
+        sd = checkpoint['state_dict']
+        self.device = torch.device(device)
+        self.n_head = int(hp['n_head'])
+        self.n_layers = int(hp['n_layers'])
+        self.input_size = int(hp['input_size'])
+        self.n_tokens = self.input_size // 3          # 127 directions + CLS
+        if self.n_tokens != 128:
+            raise _lib.TTLError('oracle kernels are built for 128 tokens (input_size 384), got %d'
+                                % self.input_size)
+
+        def dev(t):
+            return t.detach().to(self.device, dtype=torch.float32).contiguous()
+        self.t = {k: dev(v) for k, v in sd.items() if k != 'pos_encoding.pe'}
+        self.t['pe'] = dev(sd['pos_encoding.pe'][:self.n_tokens, 0, :])
+        self.d_model = self.t['embedding.0.weight'].shape[0]
+        self.d_ff = self.t['bert.layers.0.linear1.weight'].shape[0]
+        w = _lib.OracleWeights()
+        w.n_layers, w.n_head, w.d_model, w.d_ff, w.n_tokens = (self.n_layers, self.n_head, self.d_model,
+                                                               self.d_ff, self.n_tokens)
+        w.cls_token = self.t['cls_token'].data_ptr()
+        w.emb_w = self.t['embedding.0.weight'].data_ptr()
+        w.emb_b = self.t['embedding.0.bias'].data_ptr()
+        w.pe = self.t['pe'].data_ptr()
+        for i in range(self.n_layers):
+            p = 'bert.layers.%d.' % i
+            w.in_proj_w[i] = self.t[p + 'self_attn.in_proj_weight'].data_ptr()
+            w.in_proj_b[i] = self.t[p + 'self_attn.in_proj_bias'].data_ptr()
+            w.out_proj_w[i] = self.t[p + 'self_attn.out_proj.weight'].data_ptr()
+            w.out_proj_b[i] = self.t[p + 'self_attn.out_proj.bias'].data_ptr()
+            w.lin1_w[i] = self.t[p + 'linear1.weight'].data_ptr()
+            w.lin1_b[i] = self.t[p + 'linear1.bias'].data_ptr()
+            w.lin2_w[i] = self.t[p + 'linear2.weight'].data_ptr()
+            w.lin2_b[i] = self.t[p + 'linear2.bias'].data_ptr()
+            w.norm1_w[i] = self.t[p + 'norm1.weight'].data_ptr()
+            w.norm1_b[i] = self.t[p + 'norm1.bias'].data_ptr()
+            w.norm2_w[i] = self.t[p + 'norm2.weight'].data_ptr()
+            w.norm2_b[i] = self.t[p + 'norm2.bias'].data_ptr()
+        w.head_w = self.t['head.weight'].data_ptr()
+        w.head_b = self.t['head.bias'].data_ptr()
+        self.struct = w
+
+
+class OracleSingleton(object):
+    _self = None
+
+    def __new__(cls, *args, **kwargs):
+        if cls._self is None:
+            cls._self = super().__new__(cls)
+        return cls._self
+
+    def __init__(self, checkpoint, device, batch_size=4096):
+        ck = checkpoint if isinstance(checkpoint, dict) else torch.load(checkpoint, map_location='cpu')
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.TTLError('the oracle runs on a CUDA device only (got %s)' % (self.device,))
+        self._lib = _lib.load()
+        self.weights = TransformerOracleWeights(ck, self.device)
+        self.batch_size = batch_size
+
+    @classmethod
+    def clear(cls):
+        cls._self = None
+
+    # --------------------------------------------------------------------------- device
+    def predict_device(self, points, offsets):
+        """points [sum(L),3] fp32 and offsets [N+1] int64 on the device -> scores [N] fp32 (device)."""
+        n = int(offsets.shape[0]) - 1
+        scores = torch.empty((max(n, 0),), dtype=torch.float32, device=self.device)
+        if n <= 0:
+            return scores
+        sp = _lib.stream_ptr(self.device)
+        for s0 in range(0, n, self.batch_size):        # bounded scratch: [batch][127][3]
+            s1 = min(n, s0 + self.batch_size)
+            dirs = torch.empty((s1 - s0, 127, 3), dtype=torch.float32, device=self.device)
+            _lib.check(self._lib.ttl_oracle_features(_lib.ptr(points), ctypes.c_void_p(offsets.data_ptr() + 8 * s0),
+                                                     s1 - s0, _lib.ptr(dirs), sp), 'ttl_oracle_features')
+            _lib.check(self._lib.ttl_oracle_forward(ctypes.byref(self.weights.struct), _lib.ptr(dirs), s1 - s0,
+                                                    ctypes.c_void_p(scores.data_ptr() + 4 * s0), sp),
+                       'ttl_oracle_forward')
+        return scores
+
+    # --------------------------------------------------------------------------- host API
+    def predict(self, streamlines):
+        """Reference: oracles/oracle.py:39-89.  ``streamlines``: sequence of [L_i,3] arrays (or an
+        object with packed ``data`` / ``offsets``).  Returns float32 numpy [N]."""
+        if hasattr(streamlines, 'offsets') and hasattr(streamlines, 'data'):
+            data = np.ascontiguousarray(streamlines.data, dtype=np.float32)
+            offsets = np.ascontiguousarray(streamlines.offsets, dtype=np.int64)
+        else:
+            n = len(streamlines)
+            lens = np.fromiter((len(s) for s in streamlines), dtype=np.int64, count=n)
+            offsets = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+            data = (np.concatenate([np.asarray(s, dtype=np.float32) for s in streamlines])
+                    if n else np.zeros((0, 3), np.float32))
+        if len(offsets) <= 1:
+            return np.zeros((0,), dtype=np.float32)
+        pts = torch.from_numpy(data.reshape(-1, 3)).pin_memory().to(self.device, non_blocking=True)
+        off = torch.from_numpy(offsets).pin_memory().to(self.device, non_blocking=True)
+        return self.predict_device(pts, off).cpu().numpy()
