@@ -1,0 +1,71 @@
+"""CLI smoke tests mirroring the reference's tests/test_runners.py (--help must work without a GPU)
+plus, on the GPU box, an end-to-end ttl_track run on a tiny synthetic subject written to disk."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_help_option():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'ttl_track.py'), '--help'],
+                         capture_output=True, text=True)
+    assert out.returncode == 0
+    for flag in ('in_odf', 'in_seed', 'in_mask', 'out_tractogram', '--sh_basis', '--compress', '--save_seeds',
+                 '--agent', '--hyperparameters', '--n_actor', '--npv', '--min_length', '--max_length',
+                 '--noise', '--fa_map', '--binary_stopping_threshold', '--rng_seed'):
+        assert flag in out.stdout, flag
+
+
+def test_sh_basis_conversion_is_an_involution():
+    from tracktolearn_b200.datasets.files import set_sh_order_basis
+    rs = np.random.RandomState(0)
+    sh = rs.normal(size=(2, 3, 4, 45)).astype(np.float32)
+    once = set_sh_order_basis(sh, 'tournier07', target_order=8)
+    assert not np.array_equal(once, sh)
+    np.testing.assert_array_equal(set_sh_order_basis(once, 'tournier07', target_order=8), sh)
+    np.testing.assert_array_equal(once[..., 0], sh[..., 0])        # l = 0 untouched
+    # order 6 (28 coefs) -> order 8: zero padded; full basis -> even degrees only
+    assert set_sh_order_basis(sh[..., :28], 'descoteaux07', target_order=8).shape[-1] == 45
+    full = rs.normal(size=(1, 1, 1, 81)).astype(np.float32)
+    assert set_sh_order_basis(full, 'descoteaux07', target_order=8).shape[-1] == 45
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('ext', ['trk', 'tck'])
+def test_ttl_track_end_to_end(tmp_path, ext):
+    from tracktolearn_b200 import synthetic
+    from tracktolearn_b200.io import nifti
+    from tracktolearn_b200.io.streamlines import read_tck, read_trk
+    from tracktolearn_b200.runners.ttl_track import main
+    shape = (24, 26, 22)
+    sub = synthetic.make_subject(shape, seed=5)
+    affine = np.diag([1.25, 1.25, 1.25, 1.0])
+    affine[:3, 3] = [-10.0, 4.0, 2.5]
+    nifti.save(str(tmp_path / 'fodf.nii.gz'), sub['sh'].numpy(), affine)
+    nifti.save(str(tmp_path / 'mask.nii.gz'), sub['mask'].numpy(), affine)
+    nifti.save(str(tmp_path / 'seed.nii.gz'), synthetic.ellipsoid_mask(shape, frac=0.3).numpy().astype(np.uint8), affine)
+    agent = synthetic.write_agent_dir(str(tmp_path / 'agent'), kind='tracking', hidden_dims='128-128-128')
+    out = str(tmp_path / ('out.' + ext))
+    main([str(tmp_path / 'fodf.nii.gz'), str(tmp_path / 'seed.nii.gz'), str(tmp_path / 'mask.nii.gz'), out,
+          '--agent', agent, '--hyperparameters', os.path.join(agent, 'hyperparameters.json'),
+          '--n_actor', '500', '--npv', '2', '--min_length', '5', '--max_length', '60', '--save_seeds'])
+    data, offsets, hdr = (read_trk if ext == 'trk' else read_tck)(out)
+    n = len(offsets) - 1
+    assert n > 200
+    lens = np.diff(offsets)
+    assert lens.min() >= 2
+    if ext == 'trk':
+        assert hdr['n_count'] == n and np.allclose(hdr['voxel_sizes'], 1.25)
+        vox = data / 1.25 - 0.5                      # back to voxel space
+    else:
+        vox = (data - affine[:3, 3]) / 1.25
+    assert vox.min() > -1 and (vox.max(axis=0) < np.asarray(shape)).all()
+    seg = np.linalg.norm(np.diff(vox, axis=0), axis=1)
+    inner = np.ones(len(vox) - 1, dtype=bool)
+    inner[offsets[1:-1] - 1] = False
+    # step size rescaled by voxel size: 1.25 / 0.9987237 * 0.75 mm = 0.75096 voxels
+    np.testing.assert_allclose(seg[inner], 0.75 / 0.9987237, rtol=2e-4)

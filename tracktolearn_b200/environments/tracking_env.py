@@ -274,10 +274,27 @@ class TrackingEnvironment(BaseEnv):
                    'ttl_pack_streamlines')
         return pts[:total], offsets
 
+    def _pinned(self, name, numel, dtype):
+        """Cached page-locked staging buffer (grown geometrically) for device->host copies."""
+        cache = self.__dict__.setdefault('_pinned_cache', {})
+        buf = cache.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.empty((max(int(numel * 1.25), 1024),), dtype=dtype).pin_memory()
+            cache[name] = buf
+        return buf[:numel]
+
     def get_streamlines(self):
         """Reference: tracking_env.py:247-294.  The last point is dropped when the CURVATURE or
-        MASK flag stopped the streamline."""
+        MASK flag stopped the streamline.  One packed D2H copy through pinned memory."""
         pts, offsets = self.get_streamlines_device()
-        return Tractogram(data=pts.cpu().numpy(), offsets=offsets.cpu().numpy(),
+        N = self._n
+        h_pts = self._pinned('pts', pts.numel(), torch.float32)
+        h_off = self._pinned('off', N + 1, torch.int64)
+        h_flags = self._pinned('flags', N, torch.int32)
+        h_pts.copy_(pts.reshape(-1), non_blocking=True)
+        h_off.copy_(offsets, non_blocking=True)
+        h_flags.copy_(self._batch.flags[:N], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return Tractogram(data=h_pts.numpy().reshape(-1, 3).copy(), offsets=h_off.numpy().copy(),
                           data_per_streamline={'seeds': np.asarray(self.initial_points),
-                                               'flags': self.flags})
+                                               'flags': h_flags.numpy().astype(int)})

@@ -99,6 +99,36 @@ class Tracker(object):
 
         return tracking_generator()
 
+    def track_to_file(self, env, path, dims, voxel_sizes):
+        """What ``ttl_track.py`` does with ``track`` + ``nib.streamlines.save`` (runners/ttl_track.py:
+        172-186), on packed arrays: length filter (tracker.py:118-121), voxel -> file space
+        (:127-136), streamed to a .trk / .tck writer.  Returns the number of streamlines kept."""
+        from tracktolearn_b200.io.streamlines import TckWriter, TrkWriter, detect_format
+        fmt = detect_format(path)
+        affine = np.asarray(env.affine_vox2rasmm, dtype=np.float64)
+        np.random.shuffle(env.seeds)      # tracker.py:94
+        vox_size = np.mean(np.abs(affine)[np.diag_indices(4)][:3])
+        lo, hi = self.min_length / vox_size, self.max_length / vox_size
+        writer = (TrkWriter(path, dims, voxel_sizes, affine, self.save_seeds) if fmt == 'trk'
+                  else TckWriter(path))
+        try:
+            for batch in self.track_packed(env):
+                lens = streamline_lengths(batch.data, batch.offsets)
+                keep = (lo <= lens) & (lens <= hi)
+                npts = np.diff(batch.offsets)
+                sel = np.repeat(keep, npts)
+                data = batch.data[sel].astype(np.float64)
+                offsets = np.concatenate(([0], np.cumsum(npts[keep]))).astype(np.int64)
+                if fmt == 'trk':
+                    data = (data + 0.5) * vox_size
+                else:
+                    data = data @ affine[:3, :3] + affine[:3, 3]     # tracker.py:133-136
+                writer.write(data.astype(np.float32), offsets,
+                             batch.data_per_streamline['seeds'][keep] - 0.5)
+        finally:
+            writer.close()
+        return writer.n
+
     def track_and_validate(self, env):
         """Reference: tracking/tracker.py:204-259 (batch by batch, with rewards)."""
         self.alg.agent.eval()
