@@ -96,8 +96,8 @@ typedef struct ttl_batch {
                               to ld_bf16 = round_up(state_size, 64): the actor's first-layer TMA
                               operand, written by the same kernel that writes state[] */
   int32_t ld_bf16;
-  int32_t max_groups;      /* entries in grp_stops / grp_prefix: ceil(n_slots / 128) + 1 */
-  int32_t* grp_stops;      /* [max_groups] streamlines stopped this step per group of 128 ranks */
+  int32_t max_groups;      /* entries in grp_stops / grp_prefix: ceil(n_slots / 32) + 1 */
+  int32_t* grp_stops;      /* [max_groups] streamlines stopped this step per group of 32 ranks */
   int32_t* grp_prefix;     /* [max_groups] exclusive prefix of survivors per group */
 } ttl_batch;
 

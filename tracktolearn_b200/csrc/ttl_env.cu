@@ -35,7 +35,9 @@ std::atomic<long long> g_ttl_launches{0};
 
 namespace {
 
-constexpr int kGroup = 128;   // ranks per compaction group == propagate_stop block size
+constexpr int kGroup = 32;          // ranks per compaction group == rows per propagate_stop CTA
+constexpr int kLanesPerRow = 4;     // lanes that share one streamline's 64 spline taps
+constexpr int kK1Threads = kGroup * kLanesPerRow;
 
 // ------------------------------------------------------------------------------------------
 // float helpers that refuse FMA contraction, so sums of products round like numpy's
@@ -116,6 +118,61 @@ __device__ double mask_spline_value(const ttl_volume& v, float px, float py, flo
   return out;
 }
 
+// The same value computed by the 4 lanes that share a streamline: lane `sub` multiplies out the
+// 16 taps of x-slab `sub`, then the running sum is handed from lane to lane so the 64 additions
+// happen in exactly scipy's order (slab 0 first, z fastest).  All 4 lanes return the value.
+__device__ double mask_spline_value_quad(const ttl_volume& v, float px, float py, float pz, int sub,
+                                         unsigned quad_mask, int lane) {
+  const double c[3] = {(double)__fsub_rn(px, 0.5f), (double)__fsub_rn(py, 0.5f),
+                       (double)__fsub_rn(pz, 0.5f)};
+  const int dims[3] = {v.MX, v.MY, v.MZ};
+  int start[3];
+  double w[3][4];
+  bool edge = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (!(c[a] >= 0.0 && c[a] <= (double)(dims[a] - 1))) return 0.0;   // uniform across the quad
+    const double fl = floor(c[a]);
+    start[a] = (int)fl - 1;
+    edge |= (start[a] < 0) || (start[a] + 3 >= dims[a]);
+    bspline3(c[a] - fl, w[a]);
+  }
+  const int xi = edge ? mirror_idx(start[0] + sub, dims[0]) : start[0] + sub;
+  double wx = w[0][0];
+#pragma unroll
+  for (int t = 1; t < 4; ++t) wx = (sub == t) ? w[0][t] : wx;
+  int yi[4], zi[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    yi[t] = edge ? mirror_idx(start[1] + t, dims[1]) : start[1] + t;
+    zi[t] = edge ? mirror_idx(start[2] + t, dims[2]) : start[2] + t;
+  }
+  double prod[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double* line = v.mask_coef + ((size_t)xi * v.MY + yi[j]) * v.MZ;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double t = __ldg(line + zi[k]);
+      t = __dmul_rn(t, wx);
+      t = __dmul_rn(t, w[1][j]);
+      t = __dmul_rn(t, w[2][k]);
+      prod[4 * j + k] = t;
+    }
+  }
+  double acc = 0.0;
+  const int quad_base = lane & ~(kLanesPerRow - 1);
+#pragma unroll
+  for (int s4 = 0; s4 < 4; ++s4) {
+    if (sub == s4) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) acc = __dadd_rn(acc, prod[t]);
+    }
+    acc = __shfl_sync(quad_mask, acc, quad_base + s4);
+  }
+  return acc;
+}
+
 // utils.py:145-173 on the last three points (fp32, no clipping: NaN compares False).
 __device__ __forceinline__ bool too_curvy(const float* p3, float theta_rad) {
   const float ux = __fsub_rn(p3[6], p3[3]), uy = __fsub_rn(p3[7], p3[4]), uz = __fsub_rn(p3[8], p3[5]);
@@ -137,6 +194,18 @@ __device__ int stopping_flags(const ttl_volume& v, const ttl_params& prm, const 
   const float* tip = P + (size_t)(L - 1) * 3;
   const double mv = mask_spline_value(v, tip[0], tip[1], tip[2]);
   if (mask_value_out) *mask_value_out = mv;
+  if (mv < prm.mask_threshold) f |= TTL_STOPPING_MASK;
+  return f;
+}
+
+// quad-cooperative version of stopping_flags (same result in all 4 lanes)
+__device__ int stopping_flags_quad(const ttl_volume& v, const ttl_params& prm, const float* P, int L, int sub,
+                                   unsigned quad_mask, int lane) {
+  int f = 0;
+  if (L >= prm.max_nb_steps) f |= TTL_STOPPING_LENGTH;
+  if (L >= 3 && too_curvy(P + (size_t)(L - 3) * 3, prm.theta_rad)) f |= TTL_STOPPING_CURVATURE;
+  const float* tip = P + (size_t)(L - 1) * 3;
+  const double mv = mask_spline_value_quad(v, tip[0], tip[1], tip[2], sub, quad_mask, lane);
   if (mv < prm.mask_threshold) f |= TTL_STOPPING_MASK;
   return f;
 }
@@ -231,10 +300,13 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
 // ------------------------------------------------------------------------------------------
 // K1: propagate + stopping criteria + reward, one thread per alive streamline
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) propagate_stop_kernel(
+__global__ void __launch_bounds__(kK1Threads) propagate_stop_kernel(
     ttl_volume v, ttl_params prm, ttl_batch b, int cur, const float* __restrict__ actions,
     int lda, const double* __restrict__ noise) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  // 4 lanes per streamline: they redo the cheap scalar work together and split the spline taps
+  const int lane = threadIdx.x & 31, sub = threadIdx.x & (kLanesPerRow - 1);
+  const unsigned quad_mask = 0xFu << (lane & ~(kLanesPerRow - 1));
+  const int r = blockIdx.x * kGroup + (threadIdx.x / kLanesPerRow);
   const int n_alive = b.ctrl[cur];
   int stopped = 0;
   if (r < n_alive) {
@@ -262,8 +334,8 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
     qy = (float)__dadd_rn((double)py, dy);
     qz = (float)__dadd_rn((double)pz, dz);
     if (L == 1) {  // tracking_env.py:165-178: flip if the first step would stop
-      P[3] = qx; P[4] = qy; P[5] = qz;
-      if (stopping_flags(v, prm, P, 2, nullptr) != 0) {
+      const float two[6] = {px, py, pz, qx, qy, qz};
+      if (stopping_flags_quad(v, prm, two, 2, sub, quad_mask, lane) != 0) {
         qx = (float)__dadd_rn((double)px, -dx);
         qy = (float)__dadd_rn((double)py, -dy);
         qz = (float)__dadd_rn((double)pz, -dz);
@@ -277,33 +349,48 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
     const float dz = __fmul_rn(__fdiv_rn(az, nrm), stepf);
     qx = __fadd_rn(px, dx); qy = __fadd_rn(py, dy); qz = __fadd_rn(pz, dz);
     if (L == 1) {
-      P[3] = qx; P[4] = qy; P[5] = qz;
-      if (stopping_flags(v, prm, P, 2, nullptr) != 0) {
+      const float two[6] = {px, py, pz, qx, qy, qz};
+      if (stopping_flags_quad(v, prm, two, 2, sub, quad_mask, lane) != 0) {
         qx = __fadd_rn(px, -dx); qy = __fadd_rn(py, -dy); qz = __fadd_rn(pz, -dz);
       }
     }
   }
-  P[L * 3 + 0] = qx; P[L * 3 + 1] = qy; P[L * 3 + 2] = qz;
+  // the last three points as this step leaves them (the new one is not in memory yet)
   const int Ln = L + 1;
-  const int f = stopping_flags(v, prm, P, Ln, nullptr);
-  b.npts[i] = Ln;
-  b.step_flags[r] = f;
-  b.stop[r] = f != 0;
-  stopped = f != 0;
-  if (f) {
-    b.flags[i] = f;
-    b.dones[i] = 1;
-    b.lengths[i] = Ln;  // the reference records it in harvest(); nothing reads it in between
-  }
+  float last3[9];
+  last3[6] = qx; last3[7] = qy; last3[8] = qz;
+  last3[3] = px; last3[4] = py; last3[5] = pz;
+  last3[0] = L >= 2 ? P[(L - 2) * 3 + 0] : 0.f;
+  last3[1] = L >= 2 ? P[(L - 2) * 3 + 1] : 0.f;
+  last3[2] = L >= 2 ? P[(L - 2) * 3 + 2] : 0.f;
+  int f = 0;
+  if (Ln >= prm.max_nb_steps) f |= TTL_STOPPING_LENGTH;
+  if (Ln >= 3 && too_curvy(last3, prm.theta_rad)) f |= TTL_STOPPING_CURVATURE;
+  if (mask_spline_value_quad(v, qx, qy, qz, sub, quad_mask, lane) < prm.mask_threshold) f |= TTL_STOPPING_MASK;
+  float rew = 0.f;
   if (prm.compute_reward && v.peaks) {
-    // reward.py:63-67: w * f(...) stays float32 (weak python scalar)
-    b.reward[r] = __fmul_rn((float)prm.alignment_weighting, alignment_reward(v, P, Ln));
+    // reward.py:63-67: w * f(...) stays float32 (weak python scalar); Ln >= 2 always holds here
+    rew = __fmul_rn((float)prm.alignment_weighting,
+                    alignment_reward(v, last3 + (Ln >= 3 ? 0 : 3), Ln >= 3 ? 3 : 2));
+  }
+  if (sub == 0) {
+    P[L * 3 + 0] = qx; P[L * 3 + 1] = qy; P[L * 3 + 2] = qz;
+    b.npts[i] = Ln;
+    b.step_flags[r] = f;
+    b.stop[r] = f != 0;
+    stopped = f != 0;
+    if (f) {
+      b.flags[i] = f;
+      b.dones[i] = 1;
+      b.lengths[i] = Ln;  // the reference records it in harvest(); nothing reads it in between
+    }
+    if (prm.compute_reward && v.peaks) b.reward[r] = rew;
   }
   }  // r < n_alive
 
   // ---- ordered-compaction bookkeeping: stops per group of kGroup ranks; the last CTA scans ----
   __shared__ int s_is_last;
-  __shared__ int s_part[kGroup];
+  __shared__ int s_part[kK1Threads];
   const int grp_stops = __syncthreads_count(stopped);
   if (threadIdx.x == 0) {
     b.grp_stops[blockIdx.x] = grp_stops;
@@ -315,7 +402,7 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
   if (!s_is_last) return;
   __threadfence();
   const int ngrp = gridDim.x;
-  const int per = (ngrp + kGroup - 1) / kGroup;
+  const int per = (ngrp + kK1Threads - 1) / kK1Threads;
   const int g0 = min(ngrp, (int)threadIdx.x * per), g1 = min(ngrp, g0 + per);
   int keep = 0;
   for (int g = g0; g < g1; ++g) {
@@ -324,7 +411,7 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
   }
   s_part[threadIdx.x] = keep;
   __syncthreads();
-  for (int off = 1; off < kGroup; off <<= 1) {
+  for (int off = 1; off < kK1Threads; off <<= 1) {
     int a = 0;
     if ((int)threadIdx.x >= off) a = s_part[threadIdx.x - off];
     __syncthreads();
@@ -337,8 +424,8 @@ __global__ void __launch_bounds__(128) propagate_stop_kernel(
     const int rows = max(0, min(kGroup, n_alive - g * kGroup));
     pos += rows - __ldcg(b.grp_stops + g);
   }
-  if (threadIdx.x == kGroup - 1) {
-    const int total_keep = s_part[kGroup - 1];
+  if (threadIdx.x == kK1Threads - 1) {
+    const int total_keep = s_part[kK1Threads - 1];
     const int cursor = b.ctrl[6];
     int n_new = 0;
     if (prm.refill) n_new = max(0, min(b.n_slots - total_keep, b.n - cursor));
@@ -571,18 +658,9 @@ __device__ __forceinline__ void build_state_row(const ttl_volume& v, const ttl_p
 
 // rank r of the old alive list -> (number of survivors before r); all lanes return the value.
 __device__ __forceinline__ int survivors_before(const ttl_batch& b, int r, int n_old, int lane) {
-  const int g = r / kGroup, base = g * kGroup, pos = r - base;
-  // 128 stop bytes of the group, 4 per lane
-  const uint32_t word = *reinterpret_cast<const uint32_t*>(b.stop + base + 4 * lane);
-  int cnt = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int q = 4 * lane + k;
-    const bool stopped = (word >> (8 * k)) & 1u;
-    cnt += (q < pos && base + q < n_old && !stopped) ? 1 : 0;
-  }
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  return b.grp_prefix[g] + cnt;
+  const int g = r / kGroup, base = g * kGroup, pos = r - base;      // kGroup == 32: one flag per lane
+  const bool counts = lane < pos && base + lane < n_old && b.stop[base + lane] == 0;
+  return b.grp_prefix[g] + __popc(__ballot_sync(0xffffffffu, counts));
 }
 
 __global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volume v, ttl_params prm,
@@ -802,7 +880,7 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   if (n_upper > b->n_slots) n_upper = b->n_slots;
   if (ttl_div_up(n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->grp_prefix) return TTL_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<<<ttl_div_up(n_upper, 128), 128, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise));
+  TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<<<ttl_div_up(n_upper, kGroup), kK1Threads, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise));
   rc = state_kernels_ready();
   if (rc) return rc;
   TTL_LAUNCH("build_state_kernel", s,

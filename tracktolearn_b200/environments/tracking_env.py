@@ -55,7 +55,7 @@ class _BatchBuffers(object):
         self.ld_bf16 = (state_size + 63) // 64 * 64
         self.state_bf16 = [torch.zeros((slots, self.ld_bf16), dtype=torch.bfloat16, device=device),
                            torch.zeros((slots, self.ld_bf16), dtype=torch.bfloat16, device=device)]
-        self.max_groups = (slots + 127) // 128 + 1
+        self.max_groups = (slots + 31) // 32 + 1
         self.grp_stops = torch.zeros((self.max_groups,), **i32)
         self.grp_prefix = torch.zeros((self.max_groups,), **i32)
 
