@@ -247,9 +247,9 @@ def main_gpu(args):
     stream = torch.cuda.current_stream(dev)
 
     def one_step(action_buf):
-        state = env.current_state()
-        actor.forward_device(state, 0.0, n_rows_dev=env.alive_count_tensor(), n_rows=state.shape[0],
-                             want_logp=False, out_action=action_buf, state_bf16=env.current_state_bf16())
+        actor.forward_device(env.current_state(), 0.0, n_rows_dev=env.alive_count_tensor(),
+                             n_rows=env._n_alive_host, want_logp=False, out_action=action_buf,
+                             state_bf16=env.current_state_bf16(), layout=env.bf16_layout)
         env.step_device(action_buf)
         env.harvest_device()
 
@@ -259,7 +259,7 @@ def main_gpu(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput: inputs already in HBM ----------------------------
-    env.reset_streaming(0, n_seeds, N_ACTOR)
+    env.reset_streaming(0, n_seeds, N_ACTOR, fp32_state=not args.bf16_state_only)
     action_buf = torch.empty((N_ACTOR, 3), dtype=torch.float32, device=dev)
     for _ in range(args.warmup):
         one_step(action_buf)
@@ -350,19 +350,24 @@ def main_gpu(args):
     kernels = {}
     for name, (n, ms) in sorted(prof.items()):
         kernels[name] = {'launches': n, 'avg_us': 1000.0 * ms / n}
+    # algorithmic bytes per row; without the fp32 API tensor the state write is the
+    # 1280-byte bf16 operand instead of the 2460-byte fp32 row
+    state_write = 1280 if args.bf16_state_only else 2460 + 1280
+    state_bytes = 4680 + state_write + 1200 + 12
+    step_bytes = 4680 + state_write + 1200 + 512 + 48
     state_ms = avg_ms('build_state_kernel')
     step_ms = sum(avg_ms(k) or 0.0 for k in ('propagate_stop_kernel', 'build_state_kernel'))
     roofline_step = None
     if state_ms and step_ms:
-        a_state = STATE_KERNEL_BYTES_PER_ROW * rows_prof / (state_ms * 1e-3) / 1e9
-        a_step = STEP_BYTES_PER_ROW * rows_prof / (step_ms * 1e-3) / 1e9
+        a_state = state_bytes * rows_prof / (state_ms * 1e-3) / 1e9
+        a_step = step_bytes * rows_prof / (step_ms * 1e-3) / 1e9
         roofline_step = {
             'build_state_kernel': {'bound': 'hbm', 'achieved': a_state, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                                    'frac': a_state / pk['hbm_gbs'], 'traffic': None,
-                                   'bytes_per_row': STATE_KERNEL_BYTES_PER_ROW},
+                                   'bytes_per_row': state_bytes},
             'env_step (propagate_stop+build_state)': {
                 'bound': 'hbm', 'achieved': a_step, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                'frac': a_step / pk['hbm_gbs'], 'traffic': None, 'bytes_per_row': STEP_BYTES_PER_ROW},
+                'frac': a_step / pk['hbm_gbs'], 'traffic': None, 'bytes_per_row': step_bytes},
             'peak_source': pk['source']}
 
     cpu_baseline = None
@@ -386,6 +391,9 @@ def main_gpu(args):
                        'max_nb_steps': int(env.max_nb_steps), 'actor': '615-' + HIDDEN + '-6 (synthetic, tracking-like)',
                        'env': 'NoisyTrackingEnvironment noise=0 (float64 directions)',
                        'streaming_refill': True, 'alive_at_end': alive_end,
+                       'state_rows': ('bf16 actor operand only; the fp32 API tensor is not materialised in the '
+                                      'device loop (SURVEY 7 step 7)' if args.bf16_state_only
+                                      else 'fp32 API tensor + bf16 actor operand'),
                        'l2': 'inputs larger than L2: 702 MB SH volume + 2x123 MB state rows + 210 MB activations',
                        'parallelism': 'seeds sharded, volume replicated, no data-path collective'},
             'e2e': {'value': e2e_value, 'unit': 'streamline-steps/s',
@@ -414,6 +422,8 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--fp32-state', dest='bf16_state_only', action='store_false',
+                    help='also materialise the fp32 state rows every step (the reference API tensor)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
     a = ap.parse_args()
     if a.warmup < 3:

@@ -99,6 +99,12 @@ typedef struct ttl_batch {
   int32_t max_groups;      /* entries in grp_stops / grp_prefix: ceil(n_slots / 32) + 1 */
   int32_t* grp_stops;      /* [max_groups] streamlines stopped this step per group of 32 ranks */
   int32_t* grp_prefix;     /* [max_groups] exclusive prefix of survivors per group */
+  int32_t bf16_layout;     /* column order of state_bf16 rows: 0 = the reference's
+                              [7*C | 3*n_dirs | 0..]; 1 = channel-padded [7*CP | 3*n_dirs | 0..]
+                              (every neighbourhood point starts on a 16-byte boundary; the actor's
+                              first-layer weights are permuted to match, ttl_actor_plan_set_layout).
+                              state[] may be NULL with layout 1: the fp32 rows are then not
+                              materialised */
 } ttl_batch;
 
 /* ---- one-time / load-time helpers ------------------------------------------------------ */
@@ -192,7 +198,10 @@ int ttl_actor_forward(ttl_actor_plan* plan, const float* state, int32_t ld_state
 int ttl_actor_forward_packed(ttl_actor_plan* plan, const void* state_bf16, int32_t ld,
                              int32_t rows_alloc, const int32_t* n_rows_dev, int32_t n_rows_max,
                              float probabilistic, const float* eps, float* action, float* logp,
-                             float* pre, void* stream);
+                             float* pre, int32_t layout, void* stream);
+/* Prepares the plan for ttl_batch.bf16_layout == 1: packs a copy of the first layer's weights
+ * whose columns follow [n_points*CP | rest] (zero columns for the CP - C padding channels). */
+int ttl_actor_plan_set_layout(ttl_actor_plan* plan, int32_t C, int32_t CP, int32_t n_points, void* stream);
 
 /* Stand-alone dense layer used by the actor and exposed for tests:
  * C[m][ldc] (bf16) = act(A[m][k] (bf16) . W[n][k]^T (bf16) + bias[n]), tcgen05/TMEM/TMA. */

@@ -87,3 +87,25 @@ def test_tracker_track_filters_and_transforms():
     lens = streamline_lengths(batch.data, batch.offsets)
     ref = np.asarray([O.streamline_length(s) for s in batch.streamlines])
     np.testing.assert_allclose(lens, ref, rtol=1e-12, atol=1e-9)
+
+
+def test_bf16_only_state_mode_tracks_the_same_streamlines():
+    """Streaming with the fp32 state tensor materialised vs the bf16-only mode (channel-padded
+    operand layout, permuted first-layer weights): same operand values, only the K order of the
+    first GEMM differs, so trajectories agree to float rounding."""
+    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    n = len(seeds)
+    st = env.reset_streaming(0, n, 256, fp32_state=True)
+    alg.validation_episode(st, env, 0.0)
+    a = env.get_streamlines()
+    st = env.reset_streaming(0, n, 256, fp32_state=False)
+    assert st is None and env.current_state() is None and env.bf16_layout[0] == 1
+    alg.validation_episode(st, env, 0.0)
+    b = env.get_streamlines()
+    same = a.lengths == b.lengths
+    assert same.mean() > 0.98, same.mean()
+    worst = 0.0
+    for i in np.nonzero(same)[0]:
+        worst = max(worst, float(np.abs(a.streamlines[i] - b.streamlines[i]).max()))
+    assert worst < 5e-2, worst
+    assert (a.data_per_streamline['flags'] == b.data_per_streamline['flags'])[same].all()

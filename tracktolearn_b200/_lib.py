@@ -32,7 +32,7 @@ class Batch(ctypes.Structure):
                 ('npts', c_vp), ('dones', c_vp), ('alive', c_vp * 2), ('ctrl', c_vp), ('stop', c_vp), ('dest', c_vp),
                 ('step_flags', c_vp), ('reward', c_vp), ('state', c_vp * 2),
                 ('state_bf16', c_vp * 2), ('ld_bf16', c_i32), ('max_groups', c_i32), ('grp_stops', c_vp),
-                ('grp_prefix', c_vp)]
+                ('grp_prefix', c_vp), ('bf16_layout', c_i32)]
 
 
 class ActorWeights(ctypes.Structure):
@@ -67,7 +67,8 @@ SIGNATURES = {
     'ttl_actor_plan_create': (c_i32, [P(c_vp), P(ActorWeights), c_i32, c_vp, c_i64, c_vp]),
     'ttl_actor_plan_destroy': (None, [c_vp]),
     'ttl_actor_forward': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
-    'ttl_actor_forward_packed': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'ttl_actor_forward_packed': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
+    'ttl_actor_plan_set_layout': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp]),
     'ttl_gemm_bf16': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'ttl_oracle_features': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
     'ttl_oracle_forward': (c_i32, [P(OracleWeights), c_vp, c_i32, c_vp, c_vp]),

@@ -41,11 +41,11 @@ class RLAlgorithm(object):
         it = 0
         limit = max_steps if max_steps is not None else 1 << 30
         while n_up > 0 and it < limit:
-            state = env.current_state()
-            rows = state.shape[0]
+            state = env.current_state()          # None when the env produces bf16 rows only
+            rows = n_up
             actor.forward_device(state, prob, n_rows_dev=env.alive_count_tensor(), n_rows=rows,
                                  want_logp=False, out_action=action_buf,
-                                 state_bf16=env.current_state_bf16())
+                                 state_bf16=env.current_state_bf16(), layout=env.bf16_layout)
             env.step_device(action_buf)
             if env.compute_reward:
                 r = env._batch.reward[:rows].sum(dtype=torch.float64)

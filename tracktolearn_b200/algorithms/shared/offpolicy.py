@@ -49,6 +49,7 @@ class MaxEntropyActor(object):
         self._plan = None
         self._plan_rows = 0
         self._workspace = None
+        self._plan_layout = None
 
     # -- checkpoint format ---------------------------------------------------------------
     def state_dict(self):
@@ -77,6 +78,7 @@ class MaxEntropyActor(object):
         self._plan = None
         self._plan_rows = 0
         self._workspace = None
+        self._plan_layout = None
 
     def __del__(self):
         try:
@@ -115,16 +117,19 @@ class MaxEntropyActor(object):
         self._w_struct = w
 
     def forward_device(self, state, probabilistic, n_rows_dev=None, n_rows=None, eps=None,
-                       want_logp=True, want_pre=False, out_action=None, state_bf16=None):
+                       want_logp=True, want_pre=False, out_action=None, state_bf16=None, layout=None):
         """state: CUDA fp32 [rows, >= state_dim] (row stride free).  ``n_rows_dev``: optional
         device int32 tensor with the live row count (no host sync).  ``state_bf16``: the env's
         bf16 zero-padded copy of the same rows ([rows_alloc, round_up(state_dim, 64)]); with it
         the bf16 tier skips its packing pass.  Returns
         (action [rows,3], logp [rows] or None, pre [rows,6] or None)."""
-        if state.dim() < 2:
-            state = state[None, :]
-        if state.device != self.device or state.dtype != torch.float32 or state.stride(1) != 1:
-            state = state.to(self.device, dtype=torch.float32).contiguous()
+        if state is not None:
+            if state.dim() < 2:
+                state = state[None, :]
+            if state.device != self.device or state.dtype != torch.float32 or state.stride(1) != 1:
+                state = state.to(self.device, dtype=torch.float32).contiguous()
+        elif state_bf16 is None or n_rows is None:
+            raise ValueError('forward_device needs `state`, or `state_bf16` together with `n_rows`')
         rows = int(n_rows if n_rows is not None else state.shape[0])
         A = self.action_dim
         action = out_action if out_action is not None else torch.empty((rows, A), dtype=torch.float32,
@@ -138,10 +143,18 @@ class MaxEntropyActor(object):
         self._ensure_plan(rows)
         prec = _lib.PRECISION_BF16 if self.precision == 'bf16' else _lib.PRECISION_FP32
         if prec == _lib.PRECISION_BF16 and state_bf16 is not None:
+            lay = 0
+            if layout is not None and layout[0] == 1:
+                lay = 1
+                if self._plan_layout != tuple(layout):
+                    _lib.check(self._lib.ttl_actor_plan_set_layout(
+                        self._plan, int(layout[1]), int(layout[2]), int(layout[3]),
+                        _lib.stream_ptr(self.device)), 'ttl_actor_plan_set_layout')
+                    self._plan_layout = tuple(layout)
             _lib.check(self._lib.ttl_actor_forward_packed(
                 self._plan, _lib.ptr(state_bf16), int(state_bf16.stride(0)), int(state_bf16.shape[0]),
                 _lib.ptr(n_rows_dev), rows, float(probabilistic), _lib.ptr(eps), _lib.ptr(action),
-                _lib.ptr(logp), _lib.ptr(pre), _lib.stream_ptr(self.device)), 'ttl_actor_forward_packed')
+                _lib.ptr(logp), _lib.ptr(pre), lay, _lib.stream_ptr(self.device)), 'ttl_actor_forward_packed')
             self._keep = (state_bf16, eps)
             return action, logp, pre
         ld = state.stride(0) if state.shape[0] > 1 else state.shape[1]

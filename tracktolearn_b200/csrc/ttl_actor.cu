@@ -611,6 +611,23 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
   const float x = (r < n_out && c < n_in) ? w[(size_t)r * n_in + c] : 0.f;
   out[t] = __float2bfloat16_rn(x);
 }
+// first-layer weights for the channel-padded input layout: packed column q reads original column
+// p*C + ch for q = p*CP + ch (ch < C), n_points*C + (q - n_points*CP) behind the SH block, else 0
+__global__ void pack_weight_layout_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                          int n_out, int n_in, int n_pad, int k_pad, int C, int CP, int n_pts) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_pad * k_pad) return;
+  const int r = (int)(t / k_pad), q = (int)(t - (long long)r * k_pad);
+  int c = -1;
+  if (q < n_pts * CP) {
+    const int p = q / CP, ch = q - p * CP;
+    if (ch < C) c = p * C + ch;
+  } else {
+    c = n_pts * C + (q - n_pts * CP);
+  }
+  const float x = (r < n_out && c >= 0 && c < n_in) ? w[(size_t)r * n_in + c] : 0.f;
+  out[t] = __float2bfloat16_rn(x);
+}
 __global__ void pack_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int n_out, int n_pad) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n_pad) out[t] = t < n_out ? b[t] : 0.f;
@@ -941,6 +958,9 @@ struct ttl_actor_plan {
   int max_kpad, max_width;
   CUtensorMap map_w[TTL_ACTOR_MAX_LAYERS];
   CUtensorMap map_w2[TTL_ACTOR_MAX_LAYERS];  // 128-row box for the 2-CTA kernel
+  __nv_bfloat16* w0_alt;                     // first-layer weights for bf16_layout 1
+  CUtensorMap map_w0_alt, map_w0_alt2;
+  bool has_alt;
   CUtensorMap map_a[TTL_ACTOR_MAX_LAYERS];  // A operand of layer i
   // first-layer operand maps for caller-owned bf16 state buffers (ttl_actor_forward_packed)
   struct ExtMap { const void* ptr; int rows; CUtensorMap map; };
@@ -952,7 +972,7 @@ constexpr int F32_CHUNK = 8192;
 
 struct Layout {
   int64_t total;
-  int64_t off_w[TTL_ACTOR_MAX_LAYERS], off_b[TTL_ACTOR_MAX_LAYERS], off_act[2], off_f32[2], off_hp;
+  int64_t off_w[TTL_ACTOR_MAX_LAYERS], off_b[TTL_ACTOR_MAX_LAYERS], off_act[2], off_f32[2], off_hp, off_w0_alt;
   int k_pad[TTL_ACTOR_MAX_LAYERS], n_pad[TTL_ACTOR_MAX_LAYERS];
   int max_kpad, max_width;
 };
@@ -979,6 +999,7 @@ int plan_layout(const ttl_actor_weights* w, int max_rows, Layout* L) {
   for (int j = 0; j < 2; ++j) L->off_act[j] = take((int64_t)max_rows * L->max_kpad * 2);
   for (int j = 0; j < 2; ++j) L->off_f32[j] = take((int64_t)F32_CHUNK * L->max_width * 4);
   L->off_hp = take((int64_t)max_rows * 4 * 8 * 4);
+  L->off_w0_alt = take((int64_t)L->n_pad[0] * L->k_pad[0] * 2);
   L->total = off;
   return 0;
 }
@@ -989,7 +1010,7 @@ namespace {
 // map_a0: TMA map of the first layer's bf16 operand [rows][k_pad[0]].
 int run_bf16_layers(ttl_actor_plan* p, const CUtensorMap& map_a0, const int32_t* n_rows_dev,
                     int32_t n_rows_max, float probabilistic, const float* eps, float* action, float* logp,
-                    float* pre, cudaStream_t s) {
+                    float* pre, cudaStream_t s, bool alt_w0 = false) {
   const ttl_actor_weights& w = p->w;
   const int nl = w.n_layers;
   const int n_out = w.out_dim[nl - 1], k_last = w.in_dim[nl - 1];
@@ -1003,7 +1024,9 @@ int run_bf16_layers(ttl_actor_plan* p, const CUtensorMap& map_a0, const int32_t*
   for (int i = 0; i < nl - 1; ++i) {
     // layer i: act[i&1] (pitch k_pad[i]) -> act[(i+1)&1] (pitch k_pad[i+1] = n_pad[i])
     const bool fused = p->fuse_head && i == nl - 2;
-    int rc = launch_dense_bf16(i == 0 ? map_a0 : p->map_a[i], p->map_w[i], p->map_w2[i], p->bq[i], p->act[(i + 1) & 1],
+    const bool alt = alt_w0 && i == 0;
+    int rc = launch_dense_bf16(i == 0 ? map_a0 : p->map_a[i], alt ? p->map_w0_alt : p->map_w[i],
+                               alt ? p->map_w0_alt2 : p->map_w2[i], p->bq[i], p->act[(i + 1) & 1],
                                p->n_pad[i], n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1, s,
                                fused ? w.w[nl - 1] : nullptr, k_last, fused ? p->head_partial : nullptr);
     if (rc) return rc;
@@ -1053,6 +1076,8 @@ int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int3
   const int nl = w->n_layers;
   for (int i = 0; i < nl; ++i) { p->k_pad[i] = L.k_pad[i]; p->n_pad[i] = L.n_pad[i]; }
   p->head_partial = reinterpret_cast<float*>(ws + L.off_hp);
+  p->w0_alt = reinterpret_cast<__nv_bfloat16*>(ws + L.off_w0_alt);
+  p->has_alt = false;
   // the last hidden layer can carry the head when it is 6 wide and the layer fits 4 n-tiles
   p->fuse_head = w->out_dim[nl - 1] == HEAD_OUT_FUSED && L.n_pad[nl - 2] <= 1024;
   for (int i = 0; i < nl - 1; ++i) {  // hidden layers run on tensor cores
@@ -1139,8 +1164,10 @@ int ttl_actor_forward(ttl_actor_plan* p, const float* state, int32_t ld_state, c
 
 int ttl_actor_forward_packed(ttl_actor_plan* p, const void* state_bf16, int32_t ld, int32_t rows_alloc,
                              const int32_t* n_rows_dev, int32_t n_rows_max, float probabilistic,
-                             const float* eps, float* action, float* logp, float* pre, void* stream) {
+                             const float* eps, float* action, float* logp, float* pre, int32_t layout,
+                             void* stream) {
   if (!p || !state_bf16 || !action || n_rows_max > p->max_rows || n_rows_max > rows_alloc) return TTL_ERR_BAD_ARG;
+  if (layout != 0 && !(layout == 1 && p->has_alt)) return TTL_ERR_BAD_ARG;
   if (ld != p->k_pad[0] || (reinterpret_cast<uintptr_t>(state_bf16) & 15)) return TTL_ERR_BAD_ARG;
   if (probabilistic != 0.f && !eps) return TTL_ERR_BAD_ARG;
   if (n_rows_max <= 0) return 0;
@@ -1158,7 +1185,25 @@ int ttl_actor_forward_packed(ttl_actor_plan* p, const void* state_bf16, int32_t 
     map = &p->ext_maps.back().map;
   }
   return run_bf16_layers(p, *map, n_rows_dev, n_rows_max, probabilistic, eps, action, logp, pre,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, layout == 1);
+}
+
+int ttl_actor_plan_set_layout(ttl_actor_plan* p, int32_t C, int32_t CP, int32_t n_points, void* stream) {
+  if (!p || C <= 0 || CP < C || n_points <= 0) return TTL_ERR_BAD_ARG;
+  const int n_in = p->w.in_dim[0];
+  if (n_points * C > n_in || n_points * CP + (n_in - n_points * C) > p->k_pad[0]) return TTL_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long tot = (long long)p->n_pad[0] * p->k_pad[0];
+  TTL_LAUNCH("pack_weight_layout_kernel", s,
+             pack_weight_layout_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(p->w.w[0], p->w0_alt, p->w.out_dim[0], n_in,
+                                                                          p->n_pad[0], p->k_pad[0], C, CP, n_points));
+  int rc = make_tmap(&p->map_w0_alt, p->w0_alt, (uint64_t)p->n_pad[0], (uint64_t)p->k_pad[0], BN);
+  if (rc) return rc;
+  rc = make_tmap(&p->map_w0_alt2, p->w0_alt, (uint64_t)p->n_pad[0], (uint64_t)p->k_pad[0], BN / 2);
+  if (rc) return rc;
+  p->has_alt = true;
+  TTL_CHECK_LAST();
+  return 0;
 }
 
 int ttl_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t m, int32_t n,

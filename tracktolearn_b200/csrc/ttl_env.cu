@@ -646,10 +646,72 @@ __device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, 
   __syncwarp();
 }
 
+// bf16-only fast path (ttl_batch.bf16_layout == 1, no fp32 row): the state is produced straight
+// as the actor's first-layer operand.  Point p owns columns [48p, 48p+48) so every (point, chunk)
+// work item converts its float4 to 4 bf16 and stores 8 aligned bytes from registers; previous
+// directions follow at column 336.  No row staging: 512 B of shared memory per warp.
+__device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
+                                         __nv_bfloat16* __restrict__ out, int n_bf16, float* smem_f, int lane) {
+  constexpr int CP = 48, CP4 = 12, S = 7 * CP;
+  float* s_w = smem_f;
+  int* s_vox = reinterpret_cast<int*>(smem_f + 64);
+  corner_table(v, prm, P + (size_t)(L - 1) * 3, s_w, s_vox, lane);
+  __syncwarp();
+  const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int item = lane + 32 * t;
+    if (item < 7 * CP4) {
+      const int p = item / CP4, ck = item - p * CP4;
+      const int4 v0 = *reinterpret_cast<const int4*>(s_vox + p * 8);
+      const int4 v1 = *reinterpret_cast<const int4*>(s_vox + p * 8 + 4);
+      const int vx[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float4 a[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = __ldg(vol4 + (size_t)vx[k] * CP4 + ck);
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + p * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + p * 8 + 4);
+      const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc.x = fmaf(wk[k], a[k].x, acc.x);
+        acc.y = fmaf(wk[k], a[k].y, acc.y);
+        acc.z = fmaf(wk[k], a[k].z, acc.z);
+        acc.w = fmaf(wk[k], a[k].w, acc.w);
+      }
+      // the volume's padding channels are zero, so columns 45..47 of every point come out zero
+      // (NaN weights excepted, and those columns meet zero weights in the actor anyway)
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
+      *reinterpret_cast<uint2*>(out + p * CP + ck * 4) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    }
+  }
+  // previous directions, newest first, zero padded (env.py:549-563): two elements per lane
+  const int nd3 = prm.n_dirs * 3;
+  const float* last = P + (size_t)(L - 1) * 3;   // element j = last[c - 3k] - last[c - 3k - 3]
+  for (int j = 2 * lane; j < n_bf16 - S; j += 64) {
+    float val[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int jj = j + e;
+      const int k = jj / 3, c = jj - 3 * k;
+      val[e] = 0.f;
+      if (jj < nd3 && k < L - 1) val[e] = __fsub_rn(__ldg(last + c - 3 * k), __ldg(last + c - 3 * k - 3));
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(val[0], val[1]);
+    *reinterpret_cast<__nv_bfloat162*>(out + S + j) = h;
+  }
+}
+
 __device__ __forceinline__ void build_state_row(const ttl_volume& v, const ttl_params& prm, const float* P,
                                                 int L, float* __restrict__ out_f32, int n_f32,
                                                 __nv_bfloat16* __restrict__ out_bf16, int n_bf16,
-                                                float* smem_f, int lane) {
+                                                float* smem_f, int lane, int layout = 0) {
+  if (layout == 1) {   // host guarantees C == 45, CP == 48, no fp32 row
+    build_state_row_c45_bf16(v, prm, P, L, out_bf16, n_bf16, smem_f, lane);
+    return;
+  }
   if (v.C == 45 && v.CP == 48 && max(n_f32, n_bf16) <= kMaxStateLd)
     build_state_row_c45(v, prm, P, L, out_f32, n_f32, out_bf16, n_bf16, smem_f, lane);
   else
@@ -699,8 +761,8 @@ __global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volum
   __nv_bfloat16* o16 = b.state_bf16[cur ^ 1]
                            ? reinterpret_cast<__nv_bfloat16*>(b.state_bf16[cur ^ 1]) + (size_t)dst * b.ld_bf16
                            : nullptr;
-  build_state_row(v, prm, P, L, b.state[cur ^ 1] + (size_t)dst * b.ld_state, b.ld_state, o16, b.ld_bf16,
-                  smem_f, lane);
+  float* o32 = b.state[cur ^ 1] ? b.state[cur ^ 1] + (size_t)dst * b.ld_state : nullptr;
+  build_state_row(v, prm, P, L, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
 }
 
 // reset: alive[0] = identity, state goes to state[0]
@@ -715,7 +777,8 @@ __global__ void __launch_bounds__(kStateWarps * 32) reset_state_kernel(ttl_volum
   __nv_bfloat16* o16 = b.state_bf16[0]
                            ? reinterpret_cast<__nv_bfloat16*>(b.state_bf16[0]) + (size_t)r * b.ld_bf16
                            : nullptr;
-  build_state_row(v, prm, P, 1, b.state[0] + (size_t)r * b.ld_state, b.ld_state, o16, b.ld_bf16, smem_f, lane);
+  float* o32 = b.state[0] ? b.state[0] + (size_t)r * b.ld_state : nullptr;
+  build_state_row(v, prm, P, 1, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
 }
 
 // stand-alone _format_state for arbitrary streamlines [n][L][3]
@@ -832,6 +895,18 @@ int check_common(const ttl_volume* vol, const ttl_params* prm) {
   return 0;
 }
 
+// bf16_layout 1 needs the order-8 volume and room for 7*48 + 3*n_dirs columns; without fp32 rows
+// the bf16 rows must exist
+int check_layout(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b) {
+  if (b->bf16_layout == 0) return (b->state[0] && b->state[1]) ? 0 : TTL_ERR_BAD_ARG;
+  if (b->bf16_layout != 1) return TTL_ERR_BAD_ARG;
+  if (vol->C != 45 || vol->CP != 48) return TTL_ERR_UNSUPPORTED;
+  if (!b->state_bf16[0] || !b->state_bf16[1] || (b->ld_bf16 & 7)) return TTL_ERR_BAD_ARG;
+  if (7 * 48 + 3 * prm->n_dirs > b->ld_bf16) return TTL_ERR_UNSUPPORTED;
+  if (b->state[0] || b->state[1]) return TTL_ERR_BAD_ARG;   // layout 1 is the bf16-only mode
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -855,6 +930,8 @@ int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch*
   if (!b || !seeds || b->n > b->capacity || b->ld_state > kMaxStateLd || (b->ld_state & 3) ||
       b->ld_state < 7 * vol->C + 3 * prm->n_dirs || b->n_slots <= 0)
     return TTL_ERR_BAD_ARG;
+  rc = check_layout(vol, prm, b);
+  if (rc) return rc;
   if (b->n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const int n_init = b->n > b->n_slots ? b->n : b->n_slots;
@@ -876,6 +953,8 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   if (!b || !actions || lda < 3 || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
   if (prm->compute_reward && !vol->peaks) return TTL_ERR_BAD_ARG;
   if (prm->refill && prm->state_stopped) return TTL_ERR_BAD_ARG;
+  rc = check_layout(vol, prm, b);
+  if (rc) return rc;
   if (n_upper <= 0) return 0;
   if (n_upper > b->n_slots) n_upper = b->n_slots;
   if (ttl_div_up(n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->grp_prefix) return TTL_ERR_BAD_ARG;

@@ -29,7 +29,8 @@ class _BatchBuffers(object):
     ``rows``: seeds held by the batch (one streamline buffer row each); ``slots``: streamlines
     tracked at once (== rows unless the streaming tracker refills freed slots)."""
 
-    def __init__(self, rows, slots, max_pts, state_size, device):
+    def __init__(self, rows, slots, max_pts, state_size, device, fp32_state=True):
+        self.fp32_state = fp32_state
         self.rows = rows
         self.slots = slots
         self.max_pts = max_pts
@@ -48,8 +49,11 @@ class _BatchBuffers(object):
         self.dest = torch.zeros((pad,), **i32)
         self.step_flags = torch.zeros((pad,), **i32)
         self.reward = torch.zeros((pad,), dtype=torch.float32, device=device)
-        self.state = [torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device),
-                      torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device)]
+        # fp32 state rows (the API's state tensor).  Without them the step kernel produces only the
+        # bf16 rows, in the channel-padded column layout (ttl_batch.bf16_layout = 1).
+        self.state = ([torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device),
+                       torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device)]
+                      if fp32_state else [None, None])
         self.ctrl_host = torch.zeros((16,), dtype=torch.int32).pin_memory()
         # bf16 copy of the state rows, zero padded to a multiple of 64: the actor's TMA operand
         self.ld_bf16 = (state_size + 63) // 64 * 64
@@ -73,8 +77,10 @@ class _BatchBuffers(object):
         b.state_bf16[1] = self.state_bf16[1].data_ptr()
         b.alive[0] = self.alive[0].data_ptr()
         b.alive[1] = self.alive[1].data_ptr()
-        b.state[0] = self.state[0].data_ptr()
-        b.state[1] = self.state[1].data_ptr()
+        if self.fp32_state:
+            b.state[0] = self.state[0].data_ptr()
+            b.state[1] = self.state[1].data_ptr()
+        b.bf16_layout = 0 if self.fp32_state else 1
         return b
 
 
@@ -82,27 +88,30 @@ class TrackingEnvironment(BaseEnv):
     """Reference: environments/tracking_env.py:13."""
 
     # ------------------------------------------------------------------------------ reset
-    def _ensure_buffers(self, rows, slots):
+    def _ensure_buffers(self, rows, slots, fp32_state=True):
         need_pts = self.max_nb_steps + 1
         S = self.get_state_size()
         bb = self._batch
         if (bb is None or bb.rows < rows or bb.slots < slots or bb.max_pts != need_pts
-                or bb.state_size != S):
+                or bb.state_size != S or bb.fp32_state != fp32_state):
             rows = max(rows, bb.rows if bb is not None else 0)
             slots = max(slots, bb.slots if bb is not None else 0)
             self._batch = None
-            bb = _BatchBuffers(rows, slots, need_pts, S, self.device)
+            bb = _BatchBuffers(rows, slots, need_pts, S, self.device, fp32_state)
             self._batch = bb
         return bb
 
-    def _start(self, initial_points, n_slots=None):
+    def _start(self, initial_points, n_slots=None, fp32_state=True):
         """``n_slots`` < N turns on the streaming tracker: only n_slots streamlines are alive
-        at once and slots freed by stopped ones take the next seeds in the same step."""
+        at once and slots freed by stopped ones take the next seeds in the same step.
+        ``fp32_state=False``: only the bf16 actor operand is produced (no fp32 state tensor)."""
+        if not fp32_state and (self._n_coefs != 45 or 7 * 48 + 3 * self.n_dirs > (self.get_state_size() + 63) // 64 * 64):
+            fp32_state = True      # the bf16-only layout is specialised for the order-8 volume
         self.initial_points = initial_points
         N = initial_points.shape[0]
         streaming = n_slots is not None and n_slots < N
         slots = n_slots if streaming else max(N, 1)
-        bb = self._ensure_buffers(max(N, 1), slots)
+        bb = self._ensure_buffers(max(N, 1), slots, fp32_state)
         self._n = N
         self._b = bb.as_struct(N, slots)
         self._params.refill = int(streaming)
@@ -121,7 +130,7 @@ class TrackingEnvironment(BaseEnv):
                                            ctypes.byref(self._b), _lib.ptr(seeds_dev),
                                            _lib.stream_ptr(self.device)), 'ttl_env_reset')
         self._seeds_dev = seeds_dev   # keep alive until the kernel ran
-        return self._state_view(0, self._n_alive_host)
+        return self._state_view(0, self._n_alive_host) if bb.fp32_state else None
 
     def _state_view(self, which, n):
         return self._batch.state[which][:n, :self._batch.state_size]
@@ -130,10 +139,12 @@ class TrackingEnvironment(BaseEnv):
         """Reference: tracking_env.py:91-133."""
         return self._start(self.seeds[start:end])
 
-    def reset_streaming(self, start, end, n_slots):
+    def reset_streaming(self, start, end, n_slots, fp32_state=True):
         """Like ``reset`` but at most ``n_slots`` streamlines are tracked at once; the others
-        wait in the batch and take over slots as streamlines stop (device-side refill)."""
-        return self._start(self.seeds[start:end], n_slots=n_slots)
+        wait in the batch and take over slots as streamlines stop (device-side refill).
+        With ``fp32_state=False`` the fp32 state tensor is not materialised: the step kernel
+        writes the actor's bf16 operand only (``current_state_bf16()``)."""
+        return self._start(self.seeds[start:end], n_slots=n_slots, fp32_state=fp32_state)
 
     def nreset(self, n_seeds):
         """Reference: tracking_env.py:47-89."""
@@ -185,8 +196,16 @@ class TrackingEnvironment(BaseEnv):
         return (int(h[4]) & 0xffffffff) | (int(h[5]) << 32)
 
     def current_state(self):
-        """State rows of the alive set, [n_alive_upper_bound, state_size] view (no sync)."""
+        """State rows of the alive set, [n_alive_upper_bound, state_size] view (no sync).
+        None when the batch was started without fp32 state rows."""
+        if not self._batch.fp32_state:
+            return None
         return self._state_view(self._cur, self._n_alive_host)
+
+    @property
+    def bf16_layout(self):
+        """(layout id, C, CP, n_points) of ``current_state_bf16()`` rows."""
+        return (0 if self._batch.fp32_state else 1, self._n_coefs, self._volume.CP, 7)
 
     def current_state_bf16(self):
         """bf16, zero-padded copy of ``current_state()`` ([slots, round_up(state_size, 64)]) that

@@ -68,7 +68,9 @@ class Tracker(object):
             if slots is None or slots >= end - start:
                 state = env.reset(start, end)
             else:
-                state = env.reset_streaming(start, end, slots)
+                # the bf16 actor reads the bf16 rows only: do not materialise the fp32 state
+                bf16_actor = getattr(self.alg.agent.actor, 'precision', 'fp32') == 'bf16'
+                state = env.reset_streaming(start, end, slots, fp32_state=not bf16_actor)
             self.alg.validation_episode(state, env, self.prob)
             yield env.get_streamlines()
 
