@@ -294,7 +294,7 @@ def main_gpu(args):
     rows_prof = alive_end   # alive count is pinned at n_actor while seeds remain
 
     # ---- end to end through the public API, host buffers ------------------------------------
-    e2e_seeds = min(n_seeds, 4 * N_ACTOR) if not args.no_e2e else N_ACTOR // 50
+    e2e_seeds = min(n_seeds, 16 * N_ACTOR) if not args.no_e2e else N_ACTOR // 50
     env_seeds_all = env.seeds
     env.seeds = env_seeds_all[:e2e_seeds]
     tracker = Tracker(alg, N_ACTOR, min_length=10.0, max_length=MAX_LENGTH_MM)
@@ -305,7 +305,7 @@ def main_gpu(args):
     e2e_units = 0
     e2e_steps = 0
     n_streamlines = 0
-    for batch in tracker.track_packed(env):       # seeds H2D, episode, packed streamlines D2H
+    for batch in tracker.track_packed(env, copy=False):   # seeds H2D, episodes, packed streamlines D2H
         d2h += batch.data.nbytes + batch.offsets.nbytes + batch.data_per_streamline['flags'].nbytes
         e2e_units += env.streamline_steps()
         e2e_steps += alg.last_episode_steps

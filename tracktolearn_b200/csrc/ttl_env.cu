@@ -452,6 +452,7 @@ constexpr int kMaxCP = 128;        // padded channels per voxel
 // per-warp shared memory: 56 weights, 56 voxel ids, staged points, the output row
 constexpr int kWarpSmemFloats = 64 + 64 + kMaxDirPts * 3 + kMaxStateLd;
 constexpr int kWarpSmemBytes = ((kWarpSmemFloats * 4 + 127) / 128) * 128;
+constexpr int kWarpSmemSmall = 512;   // weights + voxel ids only (bf16-only path)
 
 struct TriAxis {  // one axis of one neighbourhood point
   int i0, i1;     // clamped lower / upper lattice index
@@ -481,6 +482,14 @@ __device__ __forceinline__ void tri_weights(float dx, float dy, float dz, float 
   w[5] = xz - xyz;                                  // 101
   w[6] = xy - xyz;                                  // 110
   w[7] = xyz;                                       // 111
+}
+
+// volatile: keeps the compiler from sinking the gathers next to their uses (it otherwise
+// serialises them to save registers and the kernel loses its memory-level parallelism)
+__device__ __forceinline__ float4 ldg_nc_v4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
 }
 
 // phase 0 shared by both paths: lane i (and i+32) owns corner i = 8*p + c of the 7-point
@@ -658,30 +667,38 @@ __device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& 
   corner_table(v, prm, P + (size_t)(L - 1) * 3, s_w, s_vox, lane);
   __syncwarp();
   const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
+  // all 24 gathers of this lane's three work items are issued before the first is consumed
+  float4 a[3][8];
+  int pp[3], cc[3];
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
-    const int item = lane + 32 * t;
-    if (item < 7 * CP4) {
-      const int p = item / CP4, ck = item - p * CP4;
-      const int4 v0 = *reinterpret_cast<const int4*>(s_vox + p * 8);
-      const int4 v1 = *reinterpret_cast<const int4*>(s_vox + p * 8 + 4);
-      const int vx[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      float4 a[8];
+    const int item = min(lane + 32 * t, 7 * CP4 - 1);
+    const int p = item / CP4, ck = item - p * CP4;
+    pp[t] = p;
+    cc[t] = ck;
+    const int4 v0 = *reinterpret_cast<const int4*>(s_vox + p * 8);
+    const int4 v1 = *reinterpret_cast<const int4*>(s_vox + p * 8 + 4);
+    const int vx[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a[k] = __ldg(vol4 + (size_t)vx[k] * CP4 + ck);
-      const float4 w0 = *reinterpret_cast<const float4*>(s_w + p * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(s_w + p * 8 + 4);
-      const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 8; ++k) a[t][k] = ldg_nc_v4(vol4 + (size_t)vx[k] * CP4 + ck);
+  }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        acc.x = fmaf(wk[k], a[k].x, acc.x);
-        acc.y = fmaf(wk[k], a[k].y, acc.y);
-        acc.z = fmaf(wk[k], a[k].z, acc.z);
-        acc.w = fmaf(wk[k], a[k].w, acc.w);
-      }
-      // the volume's padding channels are zero, so columns 45..47 of every point come out zero
-      // (NaN weights excepted, and those columns meet zero weights in the actor anyway)
+  for (int t = 0; t < 3; ++t) {
+    const int p = pp[t], ck = cc[t];
+    const float4 w0 = *reinterpret_cast<const float4*>(s_w + p * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(s_w + p * 8 + 4);
+    const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc.x = fmaf(wk[k], a[t][k].x, acc.x);
+      acc.y = fmaf(wk[k], a[t][k].y, acc.y);
+      acc.z = fmaf(wk[k], a[t][k].z, acc.z);
+      acc.w = fmaf(wk[k], a[t][k].w, acc.w);
+    }
+    // the volume's padding channels are zero, so columns 45..47 of every point come out zero
+    // (NaN weights excepted, and those columns meet zero weights in the actor anyway)
+    if (lane + 32 * t < 7 * CP4) {
       __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
       *reinterpret_cast<uint2*>(out + p * CP + ck * 4) =
           make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
@@ -726,10 +743,10 @@ __device__ __forceinline__ int survivors_before(const ttl_batch& b, int r, int n
 }
 
 __global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volume v, ttl_params prm,
-                                                                       ttl_batch b, int cur) {
+                                                                       ttl_batch b, int cur, int warp_smem) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * kWarpSmemBytes);
+  float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * warp_smem);
   const int r = blockIdx.x * kStateWarps + warp;
   const int n_old = b.ctrl[3];
   if (r >= n_old) return;
@@ -767,10 +784,10 @@ __global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volum
 
 // reset: alive[0] = identity, state goes to state[0]
 __global__ void __launch_bounds__(kStateWarps * 32) reset_state_kernel(ttl_volume v, ttl_params prm,
-                                                                       ttl_batch b) {
+                                                                       ttl_batch b, int warp_smem) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * kWarpSmemBytes);
+  float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * warp_smem);
   const int r = blockIdx.x * kStateWarps + warp;
   if (r >= min(b.n, b.n_slots)) return;
   const float* P = b.points + (size_t)r * b.max_pts * 3;
@@ -939,8 +956,12 @@ int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch*
   const int n0 = b->n < b->n_slots ? b->n : b->n_slots;
   rc = state_kernels_ready();
   if (rc) return rc;
+  // the bf16-only path keeps just the corner table in shared memory: a small allocation leaves
+  // the SM's 228 KB to L1, which is what dedupes the overlapping trilinear corners
+  const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;
   TTL_LAUNCH("reset_state_kernel", s,
-             reset_state_kernel<<<ttl_div_up(n0, kStateWarps), kStateWarps * 32, kStateSmem, s>>>(*vol, *prm, *b));
+             reset_state_kernel<<<ttl_div_up(n0, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
+                 *vol, *prm, *b, warp_smem));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -962,9 +983,10 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<<<ttl_div_up(n_upper, kGroup), kK1Threads, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise));
   rc = state_kernels_ready();
   if (rc) return rc;
+  const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;
   TTL_LAUNCH("build_state_kernel", s,
-             build_state_kernel<<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateSmem, s>>>(*vol, *prm, *b,
-                                                                                                     cur));
+             build_state_kernel<<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
+                 *vol, *prm, *b, cur, warp_smem));
   TTL_CHECK_LAST();
   return 0;
 }

@@ -302,9 +302,11 @@ class TrackingEnvironment(BaseEnv):
             cache[name] = buf
         return buf[:numel]
 
-    def get_streamlines(self):
+    def get_streamlines(self, copy=True):
         """Reference: tracking_env.py:247-294.  The last point is dropped when the CURVATURE or
-        MASK flag stopped the streamline.  One packed D2H copy through pinned memory."""
+        MASK flag stopped the streamline.  One packed D2H copy through pinned memory; with
+        ``copy=False`` the returned arrays are views of that staging memory and are only valid
+        until the next call."""
         pts, offsets = self.get_streamlines_device()
         N = self._n
         h_pts = self._pinned('pts', pts.numel(), torch.float32)
@@ -314,6 +316,9 @@ class TrackingEnvironment(BaseEnv):
         h_off.copy_(offsets, non_blocking=True)
         h_flags.copy_(self._batch.flags[:N], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return Tractogram(data=h_pts.numpy().reshape(-1, 3).copy(), offsets=h_off.numpy().copy(),
+        data, off = h_pts.numpy().reshape(-1, 3), h_off.numpy()
+        if copy:
+            data, off = data.copy(), off.copy()
+        return Tractogram(data=data, offsets=off,
                           data_per_streamline={'seeds': np.asarray(self.initial_points),
                                                'flags': h_flags.numpy().astype(int)})

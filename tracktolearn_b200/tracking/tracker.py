@@ -60,9 +60,10 @@ class Tracker(object):
         for start in range(0, n_seeds, rows):
             yield start, min(start + rows, n_seeds), self.n_actor
 
-    def track_packed(self, env):
-        """Yields (Tractogram with voxel-space packed streamlines, seeds, flags) per pass;
-        no length filter, no space change."""
+    def track_packed(self, env, copy=True):
+        """Yields a Tractogram with voxel-space packed streamlines (+ seeds, flags) per pass;
+        no length filter, no space change.  ``copy=False``: each batch aliases the env's pinned
+        staging buffers and must be consumed before the next one is requested."""
         self.alg.agent.eval()
         for start, end, slots in self._passes(env):
             if slots is None or slots >= end - start:
@@ -72,7 +73,7 @@ class Tracker(object):
                 bf16_actor = getattr(self.alg.agent.actor, 'precision', 'fp32') == 'bf16'
                 state = env.reset_streaming(start, end, slots, fp32_state=not bf16_actor)
             self.alg.validation_episode(state, env, self.prob)
-            yield env.get_streamlines()
+            yield env.get_streamlines(copy=copy)
 
     def track(self, env, tracts_format='trk'):
         """Reference: tracking/tracker.py:62-150.  ``tracts_format``: 'trk' / 'tck' (or the
@@ -114,7 +115,7 @@ class Tracker(object):
         writer = (TrkWriter(path, dims, voxel_sizes, affine, self.save_seeds) if fmt == 'trk'
                   else TckWriter(path))
         try:
-            for batch in self.track_packed(env):
+            for batch in self.track_packed(env, copy=False):
                 lens = streamline_lengths(batch.data, batch.offsets)
                 keep = (lo <= lens) & (lens <= hi)
                 npts = np.diff(batch.offsets)
