@@ -298,6 +298,10 @@ def main_gpu(args):
     env_seeds_all = env.seeds
     env.seeds = env_seeds_all[:e2e_seeds]
     tracker = Tracker(alg, N_ACTOR, min_length=10.0, max_length=MAX_LENGTH_MM)
+    # one untimed pass first: device buffers and pinned staging memory are allocated once per
+    # process (W >= 3 warm-up rule applies to the e2e leg too), then the same call is timed
+    for batch in tracker.track_packed(env, copy=False):
+        pass
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
