@@ -136,6 +136,21 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
                  const float* actions, int32_t lda, const double* noise, int32_t n_upper,
                  void* stream);
 
+/* The same step split in two so that TractOracle-Net can be consulted in between
+ * (OracleStoppingCriterion, stopping_criteria.py:113-154: stop where the score < 0.5 once the
+ * streamline has more than min_pts_stop points; OracleReward, oracle_reward.py:45-93: `bonus` for
+ * streamlines done this step with more than min_pts_reward points and score > 0.5):
+ *   ttl_env_step_begin          propagate + LENGTH/CURVATURE/MASK + alignment reward
+ *   ttl_oracle_features_rows    resample(128)+diff of the alive streamlines   \  caller, between
+ *   ttl_oracle_forward          scores [n_alive]                              /  the two calls
+ *   ttl_env_step_finish         ORACLE flag, bonus, compaction bookkeeping, state rows */
+int ttl_env_step_begin(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                       const float* actions, int32_t lda, const double* noise, int32_t n_upper,
+                       void* stream);
+int ttl_env_step_finish(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                        const float* scores, int32_t use_stop, int32_t min_pts_stop, int32_t min_pts_reward,
+                        float bonus, int32_t n_upper, void* stream);
+
 /* state[cur^1][dest[r]] -> out[r] for r < n_rows: the `self.state[self.continue_idx]` that
  * step() returns, in the order of the pre-harvest alive list (tracking_env.py:217-218). */
 int ttl_env_gather_step_state(const ttl_batch* b, int32_t cur, int32_t n_rows, float* out,
@@ -235,6 +250,9 @@ typedef struct ttl_oracle_weights {
  * [offsets[n]][3] fp32 -> dirs [n][127][3] fp32. */
 int ttl_oracle_features(const float* points, const int64_t* offsets, int32_t n, float* dirs,
                         void* stream);
+/* Same for the alive streamlines of a tracking batch (rows of alive[cur], npts points each):
+ * dirs [n_alive][127][3]. */
+int ttl_oracle_features_rows(const ttl_batch* b, int32_t cur, int32_t n_upper, float* dirs, void* stream);
 /* TransformerOracle.forward: dirs [n][127][3] -> scores [n] fp32. */
 int ttl_oracle_forward(const ttl_oracle_weights* w, const float* dirs, int32_t n, float* scores,
                        void* stream);

@@ -257,7 +257,7 @@ class OracleEnv:
     def __init__(self, sh, mask, seeds, voxel_size, step_size_mm, theta=30., n_dirs=100,
                  max_length_mm=200., min_length_mm=20., threshold=0.1, peaks=None,
                  compute_reward=False, alignment_weighting=1.0, noisy=False, noise=0.0,
-                 rng=None):
+                 rng=None, oracle_ckpt=None, oracle_stopping=False, oracle_bonus=0.0):
         self.volume = np.ascontiguousarray(sh, dtype=np.float32)
         self.seeds = np.asarray(seeds)
         self.theta = theta
@@ -275,15 +275,23 @@ class OracleEnv:
         self.peaks = peaks
         self.compute_reward = compute_reward
         self.alignment_weighting = alignment_weighting
+        self.oracle_ckpt = oracle_ckpt
+        self.oracle_stopping = oracle_stopping
+        self.oracle_bonus = oracle_bonus
 
     # ---- env.py:567-603 in the dict order of env.py:233-260 (no oracle criterion here)
     def _is_stopping(self, streamlines):
         n = len(streamlines)
         should_stop = np.zeros(n, dtype=bool)
         flags = np.zeros(n, dtype=int)
-        for bit, hit in ((LENGTH, is_too_long(streamlines, self.max_nb_steps)),
-                         (CURVATURE, is_too_curvy(streamlines, self.theta)),
-                         (MASK, self.mask_criterion(streamlines))):
+        criteria = [(LENGTH, is_too_long(streamlines, self.max_nb_steps)),
+                    (CURVATURE, is_too_curvy(streamlines, self.theta))]
+        if self.oracle_ckpt is not None and self.oracle_stopping:
+            # stopping_criteria.py:113-154 with min_nb_steps * 5 (env.py:246-253)
+            if streamlines.shape[1] > self.min_nb_steps * 5:
+                criteria.append((ORACLE, oracle_predict(self.oracle_ckpt, list(streamlines)) < 0.5))
+        criteria.append((MASK, self.mask_criterion(streamlines)))
+        for bit, hit in criteria:
             flags[hit] |= bit
             should_stop[hit] = True
         return should_stop, flags
@@ -346,6 +354,14 @@ class OracleEnv:
             # reward.py:46-79 with factors [peaks (w), oracle (0)]
             reward = self.alignment_weighting * peaks_alignment_reward(
                 self.peaks, self.streamlines[ci, :self.length]).astype(np.float64)
+            if self.oracle_ckpt is not None and self.oracle_bonus > 0:
+                # oracle_reward.py:70-93: sparse bonus for rows done this step that the oracle likes
+                dn = self.dones[ci]
+                if self.length > self.min_nb_steps and dn.sum() > 0:
+                    pred = oracle_predict(self.oracle_ckpt, list(self.streamlines[ci, :self.length][dn]))
+                    bonus = np.zeros(len(ci))
+                    bonus[np.arange(len(ci))[dn][pred > 0.5]] = 1.0
+                    reward = reward + self.oracle_bonus * bonus
         self.state[ci] = self._format_state(self.streamlines[ci, :self.length])
         return self.state[ci], reward, self.dones[ci], {'continue_idx': ci}
 

@@ -181,7 +181,8 @@ class Tractogram:
         self.data_per_streamline = data_per_streamline or {}
 
     def apply_affine(self, affine, lazy=False):
-        self.streamlines = [s @ affine[:3, :3].T + affine[:3, 3] for s in self.streamlines]
+        # nibabel's ArraySequence keeps float32 storage
+        self.streamlines = [(s @ affine[:3, :3].T + affine[:3, 3]).astype(np.float32) for s in self.streamlines]
         return self
 
     def __len__(self):
@@ -202,10 +203,10 @@ class StatefulTractogram:
         self.space = space
 
     def to_vox(self):
-        self._sl = [s @ self._inv[:3, :3].T + self._inv[:3, 3] for s in self._sl]
+        self._sl = [(s @ self._inv[:3, :3].T + self._inv[:3, 3]).astype(np.float32) for s in self._sl]
 
     def to_corner(self):
-        self._sl = [s + 0.5 for s in self._sl]
+        self._sl = [(s + np.float32(0.5)).astype(np.float32) for s in self._sl]
 
     @property
     def streamlines(self):

@@ -49,7 +49,8 @@ assert int(np.__version__.split('.')[0]) >= 2
 
 def make_env(cls, shape, vox, npv, step_mm, theta=30., n_dirs=100, max_length=200.,
              min_length=20., compute_reward=False, threshold=0.1, np_seed=1337,
-             vol_seed=1234, weak_step=False, noise=0.0, seed_frac=0.26):
+             vol_seed=1234, weak_step=False, noise=0.0, seed_frac=0.26, oracle_checkpoint=None,
+             oracle_stopping=False, oracle_bonus=0.0):
     sub = synthetic.make_subject(shape, seed=vol_seed)
     affine = np.diag([vox, vox, vox, 1.0])
     vol = MRIDataVolume(sub['sh'].numpy(), affine)
@@ -61,8 +62,9 @@ def make_env(cls, shape, vox, npv, step_mm, theta=30., n_dirs=100, max_length=20
     dto = {
         'n_dirs': n_dirs, 'theta': theta, 'npv': npv, 'binary_stopping_threshold': threshold,
         'step_size': step_mm, 'min_length': min_length, 'max_length': max_length,
-        'oracle_checkpoint': None, 'oracle_stopping_criterion': False, 'scoring_data': None,
-        'compute_reward': compute_reward, 'alignment_weighting': 1.0, 'oracle_bonus': 0.0,
+        'oracle_checkpoint': oracle_checkpoint, 'oracle_stopping_criterion': oracle_stopping,
+        'scoring_data': None,
+        'compute_reward': compute_reward, 'alignment_weighting': 1.0, 'oracle_bonus': oracle_bonus,
         'rng': np.random.RandomState(np_seed), 'device': torch.device('cpu'),
         'target_sh_order': 8, 'noise': noise, 'fa_map': None,
     }
@@ -156,6 +158,55 @@ def case_env(name, cls, weak_step, compute_reward, shape=(20, 22, 18), vox=1.0, 
     print(name, 'n=%d steps=%d' % (n, rec['n_steps']),
           'flags: mask=%d length=%d curv=%d' % ((fl & 1 > 0).sum(), (fl & 2 > 0).sum(), (fl & 4 > 0).sum()),
           'nan_points=%d' % np.isnan(rec['new_points']).any(axis=1).sum())
+
+
+def case_env_oracle(name='env_oracle'):
+    """TrackingEnvironment with the oracle stopping criterion and the sparse oracle bonus
+    (stopping_criteria.py:85-154, oracle_reward.py:10-93) driven by a 1-layer TransformerOracle
+    whose head is rescaled so that scores straddle 0.5."""
+    import tempfile
+    from TrackToLearn.oracles.oracle import OracleSingleton
+    from TrackToLearn.oracles.transformer_oracle import TransformerOracle
+    ck = synthetic.oracle_checkpoint(n_head=4, n_layers=1, input_size=384, seed=31)
+    model = TransformerOracle.load_from_checkpoint(
+        {'hyper_parameters': ck['hyper_parameters'],
+         'state_dict': {k: v.clone() for k, v in ck['state_dict'].items()}})
+    rng = np.random.RandomState(8)
+    probe = synthetic.random_streamlines(64, rng, min_pts=4, max_pts=20)
+    feats = np.diff(np.stack(_reference_stubs.set_number_of_points(probe, 128)), axis=1).astype(np.float32)
+    with torch.no_grad():
+        hidden = model.bert(model.pos_encoding(model.embedding(torch.cat(
+            (model.cls_token.repeat(64, 1, 1), torch.from_numpy(feats)), dim=1)) * np.sqrt(32.0)))[:, 0]
+        logit = (hidden @ ck['state_dict']['head.weight'].t())[:, 0]
+    scale = 6.0 / float(logit.std())
+    head_w = ck['state_dict']['head.weight'] * scale
+    head_b = torch.tensor([-float((logit * scale).median())])
+    ck['state_dict']['head.weight'] = head_w
+    ck['state_dict']['head.bias'] = head_b
+    path = os.path.join(tempfile.mkdtemp(), 'oracle.ckpt')
+    torch.save(ck, path)
+    OracleSingleton._self = None
+    shape, vox, step_mm = (20, 22, 18), 1.0, 0.75
+    env, sub = make_env(TrackingEnvironment, shape, vox, npv=1, step_mm=step_mm, max_length=13.6,
+                        min_length=1.6, compute_reward=True, weak_step=True, oracle_checkpoint=path,
+                        oracle_stopping=True, oracle_bonus=10.0)
+    np.random.RandomState(7).shuffle(env.seeds)
+    n = min(48, len(env.seeds))
+    actions = make_actions(n, env.max_nb_steps + 2, np.random.RandomState(99))
+    rec = run_episode(env, n, actions, keep_states=(0, 12))
+    rec['meta_shape'] = np.asarray(shape, dtype=np.int32)
+    rec['meta'] = np.asarray([vox, step_mm, 30.0, 13.6, 0.1, float(env.max_nb_steps), float(env.step_size)],
+                             dtype=np.float64)
+    rec['head_w'] = head_w.numpy()
+    rec['head_b'] = head_b.numpy()
+    rec['min_nb_steps'] = np.int32(env.min_nb_steps)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **rec)
+    fl = rec['final_flags']
+    print(name, 'n=%d steps=%d' % (n, rec['n_steps']),
+          'flags: mask=%d length=%d curv=%d oracle=%d' % ((fl & 1 > 0).sum(), (fl & 2 > 0).sum(),
+                                                          (fl & 4 > 0).sum(), (fl & 64 > 0).sum()),
+          'bonus rows=%d' % int((rec['rewards'] > 5).sum()))
+    OracleSingleton._self = None
 
 
 def case_edges(name='edges'):
@@ -262,5 +313,6 @@ if __name__ == '__main__':
         case_env('env_plain_reward', TrackingEnvironment, weak_step=True, compute_reward=True,
                  shape=(18, 20, 22), vox=1.25, step_mm=0.9375, theta=40.0, max_length=17.0)
         case_edges()
+        case_env_oracle()
     case_actor()
     case_oracle_net()

@@ -30,3 +30,14 @@ def split_by_counts(arr, counts):
         out.append(arr[o:o + c])
         o += c
     return out
+
+
+def oracle_ckpt_for(g):
+    """The 1-layer TransformerOracle checkpoint of the env_oracle fixture (head rescaled so that
+    scores straddle 0.5; the rescaled head travels in the fixture)."""
+    import torch
+    from tracktolearn_b200 import synthetic
+    ck = synthetic.oracle_checkpoint(n_head=4, n_layers=1, input_size=384, seed=31)
+    ck['state_dict']['head.weight'] = torch.from_numpy(np.asarray(g['head_w']))
+    ck['state_dict']['head.bias'] = torch.from_numpy(np.asarray(g['head_b']))
+    return ck

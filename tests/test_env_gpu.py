@@ -188,3 +188,38 @@ def test_format_state_generic_channel_count():
     sr, _, dr, _ = renv.step(act)
     np.testing.assert_array_equal(dg, dr)
     np.testing.assert_allclose(sg.cpu().numpy(), sr, rtol=0, atol=STATE_TOL)
+
+
+def test_episode_with_oracle_criterion_and_bonus_matches_reference_fixture():
+    """S9 / S13: TractOracle-Net consulted inside step() (stopping criterion from 5*min_nb_steps
+    points on, sparse bonus for finished streamlines the oracle likes)."""
+    from tests.gpu_helpers import make_gpu_env
+    from tests.helpers import oracle_ckpt_for
+    from tracktolearn_b200.oracles.oracle import OracleSingleton
+    g = load_golden('env_oracle')
+    OracleSingleton.clear()
+    env, _ = make_gpu_env(g, False, True, seeds=g['seeds'], oracle_checkpoint=oracle_ckpt_for(g),
+                          oracle_stopping=True, oracle_bonus=10.0, min_length=1.6)
+    assert env.min_nb_steps == int(g['min_nb_steps'])
+    n = len(g['seeds'])
+    env.reset(0, n)
+    counts = g['alive_counts']
+    ci_g = split_by_counts(g['continue_idx'], counts)
+    dones_g = split_by_counts(g['dones'], counts)
+    flags_g = split_by_counts(g['step_flags'], counts)
+    rew_g = split_by_counts(g['rewards'], counts)
+    for t in range(int(g['n_steps'])):
+        ci = env.continue_idx.copy()
+        np.testing.assert_array_equal(ci, ci_g[t])
+        st, r, done, _ = env.step(g['actions'][t][ci])
+        np.testing.assert_array_equal(done.astype(np.uint8), dones_g[t])
+        np.testing.assert_array_equal(env.flags[ci], flags_g[t])
+        np.testing.assert_allclose(r, rew_g[t], rtol=0, atol=1e-5)
+        if 'state_%d' % t in g:
+            np.testing.assert_allclose(st.cpu().numpy(), g['state_%d' % t], rtol=0, atol=STATE_TOL, equal_nan=True)
+        env.harvest()
+    np.testing.assert_array_equal(env.flags, g['final_flags'])
+    np.testing.assert_array_equal(env.lengths, g['final_lengths'])
+    tr = env.get_streamlines()
+    np.testing.assert_array_equal(tr.lengths, g['sl_lengths'])
+    OracleSingleton.clear()

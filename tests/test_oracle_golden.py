@@ -120,3 +120,31 @@ def test_seeds_restatement_matches_loop():
     where = np.argwhere(mask)
     slow = np.asarray([s + np.random.random(3) - .5 for _ in range(3) for s in where])
     np.testing.assert_array_equal(fast, slow)
+
+
+def test_env_with_oracle_criterion_and_bonus_matches_reference():
+    """OracleStoppingCriterion + OracleReward (sparse bonus 10) inside step()."""
+    from tests.helpers import oracle_ckpt_for
+    g = load_golden('env_oracle')
+    sub = subject_for(g)
+    m = meta(g)
+    ck = oracle_ckpt_for(g)
+    env = O.OracleEnv(sub['sh'], sub['mask'], g['seeds'], m['vox'], m['step_mm'], theta=m['theta'],
+                      max_length_mm=m['max_length'], min_length_mm=1.6, peaks=sub['peaks'],
+                      compute_reward=True, noisy=False, oracle_ckpt=ck, oracle_stopping=True, oracle_bonus=10.0)
+    assert env.min_nb_steps == int(g['min_nb_steps'])
+    n = len(g['seeds'])
+    env.reset(0, n)
+    counts = g['alive_counts']
+    dones_g = split_by_counts(g['dones'], counts)
+    flags_g = split_by_counts(g['step_flags'], counts)
+    rew_g = split_by_counts(g['rewards'], counts)
+    for t in range(int(g['n_steps'])):
+        ci = env.continue_idx.copy()
+        st, r, done, _ = env.step(g['actions'][t][ci])
+        np.testing.assert_array_equal(done.astype(np.uint8), dones_g[t])
+        np.testing.assert_array_equal(env.flags[ci], flags_g[t])
+        np.testing.assert_allclose(r, rew_g[t], rtol=0, atol=1e-5)
+        env.harvest()
+    np.testing.assert_array_equal(env.flags, g['final_flags'])
+    assert (np.asarray(g['final_flags']) & O.ORACLE).any()

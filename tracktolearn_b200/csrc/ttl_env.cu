@@ -297,12 +297,71 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
   b.dones[i] = 0;
 }
 
+// Ordered-compaction bookkeeping shared by propagate_stop_kernel and oracle_apply_kernel: every
+// CTA (kGroup ranks, kK1Threads threads) publishes how many of its ranks stopped; the last CTA to
+// arrive scans the per-group survivor counts and updates the control block (next alive count,
+// slot refill, counters).  `stopped` must be non-zero in exactly one thread per stopped rank.
+__device__ void compaction_bookkeeping(const ttl_batch& b, const ttl_params& prm, int cur, int n_alive,
+                                       int stopped) {
+  __shared__ int s_is_last;
+  __shared__ int s_part[kK1Threads];
+  const int grp_stops = __syncthreads_count(stopped);
+  if (threadIdx.x == 0) {
+    b.grp_stops[blockIdx.x] = grp_stops;
+    __threadfence();
+    const int ticket = atomicAdd(b.ctrl + 7, 1);
+    s_is_last = ticket == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const int ngrp = gridDim.x;
+  const int per = (ngrp + kK1Threads - 1) / kK1Threads;
+  const int g0 = min(ngrp, (int)threadIdx.x * per), g1 = min(ngrp, g0 + per);
+  int keep = 0;
+  for (int g = g0; g < g1; ++g) {
+    const int rows = max(0, min(kGroup, n_alive - g * kGroup));
+    keep += rows - __ldcg(b.grp_stops + g);
+  }
+  s_part[threadIdx.x] = keep;
+  __syncthreads();
+  for (int off = 1; off < kK1Threads; off <<= 1) {
+    int a = 0;
+    if ((int)threadIdx.x >= off) a = s_part[threadIdx.x - off];
+    __syncthreads();
+    s_part[threadIdx.x] += a;
+    __syncthreads();
+  }
+  int pos = s_part[threadIdx.x] - keep;
+  for (int g = g0; g < g1; ++g) {
+    b.grp_prefix[g] = pos;
+    const int rows = max(0, min(kGroup, n_alive - g * kGroup));
+    pos += rows - __ldcg(b.grp_stops + g);
+  }
+  if (threadIdx.x == kK1Threads - 1) {
+    const int total_keep = s_part[kK1Threads - 1];
+    const int cursor = b.ctrl[6];
+    int n_new = 0;
+    if (prm.refill) n_new = max(0, min(b.n_slots - total_keep, b.n - cursor));
+    b.ctrl[cur ^ 1] = total_keep + n_new;   // alive count of the next list
+    b.ctrl[2] = b.ctrl[2] + 1;
+    b.ctrl[3] = n_alive;
+    b.ctrl[6] = cursor + n_new;
+    b.ctrl[7] = 0;
+    b.ctrl[8] = total_keep;
+    b.ctrl[9] = n_new;
+    b.ctrl[10] = cursor;
+    long long* total = reinterpret_cast<long long*>(b.ctrl + 4);
+    *total += n_alive;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: propagate + stopping criteria + reward, one thread per alive streamline
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kK1Threads) propagate_stop_kernel(
     ttl_volume v, ttl_params prm, ttl_batch b, int cur, const float* __restrict__ actions,
-    int lda, const double* __restrict__ noise) {
+    int lda, const double* __restrict__ noise, int defer) {
   // 4 lanes per streamline: they redo the cheap scalar work together and split the spline taps
   const int lane = threadIdx.x & 31, sub = threadIdx.x & (kLanesPerRow - 1);
   const unsigned quad_mask = 0xFu << (lane & ~(kLanesPerRow - 1));
@@ -384,62 +443,44 @@ __global__ void __launch_bounds__(kK1Threads) propagate_stop_kernel(
       b.dones[i] = 1;
       b.lengths[i] = Ln;  // the reference records it in harvest(); nothing reads it in between
     }
-    if (prm.compute_reward && v.peaks) b.reward[r] = rew;
+    if (prm.compute_reward) b.reward[r] = rew;
   }
   }  // r < n_alive
 
-  // ---- ordered-compaction bookkeeping: stops per group of kGroup ranks; the last CTA scans ----
-  __shared__ int s_is_last;
-  __shared__ int s_part[kK1Threads];
-  const int grp_stops = __syncthreads_count(stopped);
-  if (threadIdx.x == 0) {
-    b.grp_stops[blockIdx.x] = grp_stops;
-    __threadfence();
-    const int ticket = atomicAdd(b.ctrl + 7, 1);
-    s_is_last = ticket == (int)gridDim.x - 1;
+  if (!defer) compaction_bookkeeping(b, prm, cur, n_alive, stopped);
+}
+
+// OracleStoppingCriterion (stopping_criteria.py:113-154) and OracleReward (oracle_reward.py:45-93)
+// on top of what propagate_stop_kernel decided: scores [n_alive] are TractOracle-Net's predictions
+// for the alive streamlines (including the point just added).  Runs with the K1 geometry (4 threads
+// per rank, only thread 0 of each quad works) so it can share the compaction bookkeeping.
+__global__ void __launch_bounds__(kK1Threads) oracle_apply_kernel(ttl_params prm, ttl_batch b, int cur,
+                                                                 const float* __restrict__ scores,
+                                                                 int use_stop, int min_pts_stop,
+                                                                 int min_pts_reward, float bonus) {
+  const int sub = threadIdx.x & (kLanesPerRow - 1);
+  const int r = blockIdx.x * kGroup + (threadIdx.x / kLanesPerRow);
+  const int n_alive = b.ctrl[cur];
+  int stopped = 0;
+  if (r < n_alive && sub == 0) {
+    const int i = b.alive[cur][r];
+    const int L = b.npts[i];
+    int f = b.step_flags[r];
+    const float sc = scores[r];
+    if (use_stop && L > min_pts_stop && sc < 0.5f) f |= TTL_STOPPING_ORACLE;
+    if (f != b.step_flags[r]) {
+      b.step_flags[r] = f;
+      b.stop[r] = 1;
+      b.flags[i] = f;
+      b.dones[i] = 1;
+      b.lengths[i] = L;
+    }
+    stopped = f != 0;
+    // sparse bonus for streamlines that are done after this step and that the oracle likes
+    if (prm.compute_reward && bonus > 0.f && stopped && L > min_pts_reward && sc > 0.5f)
+      b.reward[r] = (float)((double)b.reward[r] + (double)bonus);
   }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  const int ngrp = gridDim.x;
-  const int per = (ngrp + kK1Threads - 1) / kK1Threads;
-  const int g0 = min(ngrp, (int)threadIdx.x * per), g1 = min(ngrp, g0 + per);
-  int keep = 0;
-  for (int g = g0; g < g1; ++g) {
-    const int rows = max(0, min(kGroup, n_alive - g * kGroup));
-    keep += rows - __ldcg(b.grp_stops + g);
-  }
-  s_part[threadIdx.x] = keep;
-  __syncthreads();
-  for (int off = 1; off < kK1Threads; off <<= 1) {
-    int a = 0;
-    if ((int)threadIdx.x >= off) a = s_part[threadIdx.x - off];
-    __syncthreads();
-    s_part[threadIdx.x] += a;
-    __syncthreads();
-  }
-  int pos = s_part[threadIdx.x] - keep;
-  for (int g = g0; g < g1; ++g) {
-    b.grp_prefix[g] = pos;
-    const int rows = max(0, min(kGroup, n_alive - g * kGroup));
-    pos += rows - __ldcg(b.grp_stops + g);
-  }
-  if (threadIdx.x == kK1Threads - 1) {
-    const int total_keep = s_part[kK1Threads - 1];
-    const int cursor = b.ctrl[6];
-    int n_new = 0;
-    if (prm.refill) n_new = max(0, min(b.n_slots - total_keep, b.n - cursor));
-    b.ctrl[cur ^ 1] = total_keep + n_new;   // alive count of the next list
-    b.ctrl[2] = b.ctrl[2] + 1;
-    b.ctrl[3] = n_alive;
-    b.ctrl[6] = cursor + n_new;
-    b.ctrl[7] = 0;
-    b.ctrl[8] = total_keep;
-    b.ctrl[9] = n_new;
-    b.ctrl[10] = cursor;
-    long long* total = reinterpret_cast<long long*>(b.ctrl + 4);
-    *total += n_alive;
-  }
+  compaction_bookkeeping(b, prm, cur, n_alive, stopped);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -972,7 +1013,7 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   int rc = check_common(vol, prm);
   if (rc) return rc;
   if (!b || !actions || lda < 3 || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
-  if (prm->compute_reward && !vol->peaks) return TTL_ERR_BAD_ARG;
+  if (prm->compute_reward && !vol->peaks && prm->alignment_weighting > 0) return TTL_ERR_BAD_ARG;
   if (prm->refill && prm->state_stopped) return TTL_ERR_BAD_ARG;
   rc = check_layout(vol, prm, b);
   if (rc) return rc;
@@ -980,7 +1021,50 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   if (n_upper > b->n_slots) n_upper = b->n_slots;
   if (ttl_div_up(n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->grp_prefix) return TTL_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<<<ttl_div_up(n_upper, kGroup), kK1Threads, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise));
+  TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<<<ttl_div_up(n_upper, kGroup), kK1Threads, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise, 0));
+  rc = state_kernels_ready();
+  if (rc) return rc;
+  const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;
+  TTL_LAUNCH("build_state_kernel", s,
+             build_state_kernel<<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
+                 *vol, *prm, *b, cur, warp_smem));
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_env_step_begin(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                       const float* actions, int32_t lda, const double* noise, int32_t n_upper,
+                       void* stream) {
+  int rc = check_common(vol, prm);
+  if (rc) return rc;
+  if (!b || !actions || lda < 3 || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
+  if (prm->compute_reward && !vol->peaks && prm->alignment_weighting > 0) return TTL_ERR_BAD_ARG;
+  if (prm->refill && prm->state_stopped) return TTL_ERR_BAD_ARG;
+  rc = check_layout(vol, prm, b);
+  if (rc) return rc;
+  if (n_upper <= 0) return 0;
+  if (n_upper > b->n_slots) n_upper = b->n_slots;
+  if (ttl_div_up(n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->grp_prefix) return TTL_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  TTL_LAUNCH("propagate_stop_kernel", s,
+             propagate_stop_kernel<<<ttl_div_up(n_upper, kGroup), kK1Threads, 0, s>>>(*vol, *prm, *b, cur, actions,
+                                                                                    lda, noise, 1));
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_env_step_finish(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                        const float* scores, int32_t use_stop, int32_t min_pts_stop, int32_t min_pts_reward,
+                        float bonus, int32_t n_upper, void* stream) {
+  int rc = check_common(vol, prm);
+  if (rc) return rc;
+  if (!b || !scores || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
+  if (n_upper <= 0) return 0;
+  if (n_upper > b->n_slots) n_upper = b->n_slots;
+  cudaStream_t s = (cudaStream_t)stream;
+  TTL_LAUNCH("oracle_apply_kernel", s,
+             oracle_apply_kernel<<<ttl_div_up(n_upper, kGroup), kK1Threads, 0, s>>>(
+                 *prm, *b, cur, scores, use_stop, min_pts_stop, min_pts_reward, bonus));
   rc = state_kernels_ready();
   if (rc) return rc;
   const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;

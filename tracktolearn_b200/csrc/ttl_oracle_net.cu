@@ -23,15 +23,8 @@ namespace {
 // ------------------------------------------------------------------------------------------
 constexpr int kOraclePts = 128;
 
-__global__ void __launch_bounds__(128) oracle_features_kernel(const float* __restrict__ points,
-                                                              const long long* __restrict__ offsets, int n,
-                                                              float* __restrict__ dirs) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  const long long o0 = offsets[s];
-  const int N = (int)(offsets[s + 1] - o0);
-  const float* P = points + o0 * 3;
-  float* D = dirs + (size_t)s * (kOraclePts - 1) * 3;
+// One streamline: P = its N points, D = its 127 output directions.
+__device__ void resample_and_diff(const float* __restrict__ P, int N, float* __restrict__ D) {
   if (N <= 0) {
     for (int j = 0; j < (kOraclePts - 1) * 3; ++j) D[j] = 0.f;
     return;
@@ -98,6 +91,24 @@ __global__ void __launch_bounds__(128) oracle_features_kernel(const float* __res
   D[3 * (kOraclePts - 2) + 0] = __fsub_rn(P[3 * (N - 1) + 0], res126[0]);
   D[3 * (kOraclePts - 2) + 1] = __fsub_rn(P[3 * (N - 1) + 1], res126[1]);
   D[3 * (kOraclePts - 2) + 2] = __fsub_rn(P[3 * (N - 1) + 2], res126[2]);
+}
+
+__global__ void __launch_bounds__(128) oracle_features_kernel(const float* __restrict__ points,
+                                                              const long long* __restrict__ offsets, int n,
+                                                              float* __restrict__ dirs) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const long long o0 = offsets[s];
+  resample_and_diff(points + o0 * 3, (int)(offsets[s + 1] - o0), dirs + (size_t)s * (kOraclePts - 1) * 3);
+}
+
+// The alive streamlines of a tracking batch, straight from the streamline buffer (what
+// OracleStoppingCriterion / OracleReward score every step, stopping_criteria.py:113-154).
+__global__ void __launch_bounds__(128) oracle_features_rows_kernel(ttl_batch b, int cur, float* __restrict__ dirs) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= b.ctrl[cur]) return;
+  const int row = b.alive[cur][r];
+  resample_and_diff(b.points + (size_t)row * b.max_pts * 3, b.npts[row], dirs + (size_t)r * (kOraclePts - 1) * 3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -311,6 +322,16 @@ int ttl_oracle_features(const float* points, const int64_t* offsets, int32_t n, 
   cudaStream_t s = (cudaStream_t)stream;
   TTL_LAUNCH("oracle_features_kernel", s,
              oracle_features_kernel<<<ttl_div_up(n, 128), 128, 0, s>>>(points, (const long long*)offsets, n, dirs));
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_oracle_features_rows(const ttl_batch* b, int32_t cur, int32_t n_upper, float* dirs, void* stream) {
+  if (!b || !dirs || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
+  if (n_upper <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  TTL_LAUNCH("oracle_features_rows_kernel", s,
+             oracle_features_rows_kernel<<<ttl_div_up(n_upper, 128), 128, 0, s>>>(*b, cur, dirs));
   TTL_CHECK_LAST();
   return 0;
 }

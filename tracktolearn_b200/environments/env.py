@@ -58,8 +58,12 @@ class BaseEnv(object):
         # (tracking_env.py:214-215).  Trackers that never read them switch this off.
         self.state_of_stopped = env_dto.get('state_of_stopped', True)
         self._float64_directions = False   # TrackingEnvironment; Noisy env flips it
-        if self.oracle_checkpoint and (self.oracle_stopping_criterion or self.oracle_bonus):
-            raise NotImplementedError('oracle stopping criterion / bonus inside step(): see DESIGN.md')
+        # TractOracle-Net inside the step (stopping_criteria.py:85-154, oracle_reward.py:10-93)
+        self._oracle = None
+        if self.oracle_checkpoint and (self.oracle_stopping_criterion
+                                       or (self.compute_reward and self.oracle_bonus > 0)):
+            from tracktolearn_b200.oracles.oracle import OracleSingleton
+            self._oracle = OracleSingleton(self.oracle_checkpoint, self.device)
 
         self._uploaded = False
         self.load_subject()

@@ -161,10 +161,34 @@ class TrackingEnvironment(BaseEnv):
         if actions.dtype != torch.float32 or actions.device != self.device or actions.stride(-1) != 1:
             actions = actions.to(self.device, dtype=torch.float32).contiguous()
         lda = actions.stride(0) if actions.dim() == 2 and actions.shape[0] > 1 else actions.shape[-1]
-        _lib.check(self._lib.ttl_env_step(
-            ctypes.byref(self._volume), ctypes.byref(self._params), ctypes.byref(self._b), self._cur,
-            _lib.ptr(actions), int(lda), _lib.ptr(noise), int(self._n_alive_host),
-            _lib.stream_ptr(self.device)), 'ttl_env_step')
+        sp = _lib.stream_ptr(self.device)
+        n_up = int(self._n_alive_host)
+        if self._oracle is None:
+            _lib.check(self._lib.ttl_env_step(
+                ctypes.byref(self._volume), ctypes.byref(self._params), ctypes.byref(self._b), self._cur,
+                _lib.ptr(actions), int(lda), _lib.ptr(noise), n_up, sp), 'ttl_env_step')
+        else:
+            # propagate + geometric criteria, then score every alive streamline, then ORACLE flag /
+            # bonus / compaction / state rows
+            _lib.check(self._lib.ttl_env_step_begin(
+                ctypes.byref(self._volume), ctypes.byref(self._params), ctypes.byref(self._b), self._cur,
+                _lib.ptr(actions), int(lda), _lib.ptr(noise), n_up, sp), 'ttl_env_step_begin')
+            if n_up > 0:
+                slots = self._b.n_slots
+                if getattr(self, '_oracle_dirs', None) is None or self._oracle_dirs.shape[0] < slots:
+                    self._oracle_dirs = torch.empty((slots, 127, 3), dtype=torch.float32, device=self.device)
+                    self._oracle_scores = torch.zeros((slots,), dtype=torch.float32, device=self.device)
+                _lib.check(self._lib.ttl_oracle_features_rows(ctypes.byref(self._b), self._cur, n_up,
+                                                              _lib.ptr(self._oracle_dirs), sp),
+                           'ttl_oracle_features_rows')
+                _lib.check(self._lib.ttl_oracle_forward(ctypes.byref(self._oracle.weights.struct),
+                                                        _lib.ptr(self._oracle_dirs), n_up,
+                                                        _lib.ptr(self._oracle_scores), sp), 'ttl_oracle_forward')
+                bonus = float(self.oracle_bonus) if self.compute_reward else 0.0
+                _lib.check(self._lib.ttl_env_step_finish(
+                    ctypes.byref(self._volume), ctypes.byref(self._params), ctypes.byref(self._b), self._cur,
+                    _lib.ptr(self._oracle_scores), int(bool(self.oracle_stopping_criterion)),
+                    int(self.min_nb_steps * 5), int(self.min_nb_steps), bonus, n_up, sp), 'ttl_env_step_finish')
         self._keep = (actions, noise)
         self.length += 1
         self._pending_harvest = True
