@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: TractOracle-Net batched scoring of finished streamlines.
+
+    python benchmarks/oracle_bench.py [--n 131072] [--cpu-n 512]
+
+Streamlines: ragged smooth random walks, lengths U{20..267} points; model:
+n_head=4, n_layers=4, d=32, ff=2048, 128 tokens (assumed hyper-parameters, real blob missing).
+Reports device-resident and host-to-host streamlines/s, achieved TFLOP/s against the
+146.8 MFLOP/streamline figure, and the numpy oracle on the host cores for a small sample."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+FLOP_PER_STREAMLINE = 4 * 36700160 + 2 * 128 * 3 * 32 + 2 * 32
+
+
+def make_streamlines(n, seed=0):
+    rng = np.random.RandomState(seed)
+    lens = rng.randint(20, 268, size=n)
+    offsets = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    total = int(offsets[-1])
+    steps = rng.normal(size=(total, 3)).astype(np.float32)
+    # smooth the directions a little and normalise to 0.75 voxel steps
+    steps = steps + 2.0 * np.roll(steps, 1, axis=0) + np.roll(steps, 2, axis=0)
+    steps *= 0.75 / np.linalg.norm(steps, axis=1, keepdims=True)
+    pts = np.cumsum(steps, axis=0)
+    starts = np.repeat(pts[offsets[:-1]], lens, axis=0)
+    return (pts - starts + 40.0).astype(np.float32), offsets
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=131072)
+    ap.add_argument('--cpu-n', type=int, default=256)
+    a = ap.parse_args()
+    import torch
+    from tracktolearn_b200 import _lib, synthetic
+    from tracktolearn_b200.oracles.oracle import OracleSingleton
+    from tracktolearn_b200.tracking.tractogram import Tractogram
+    dev = torch.device('cuda:0')
+    ck = synthetic.oracle_checkpoint(n_head=4, n_layers=4, input_size=384, seed=2222)
+    model = OracleSingleton(ck, dev)
+    data, offsets = make_streamlines(a.n)
+    pts = torch.from_numpy(data).to(dev)
+    off = torch.from_numpy(offsets).to(dev)
+    model.predict_device(pts, off)          # warm-up
+    torch.cuda.synchronize()
+    lib = _lib.load()
+    lib.ttl_prof_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    scores = model.predict_device(pts, off)
+    e1.record()
+    torch.cuda.synchronize()
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    prof = _lib.prof_report()
+    lib.ttl_prof_enable(0)
+    t0 = time.perf_counter()
+    host_scores = model.predict(Tractogram(data=data, offsets=offsets))
+    torch.cuda.synchronize()
+    host_s = time.perf_counter() - t0
+    # CPU oracle on a sample
+    from oracle import ttl_oracle as O
+    sl = [data[offsets[i]:offsets[i + 1]] for i in range(a.cpu_n)]
+    t0 = time.perf_counter()
+    ref = O.oracle_predict(ck, sl)
+    cpu_s = time.perf_counter() - t0
+    err = float(np.abs(ref - host_scores[:a.cpu_n]).max())
+    fwd_ms = prof.get('oracle_forward_kernel', (0, 0.0))[1]
+    out = {
+        'metric': 'oracle streamlines/sec', 'n': a.n,
+        'device_resident_streamlines_per_s': a.n / dev_s,
+        'host_to_host_streamlines_per_s': a.n / host_s,
+        'forward_kernel_tflops': a.n * FLOP_PER_STREAMLINE / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None,
+        'kernels_ms': {k: v[1] for k, v in prof.items()},
+        'cpu_port_streamlines_per_s': a.cpu_n / cpu_s, 'cpu_cores': os.cpu_count(), 'cpu_sample': a.cpu_n,
+        'max_abs_err_vs_cpu_oracle': err, 'dtype': 'f32 (CUDA cores)',
+        'flop_per_streamline': FLOP_PER_STREAMLINE,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()
