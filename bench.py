@@ -47,6 +47,7 @@ STEP_BYTES_PER_ROW = 8900            # gather 4680 + state 2460 + d
 STATE_KERNEL_BYTES_PER_ROW = 4680 + 2460 + 1200 + 12
 WORKLOAD = 'whole-brain synthetic 145x174x145 1.25mm order-8 fODF, npv=20, n_actor=50000'
 CPU_SAMPLE_ROWS = 4096
+BURN_IN = 128
 
 
 def peaks():
@@ -246,12 +247,13 @@ def main_gpu(args):
     actor = alg.agent.actor
     stream = torch.cuda.current_stream(dev)
 
-    def one_step(action_buf):
-        actor.forward_device(env.current_state(), 0.0, n_rows_dev=env.alive_count_tensor(),
-                             n_rows=env._n_alive_host, want_logp=False, out_action=action_buf,
-                             state_bf16=env.current_state_bf16(), layout=env.bf16_layout)
-        env.step_device(action_buf)
-        env.harvest_device()
+    from tracktolearn_b200.algorithms.rl import StepRunner
+    runner_box = {}
+
+    def one_step(action_buf=None):
+        # the same enqueue-only iteration Tracker / validation_episode run (CUDA-graph replay
+        # after two warm iterations)
+        runner_box['r'].step()
 
     def barrier():
         if world > 1:
@@ -260,12 +262,20 @@ def main_gpu(args):
 
     # ---- device-resident throughput: inputs already in HBM ----------------------------
     env.reset_streaming(0, n_seeds, N_ACTOR, fp32_state=not args.bf16_state_only)
-    action_buf = torch.empty((N_ACTOR, 3), dtype=torch.float32, device=dev)
+    action_buf = None
+    runner_box['r'] = StepRunner(env, actor, 0.0, use_graph=args.graph)
+    # burn-in (untimed, part of preparing the workload): with slot refill the alive set needs about
+    # two mean lifetimes to reach its steady-state mix of streamline ages and positions; right after
+    # reset every streamline still sits on the seed shell and the gather enjoys unrepresentative L2
+    # locality
+    for _ in range(BURN_IN):
+        one_step(action_buf)
     for _ in range(args.warmup):
         one_step(action_buf)
     env.n_alive()
     steps_before = env.streamline_steps()
     launches_before = lib.ttl_launch_count()
+    replays_before = runner_box['r'].replays
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -277,7 +287,9 @@ def main_gpu(args):
     barrier()
     clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
-    gpu_launches = int(lib.ttl_launch_count() - launches_before)
+    # kernels launched one by one + kernels replayed from the captured step graphs
+    gpu_launches = int(lib.ttl_launch_count() - launches_before) + \
+        (runner_box['r'].replays - replays_before) * runner_box['r'].kernels_per_step
     env.n_alive()
     units = env.streamline_steps() - steps_before
     alive_end = int(env._batch.ctrl_host[env._cur])
@@ -285,8 +297,9 @@ def main_gpu(args):
     # ---- per-kernel device times (CUDA events on the launching stream) -------------------
     prof_steps = min(20, args.steps)
     lib.ttl_prof_enable(1)
+    plain = StepRunner(env, actor, 0.0, use_graph=False)
     for _ in range(prof_steps):
-        one_step(action_buf)
+        plain.step()
     torch.cuda.synchronize(dev)
     prof = _lib.prof_report()
     lib.ttl_prof_enable(0)
@@ -394,7 +407,7 @@ def main_gpu(args):
                        'n_actor': N_ACTOR, 'seeds_per_gpu': n_seeds, 'step_mm': STEP_MM,
                        'max_nb_steps': int(env.max_nb_steps), 'actor': '615-' + HIDDEN + '-6 (synthetic, tracking-like)',
                        'env': 'NoisyTrackingEnvironment noise=0 (float64 directions)',
-                       'streaming_refill': True, 'alive_at_end': alive_end,
+                       'streaming_refill': True, 'alive_at_end': alive_end, 'burn_in_steps': BURN_IN,
                        'state_rows': ('bf16 actor operand only; the fp32 API tensor is not materialised in the '
                                       'device loop (SURVEY 7 step 7)' if args.bf16_state_only
                                       else 'fp32 API tensor + bf16 actor operand'),
@@ -428,6 +441,7 @@ if __name__ == '__main__':
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--fp32-state', dest='bf16_state_only', action='store_false',
                     help='also materialise the fp32 state rows every step (the reference API tensor)')
+    ap.add_argument('--graph', action='store_true', help='replay the 6 kernels of a step from a CUDA graph')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
     a = ap.parse_args()
     if a.warmup < 3:
