@@ -197,6 +197,9 @@ int64_t ttl_actor_workspace_bytes(const ttl_actor_weights* w, int32_t max_rows);
 int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int32_t max_rows,
                           void* workspace, int64_t workspace_bytes, void* stream);
 void ttl_actor_plan_destroy(ttl_actor_plan* plan);
+/* The fp32 weights the plan was created from changed in place (an optimiser step,
+ * algorithms/sac_auto.py:220-232): repack the bf16 copies.  Three small launches. */
+int ttl_actor_plan_refresh(ttl_actor_plan* plan, void* stream);
 
 /* MaxEntropyActor.forward (offpolicy.py:94-140): state [n][ld_state] fp32 ->
  * action [n][3] = tanh(mu + exp(clamp(log_std,-20,2)) * probabilistic * eps), logp [n]

@@ -209,6 +209,37 @@ def case_env_oracle(name='env_oracle'):
     OracleSingleton._self = None
 
 
+def case_sac_update(name='sac_update'):
+    """Two SACAuto.update steps of the reference (sac_auto.py:139-250) on a fixed batch, small nets."""
+    from TrackToLearn.algorithms.sac_auto import SACAuto
+    torch.manual_seed(123)
+    alg = SACAuto(24, 3, '16-12', lr=3e-4, gamma=0.95, alpha=0.2, n_actors=8, batch_size=16, replay_size=8,
+                  rng=np.random.RandomState(0), device=torch.device('cpu'))
+    rec = {}
+    for k, v in alg.agent.actor.state_dict().items():
+        rec['actor0.' + k] = v.numpy().copy()
+    for k, v in alg.agent.critic.state_dict().items():
+        rec['critic0.' + k] = v.numpy().copy()
+    g = torch.Generator().manual_seed(5)
+    batch = (torch.randn((16, 24), generator=g), torch.rand((16, 3), generator=g) * 2 - 1,
+             torch.randn((16, 24), generator=g), torch.rand((16,), generator=g),
+             (torch.rand((16,), generator=g) > 0.3).float())
+    for i, name_ in enumerate(('state', 'action', 'next_state', 'reward', 'not_done')):
+        rec['batch.' + name_] = batch[i].numpy()
+    torch.manual_seed(77)
+    for _ in range(2):
+        alg.update(batch)
+    for k, v in alg.agent.actor.state_dict().items():
+        rec['actor2.' + k] = v.numpy().copy()
+    for k, v in alg.agent.critic.state_dict().items():
+        rec['critic2.' + k] = v.numpy().copy()
+    for k, v in alg.target.critic.state_dict().items():
+        rec['target_critic2.' + k] = v.numpy().copy()
+    rec['log_alpha2'] = alg.log_alpha.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **rec)
+    print(name, 'log_alpha', rec['log_alpha2'])
+
+
 def case_edges(name='edges'):
     """_format_state / stopping flags / reward on crafted streamlines: outside the volume,
     negative, on the lattice, NaN/inf, zero-length segments."""
@@ -316,3 +347,4 @@ if __name__ == '__main__':
         case_env_oracle()
     case_actor()
     case_oracle_net()
+    case_sac_update()

@@ -109,3 +109,41 @@ def test_bf16_only_state_mode_tracks_the_same_streamlines():
         worst = max(worst, float(np.abs(a.streamlines[i] - b.streamlines[i]).max()))
     assert worst < 5e-2, worst
     assert (a.data_per_streamline['flags'] == b.data_per_streamline['flags'])[same].all()
+
+
+def test_training_episode_rollout_replay_and_update():
+    """A3 / config 4: DDPG._episode-style rollout with the tensor-core actor sampling at
+    probabilistic=1, transitions pushed to the device replay buffer, one SAC update per env step,
+    weights shared between learner and inference actor."""
+    from tests.gpu_helpers import make_gpu_env
+    from tracktolearn_b200.algorithms.sac_auto import SACAuto
+    shape = (24, 26, 22)
+    sub = {k: (v.numpy() if v is not None else None) for k, v in synthetic.make_subject(shape, seed=11).items()}
+    rs = np.random.RandomState(3)
+    seeds = synthetic.seeds_from_mask(synthetic.ellipsoid_mask(shape, frac=0.3).numpy(), 1, rs)
+    g = {'meta_shape': np.asarray(shape), 'meta': np.asarray([1.0, 0.75, 30.0, 30.0, 0.1, 40.0, 0.75])}
+    env, _ = make_gpu_env(g, False, True, sub=sub, seeds=seeds)
+    alg = SACAuto(615, 3, '128-128-128', n_actors=200, device=torch.device('cuda:0'), precision='bf16')
+    alg.agent.actor.load_state_dict(synthetic.actor_state_dict(615, '128-128-128', seed=5, kind='tracking'))
+    learner = alg.enable_training(replay_size=20000, batch_size=256, start_timesteps=150)
+    w_before = learner.actor.layers[0].weight.detach().clone()
+    np.random.seed(0)
+    torch.manual_seed(0)
+    state = env.nreset(200)
+    reward, losses, length, _ = alg._episode(state, env)
+    assert length >= 3 and len(alg.replay_buffer) == alg.t - 1
+    assert len(losses) >= 1 and all(np.isfinite(float(l['critic_loss'])) for l in losses)
+    assert not torch.equal(w_before, learner.actor.layers[0].weight)
+    # transitions are consistent: next_state of a surviving streamline at step t is a state at t+1
+    rb = alg.replay_buffer
+    n0 = 200
+    first_next = rb.next_state[:n0]
+    alive0 = rb.not_done[:n0, 0] > 0
+    second_states = rb.state[n0:n0 + int(alive0.sum())]
+    torch.testing.assert_close(first_next[alive0], second_states, rtol=0, atol=0)
+    assert float(rb.reward[:len(rb)].abs().sum()) > 0
+    # inference actor == learner's torch actor after the updates (bf16 tolerance)
+    st = rb.state[:64]
+    mu_ref = torch.tanh(learner.actor.layers(st)[:, :3])
+    a_inf = alg.agent.select_action(st, 0.0)
+    assert (a_inf - mu_ref).abs().max().item() < 2e-2

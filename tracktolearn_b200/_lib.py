@@ -69,6 +69,7 @@ SIGNATURES = {
     'ttl_actor_workspace_bytes': (c_i64, [P(ActorWeights), c_i32]),
     'ttl_actor_plan_create': (c_i32, [P(c_vp), P(ActorWeights), c_i32, c_vp, c_i64, c_vp]),
     'ttl_actor_plan_destroy': (None, [c_vp]),
+    'ttl_actor_plan_refresh': (c_i32, [c_vp, c_vp]),
     'ttl_actor_forward': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
     'ttl_actor_forward_packed': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
     'ttl_actor_plan_set_layout': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp]),

@@ -30,5 +30,66 @@ class SACAuto(RLAlgorithm):
         """Reference: algorithms/sac.py:123-133."""
         return self.agent.select_action(state, probabilistic=1.0)
 
+    # ------------------------------------------------------------------------------ training
+    def enable_training(self, lr=3e-4, gamma=0.99, replay_size=None, batch_size=None, start_timesteps=None):
+        """Build the learner (torch autograd networks + Adam, sac_train.py), make the tensor-core
+        actor read ITS weights, and allocate the device-resident replay buffer."""
+        from tracktolearn_b200.algorithms.sac_train import SACAutoLearner
+        from tracktolearn_b200.algorithms.shared.replay import OffPolicyReplayBuffer
+        actor = self.agent.actor
+        hidden = '-'.join(str(int(w)) for w in actor.hidden_layers)
+        self.learner = SACAutoLearner(actor.state_dim, actor.action_dim, hidden, lr=lr, gamma=gamma,
+                                      alpha=self.alpha, device=self.device)
+        self.learner.actor.load_state_dict(actor.state_dict())
+        self.learner.target_actor.load_state_dict(actor.state_dict())
+        self.learner.broadcast_parameters()
+        actor.share_parameters(self.learner.actor.state_dict())
+        if replay_size is not None:
+            self.replay_size = replay_size
+        if batch_size is not None:
+            self.batch_size = batch_size
+        if start_timesteps is not None:
+            self.start_timesteps = start_timesteps
+        self.replay_buffer = OffPolicyReplayBuffer(actor.state_dim, actor.action_dim, max_size=int(self.replay_size),
+                                                   device=self.device)
+        return self.learner
+
     def update(self, batch):
-        raise NotImplementedError('SAC updates are outside the hot path of this package')
+        """Reference: sac_auto.py:139-250."""
+        losses = self.learner.update(batch)
+        self.agent.actor.refresh_weights()
+        self.total_it += 1
+        return losses
+
+    def _episode(self, initial_state, env):
+        """Rollout + update loop (reference: algorithms/ddpg.py:141-232): sample an action for every
+        alive streamline, step the env, push the transitions of all of them to the replay buffer,
+        do ONE gradient update per environment step once ``start_timesteps`` transitions have been
+        seen, harvest.  Everything stays on the device; the only host read per step is the alive
+        count."""
+        import ctypes
+        from tracktolearn_b200 import _lib
+        actor = self.agent.actor
+        running_reward = 0.0
+        episode_length = 0
+        losses_log = []
+        A = env._n_alive_host
+        S = env.get_state_size()
+        while A > 0:
+            state = env.current_state()[:A]
+            action, _, _ = actor.forward_device(state, 1.0, n_rows=A, want_logp=False)
+            env.step_device(action)
+            next_state = torch.empty((A, S), dtype=torch.float32, device=env.device)
+            _lib.check(env._lib.ttl_env_gather_step_state(ctypes.byref(env._b), env._cur, A, _lib.ptr(next_state),
+                                                          S, _lib.stream_ptr(env.device)), 'ttl_env_gather_step_state')
+            reward = env._batch.reward[:A] if env.compute_reward else torch.zeros((A,), device=env.device)
+            done = env._batch.stop[:A]
+            self.replay_buffer.add(state, action, next_state, reward, done)
+            running_reward += float(reward.sum().item()) if env.compute_reward else 0.0
+            if self.t >= self.start_timesteps:
+                losses_log.append(self.update(self.replay_buffer.sample(self.batch_size)))
+            self.t += A
+            env.harvest_device()
+            A = env.n_alive()
+            episode_length += 1
+        return running_reward, losses_log, episode_length, {}

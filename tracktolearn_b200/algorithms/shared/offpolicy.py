@@ -71,6 +71,23 @@ class MaxEntropyActor(object):
     def parameters(self):
         return list(self._sd.values())
 
+    def share_parameters(self, module_state_dict):
+        """Alias the weights of a torch module (its ``state_dict()`` tensors share storage with the
+        parameters): optimiser steps then change the tensors this actor packs from, and
+        ``refresh_weights`` makes the tensor-core copies current."""
+        for k in self._sd:
+            t = module_state_dict[k]
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError('shared parameter %s must be a contiguous fp32 tensor on %s' % (k, self.device))
+            self._sd[k] = t
+        self._drop_plan()
+
+    def refresh_weights(self):
+        if self._plan is not None:
+            _lib.check(self._lib.ttl_actor_plan_refresh(self._plan, _lib.stream_ptr(self.device)),
+                       'ttl_actor_plan_refresh')
+            self._plan_layout = None
+
     # -- forward -------------------------------------------------------------------------
     def _drop_plan(self):
         if self._plan is not None:

@@ -1206,6 +1206,24 @@ int ttl_actor_plan_set_layout(ttl_actor_plan* p, int32_t C, int32_t CP, int32_t 
   return 0;
 }
 
+int ttl_actor_plan_refresh(ttl_actor_plan* p, void* stream) {
+  // the fp32 weights changed in place (an optimiser step): repack the bf16 copies
+  if (!p) return TTL_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const ttl_actor_weights& w = p->w;
+  for (int i = 0; i < w.n_layers - 1; ++i) {
+    const long long tot = (long long)p->n_pad[i] * p->k_pad[i];
+    TTL_LAUNCH("pack_weight_bf16_kernel", s,
+               pack_weight_bf16_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(w.w[i], p->wq[i], w.out_dim[i], w.in_dim[i],
+                                                                          p->n_pad[i], p->k_pad[i]));
+    const int bp = round_up(p->n_pad[i], BN);
+    TTL_LAUNCH("pack_bias_kernel", s, pack_bias_kernel<<<ttl_div_up(bp, 256), 256, 0, s>>>(w.b[i], p->bq[i], w.out_dim[i], bp));
+  }
+  p->has_alt = false;   // ttl_actor_plan_set_layout repacks the permuted first layer on demand
+  TTL_CHECK_LAST();
+  return 0;
+}
+
 int ttl_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t m, int32_t n,
                   int32_t k, int32_t ldc, int32_t relu, const int32_t* m_dev, void* stream) {
   if (!A || !W || !bias || !C || (k % BK) || (n % BK) || ldc < n || (ldc % 8)) return TTL_ERR_BAD_ARG;
