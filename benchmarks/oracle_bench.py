@@ -38,6 +38,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--n', type=int, default=131072)
     ap.add_argument('--cpu-n', type=int, default=256)
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
     a = ap.parse_args()
     import torch
     from tracktolearn_b200 import _lib, synthetic
@@ -45,7 +46,7 @@ def main():
     from tracktolearn_b200.tracking.tractogram import Tractogram
     dev = torch.device('cuda:0')
     ck = synthetic.oracle_checkpoint(n_head=4, n_layers=4, input_size=384, seed=2222)
-    model = OracleSingleton(ck, dev)
+    model = OracleSingleton(ck, dev, precision=a.precision)
     data, offsets = make_streamlines(a.n)
     pts = torch.from_numpy(data).to(dev)
     off = torch.from_numpy(offsets).to(dev)
@@ -72,7 +73,7 @@ def main():
     ref = O.oracle_predict(ck, sl)
     cpu_s = time.perf_counter() - t0
     err = float(np.abs(ref - host_scores[:a.cpu_n]).max())
-    fwd_ms = prof.get('oracle_forward_kernel', (0, 0.0))[1]
+    fwd_ms = prof.get('oracle_forward_tc_kernel' if a.precision == 'fp16' else 'oracle_forward_kernel', (0, 0.0))[1]
     out = {
         'metric': 'oracle streamlines/sec', 'n': a.n,
         'device_resident_streamlines_per_s': a.n / dev_s,
@@ -80,7 +81,8 @@ def main():
         'forward_kernel_tflops': a.n * FLOP_PER_STREAMLINE / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None,
         'kernels_ms': {k: v[1] for k, v in prof.items()},
         'cpu_port_streamlines_per_s': a.cpu_n / cpu_s, 'cpu_cores': os.cpu_count(), 'cpu_sample': a.cpu_n,
-        'max_abs_err_vs_cpu_oracle': err, 'dtype': 'f32 (CUDA cores)',
+        'max_abs_err_vs_cpu_oracle': err,
+        'dtype': 'f16 tcgen05 feed-forward, f32 attention' if a.precision == 'fp16' else 'f32 (CUDA cores)',
         'flop_per_streamline': FLOP_PER_STREAMLINE,
     }
     print(json.dumps(out))

@@ -260,6 +260,19 @@ int ttl_oracle_features_rows(const ttl_batch* b, int32_t cur, int32_t n_upper, f
 int ttl_oracle_forward(const ttl_oracle_weights* w, const float* dirs, int32_t n, float* scores,
                        void* stream);
 
+/* fp16 tensor-core tier (the reference's CUDA path autocasts to fp16, oracles/oracle.py:9,76):
+ * linear1 / linear2 of every encoder layer run on tcgen05 with fp16 operands and fp32 TMEM
+ * accumulators; attention, LayerNorm and the embedding stay fp32.  The plan holds fp16 copies of
+ * the feed-forward weights in `workspace` (device, 1024-byte aligned,
+ * ttl_oracle_workspace_bytes() bytes) and their TMA descriptors. */
+typedef struct ttl_oracle_plan ttl_oracle_plan;
+int64_t ttl_oracle_workspace_bytes(const ttl_oracle_weights* w);
+int ttl_oracle_plan_create(ttl_oracle_plan** out, const ttl_oracle_weights* w, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+void ttl_oracle_plan_destroy(ttl_oracle_plan* plan);
+int ttl_oracle_forward_tc(ttl_oracle_plan* plan, const float* dirs, int32_t n, float* scores,
+                          void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 int ttl_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */

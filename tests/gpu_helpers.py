@@ -7,7 +7,7 @@ from tracktolearn_b200.datasets.utils import MRIDataVolume
 
 
 def make_gpu_env(g, noisy, compute_reward, sub=None, seeds=None, oracle_checkpoint=None,
-                 oracle_stopping=False, oracle_bonus=0.0, min_length=1.0, **over):
+                 oracle_stopping=False, oracle_bonus=0.0, min_length=1.0, oracle_precision='fp32', **over):
     from tracktolearn_b200.environments import NoisyTrackingEnvironment, TrackingEnvironment
     sub = sub or subject_for(g)
     m = meta(g)
@@ -21,7 +21,7 @@ def make_gpu_env(g, noisy, compute_reward, sub=None, seeds=None, oracle_checkpoi
            'scoring_data': None,
            'compute_reward': compute_reward, 'alignment_weighting': 1.0, 'oracle_bonus': oracle_bonus,
            'rng': np.random.RandomState(1337), 'device': torch.device('cuda:0'), 'target_sh_order': 8,
-           'noise': 0.0, 'fa_map': None}
+           'noise': 0.0, 'fa_map': None, 'oracle_precision': oracle_precision}
     cls = NoisyTrackingEnvironment if noisy else TrackingEnvironment
     env = cls(subject, 'testing', dto)
     if seeds is not None:

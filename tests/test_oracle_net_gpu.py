@@ -11,10 +11,15 @@ from tracktolearn_b200 import synthetic
 pytestmark = pytest.mark.gpu
 
 
-def _oracle(ck):
+# fp16 tensor-core tier: linear1 / linear2 take fp16 operands (what the reference's CUDA path does
+# under autocast); scores are sigmoid outputs in [0, 1], tolerance absolute.
+FP16_TOL = 5e-3
+
+
+def _oracle(ck, precision='fp32'):
     from tracktolearn_b200.oracles.oracle import OracleSingleton
     OracleSingleton.clear()
-    return OracleSingleton(ck, torch.device('cuda:0'), batch_size=4096)
+    return OracleSingleton(ck, torch.device('cuda:0'), batch_size=4096, precision=precision)
 
 
 def test_oracle_net_matches_reference_fixture():
@@ -47,3 +52,31 @@ def test_oracle_net_matches_numpy_oracle(n_head, n_layers):
     got = model.predict(sl)
     ref = O.oracle_predict(ck, sl)
     np.testing.assert_allclose(got, ref, rtol=0, atol=5e-5)
+
+
+def test_oracle_net_fp16_tensor_core_tier_matches_reference_fixture():
+    g = load_golden('oracle_net')
+    n_head, n_layers, input_size, seed = [int(v) for v in g['hp']]
+    ck = synthetic.oracle_checkpoint(n_head=n_head, n_layers=n_layers, input_size=input_size, seed=seed)
+    sl = split_by_counts(g['sl_points'], g['sl_lengths'])
+    scores = _oracle(ck, 'fp16').predict(sl)
+    np.testing.assert_allclose(scores, g['scores'], rtol=0, atol=FP16_TOL)
+
+
+@pytest.mark.parametrize('n_head,n_layers,n', [(4, 4, 700), (2, 1, 1), (8, 2, 300)])
+def test_oracle_net_fp16_tensor_core_tier_matches_numpy_oracle(n_head, n_layers, n):
+    """More streamlines than resident CTAs (2 x 148) so the persistent loop, the weight ring and every
+    barrier wrap around across streamlines; n = 1 covers a single CTA."""
+    ck = synthetic.oracle_checkpoint(n_head=n_head, n_layers=n_layers, seed=78)
+    rng = np.random.RandomState(n_head * 10 + n_layers)
+    sl = synthetic.random_streamlines(n, rng, min_pts=2, max_pts=200)
+    model = _oracle(ck, 'fp16')
+    got = model.predict(sl)
+    ref = O.oracle_predict(ck, sl)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=FP16_TOL)
+    # same inputs, fp32 tier: the two tiers agree on which side of 0.5 every clear-cut score lies
+    got32 = _oracle(ck, 'fp32').predict(sl)
+    clear = np.abs(got32 - 0.5) > 2 * FP16_TOL
+    np.testing.assert_array_equal(got[clear] > 0.5, got32[clear] > 0.5)
+    # deterministic
+    np.testing.assert_array_equal(_oracle(ck, 'fp16').predict(sl), got)

@@ -76,6 +76,10 @@ SIGNATURES = {
     'ttl_gemm_bf16': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'ttl_oracle_features': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
     'ttl_oracle_forward': (c_i32, [P(OracleWeights), c_vp, c_i32, c_vp, c_vp]),
+    'ttl_oracle_workspace_bytes': (c_i64, [P(OracleWeights)]),
+    'ttl_oracle_plan_create': (c_i32, [P(c_vp), P(OracleWeights), c_vp, c_i64, c_vp]),
+    'ttl_oracle_plan_destroy': (None, [c_vp]),
+    'ttl_oracle_forward_tc': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
 }
 
 _lib = None

@@ -14,7 +14,14 @@
 //                           weights are streamed through shared memory in 16 KB chunks; all layers
 //                           in one launch, fp32 throughout (the reference's CPU precision; its CUDA
 //                           path autocasts to fp16).  ~147 MFLOP per streamline on the FP32 pipes.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstddef>
+#include <new>
+
 #include "ttl_common.cuh"
+#include "ttl_tc.cuh"
 
 namespace {
 
@@ -200,78 +207,97 @@ __device__ __forceinline__ void attention(const OracleSmem& sm, const float q[D_
   }
 }
 
+// The 128 token threads of a CTA synchronise on named barrier 1 (the tensor-core kernel has two
+// more warps that must not take part).
+__device__ __forceinline__ void token_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// relu(Linear(3,32)) * sqrt(32) + positional encoding for token `tid` of streamline `s`
+__device__ __forceinline__ void embed_token(const ttl_oracle_weights& W, const float* __restrict__ dirs, int s,
+                                            int tid, float x[D_MODEL]) {
+  float t3[3];
+  if (tid == 0) {
+    t3[0] = __ldg(W.cls_token); t3[1] = __ldg(W.cls_token + 1); t3[2] = __ldg(W.cls_token + 2);
+  } else {
+    const float* d = dirs + ((size_t)s * (N_TOK - 1) + (tid - 1)) * 3;
+    t3[0] = d[0]; t3[1] = d[1]; t3[2] = d[2];
+  }
+  const float scale = sqrtf((float)D_MODEL);
+#pragma unroll
+  for (int i = 0; i < D_MODEL; ++i) {
+    float e = __ldg(W.emb_b + i);
+    e = fmaf(__ldg(W.emb_w + 3 * i), t3[0], e);
+    e = fmaf(__ldg(W.emb_w + 3 * i + 1), t3[1], e);
+    e = fmaf(__ldg(W.emb_w + 3 * i + 2), t3[2], e);
+    x[i] = fmaxf(e, 0.f) * scale + __ldg(W.pe + tid * D_MODEL + i);
+  }
+}
+
+// x <- LayerNorm1(x + out_proj(attention(x))) for layer l; K/V of the layer go through sm.k / sm.v,
+// the projection weights through sm.w / sm.b.
+__device__ __forceinline__ void attention_block(const ttl_oracle_weights& W, int l, OracleSmem& sm, int tid,
+                                                float x[D_MODEL]) {
+  float q[D_MODEL];
+  token_sync();
+  stage(sm.w, W.in_proj_w[l], 3 * D_MODEL * D_MODEL, tid);
+  stage(sm.b, W.in_proj_b[l], 3 * D_MODEL, tid);
+  token_sync();
+  {
+    float kv[D_MODEL];
+    matvec32<D_MODEL>(sm.w, sm.b, x, q);
+    matvec32<D_MODEL>(sm.w + D_MODEL * D_MODEL, sm.b + D_MODEL, x, kv);
+#pragma unroll
+    for (int i = 0; i < D_MODEL; ++i) sm.k[tid][i] = kv[i];
+    matvec32<D_MODEL>(sm.w + 2 * D_MODEL * D_MODEL, sm.b + 2 * D_MODEL, x, kv);
+#pragma unroll
+    for (int i = 0; i < D_MODEL; ++i) sm.v[tid][i] = kv[i];
+  }
+  token_sync();
+  float att[D_MODEL];
+  switch (W.n_head) {
+    case 1: attention<1>(sm, q, att); break;
+    case 2: attention<2>(sm, q, att); break;
+    case 4: attention<4>(sm, q, att); break;
+    default: attention<8>(sm, q, att); break;
+  }
+  token_sync();
+  stage(sm.w, W.out_proj_w[l], D_MODEL * D_MODEL, tid);
+  stage(sm.b, W.out_proj_b[l], D_MODEL, tid);
+  token_sync();
+  {
+    float y[D_MODEL];
+    matvec32<D_MODEL>(sm.w, sm.b, att, y);
+#pragma unroll
+    for (int i = 0; i < D_MODEL; ++i) x[i] += y[i];
+  }
+  layer_norm32(x, W.norm1_w[l], W.norm1_b[l]);
+}
+
+__device__ __forceinline__ void score_head(const ttl_oracle_weights& W, const float x[D_MODEL], float* out) {
+  float y = __ldg(W.head_b);
+#pragma unroll
+  for (int i = 0; i < D_MODEL; ++i) y = fmaf(__ldg(W.head_w + i), x[i], y);
+  *out = 1.f / (1.f + expf(-y));
+}
+
+// ---- fp32 tier: everything on the FP32 pipes ----
 __global__ void __launch_bounds__(N_TOK, 3) oracle_forward_kernel(ttl_oracle_weights W,
                                                                  const float* __restrict__ dirs, int n,
                                                                  float* __restrict__ scores) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   OracleSmem& sm = *reinterpret_cast<OracleSmem*>(smem_raw);
   const int tid = threadIdx.x;   // token index
-  const int n_head = W.n_head;
   for (int s = blockIdx.x; s < n; s += gridDim.x) {
-    // ---- embedding: relu(Linear(3,32)) * sqrt(32) + positional encoding ----
     float x[D_MODEL];
-    {
-      float t3[3];
-      if (tid == 0) {
-        t3[0] = __ldg(W.cls_token); t3[1] = __ldg(W.cls_token + 1); t3[2] = __ldg(W.cls_token + 2);
-      } else {
-        const float* d = dirs + ((size_t)s * (N_TOK - 1) + (tid - 1)) * 3;
-        t3[0] = d[0]; t3[1] = d[1]; t3[2] = d[2];
-      }
-      const float scale = sqrtf((float)D_MODEL);
-#pragma unroll
-      for (int i = 0; i < D_MODEL; ++i) {
-        float e = __ldg(W.emb_b + i);
-        e = fmaf(__ldg(W.emb_w + 3 * i), t3[0], e);
-        e = fmaf(__ldg(W.emb_w + 3 * i + 1), t3[1], e);
-        e = fmaf(__ldg(W.emb_w + 3 * i + 2), t3[2], e);
-        x[i] = fmaxf(e, 0.f) * scale + __ldg(W.pe + tid * D_MODEL + i);
-      }
-    }
+    embed_token(W, dirs, s, tid, x);
     for (int l = 0; l < W.n_layers; ++l) {
-      // ---- self attention: K and V rows to shared memory, Q stays in registers ----
-      float q[D_MODEL];
-      __syncthreads();
-      stage(sm.w, W.in_proj_w[l], 3 * D_MODEL * D_MODEL, tid);
-      stage(sm.b, W.in_proj_b[l], 3 * D_MODEL, tid);
-      __syncthreads();
-      {
-        float kv[D_MODEL];
-        matvec32<D_MODEL>(sm.w, sm.b, x, q);
-        matvec32<D_MODEL>(sm.w + D_MODEL * D_MODEL, sm.b + D_MODEL, x, kv);
-#pragma unroll
-        for (int i = 0; i < D_MODEL; ++i) sm.k[tid][i] = kv[i];
-        matvec32<D_MODEL>(sm.w + 2 * D_MODEL * D_MODEL, sm.b + 2 * D_MODEL, x, kv);
-#pragma unroll
-        for (int i = 0; i < D_MODEL; ++i) sm.v[tid][i] = kv[i];
-      }
-      __syncthreads();
-      float att[D_MODEL];
-      switch (n_head) {
-        case 1: attention<1>(sm, q, att); break;
-        case 2: attention<2>(sm, q, att); break;
-        case 4: attention<4>(sm, q, att); break;
-        default: attention<8>(sm, q, att); break;
-      }
-      // ---- output projection, residual, LayerNorm 1 ----
-      __syncthreads();
-      stage(sm.w, W.out_proj_w[l], D_MODEL * D_MODEL, tid);
-      stage(sm.b, W.out_proj_b[l], D_MODEL, tid);
-      __syncthreads();
-      {
-        float y[D_MODEL];
-        matvec32<D_MODEL>(sm.w, sm.b, att, y);
-#pragma unroll
-        for (int i = 0; i < D_MODEL; ++i) x[i] += y[i];
-      }
-      layer_norm32(x, W.norm1_w[l], W.norm1_b[l]);
+      attention_block(W, l, sm, tid, x);
       // ---- feed forward 32 -> d_ff -> 32 in chunks of 64 hidden units ----
       float out[D_MODEL];
 #pragma unroll
       for (int i = 0; i < D_MODEL; ++i) out[i] = 0.f;
       const int d_ff = W.d_ff;
       for (int c0 = 0; c0 < d_ff; c0 += FF_CHUNK) {
-        __syncthreads();
+        token_sync();
         // W1 rows c0..c0+63 ([64][32], contiguous) and W2 columns c0..c0+63 ([32][64])
         stage(sm.w, W.lin1_w[l] + (size_t)c0 * D_MODEL, FF_CHUNK * D_MODEL, tid);
         stage(sm.b, W.lin1_b[l] + c0, FF_CHUNK, tid);
@@ -279,7 +305,7 @@ __global__ void __launch_bounds__(N_TOK, 3) oracle_forward_kernel(ttl_oracle_wei
           const int i = t / FF_CHUNK, j = t - i * FF_CHUNK;
           sm.w[FF_CHUNK * D_MODEL + t] = __ldg(W.lin2_w[l] + (size_t)i * d_ff + c0 + j);
         }
-        __syncthreads();
+        token_sync();
         float hbuf[FF_CHUNK];
         matvec32<FF_CHUNK>(sm.w, sm.b, x, hbuf);
 #pragma unroll
@@ -303,16 +329,284 @@ __global__ void __launch_bounds__(N_TOK, 3) oracle_forward_kernel(ttl_oracle_wei
       for (int i = 0; i < D_MODEL; ++i) x[i] += out[i] + __ldg(W.lin2_b[l] + i);
       layer_norm32(x, W.norm2_w[l], W.norm2_b[l]);
     }
-    if (tid == 0) {
-      float y = __ldg(W.head_b);
-#pragma unroll
-      for (int i = 0; i < D_MODEL; ++i) y = fmaf(__ldg(W.head_w + i), x[i], y);
-      scores[s] = 1.f / (1.f + expf(-y));
-    }
+    if (tid == 0) score_head(W, x, scores + s);
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// fp16 tensor-core tier: the feed-forward block (91 % of the FLOPs) on tcgen05
+// ------------------------------------------------------------------------------------------
+// The reference's CUDA path runs the model under torch.autocast(fp16) (oracles/oracle.py:9,76):
+// linear layers take fp16 operands and accumulate in fp32.  This tier does the same for
+// linear1 / linear2; attention, LayerNorm and the embedding stay fp32 on the token threads.
+//
+// One CTA = one streamline at a time (128 tokens = the M of a 128-row UMMA), two CTAs per SM:
+//   warps 0-3  token threads (thread t = token t = TMEM lane t): attention block in fp32, then per
+//              64-wide hidden chunk c the epilogue of GEMM1: tcgen05.ld acc1 -> +b1, ReLU, fp16 ->
+//              swizzled store into H[c&1], the A operand of GEMM2
+//   warp 4     TMA producer: streams the fp16 weights (W1 chunk pair 8 KB + two W2 tiles 2x4 KB per
+//              stage) through a 2-stage ring, running ahead across layers and streamlines
+//   warp 5     MMA issuer: GEMM1(c) acc1[c&1] = X . W1_c^T (M128 N64 K32), then GEMM2(c-1)
+//              acc2 += H_{c-1} . W2_{c-1}^T (M128 N32 K64), so the tensor pipe works on chunk c+1
+//              while the token threads are in the epilogue of chunk c.
+// TMEM: 256 columns per CTA (acc1 2 x 64, acc2 32).  The hidden activations never leave the SM.
+namespace tcgen {
+using namespace ttl_tc;
+constexpr int CH = 64;                       // hidden units per chunk
+constexpr int NST = 2;                       // weight ring stages (one stage = two chunks)
+constexpr int STAGE_BYTES = 16384;           // 8 KB W1 pair tile + 2 x 4 KB W2 tiles
+constexpr int OFF_XA = 0;                    // [128][128 B] SW128, x (fp16) in the first 64 B of a row
+constexpr int OFF_H = 16384;                 // 2 x [128][128 B] SW128; aliases OracleSmem::k / ::v
+constexpr int OFF_W = OFF_H + 32768;         // OracleSmem::w / ::b continue here (fp32 staging, b1)
+constexpr int OFF_RING = OFF_H + (int)sizeof(OracleSmem);
+constexpr int OFF_BAR = OFF_RING + NST * STAGE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 256;
+constexpr int ACC2_COL = 128;
+static_assert(offsetof(OracleSmem, w) == 32768, "k and v must cover exactly the two H buffers");
+static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
+}  // namespace tcgen
+
+__global__ void __launch_bounds__(tcgen::THREADS, 2)
+oracle_forward_tc_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensorMap tma_w1,
+                         const __grid_constant__ CUtensorMap tma_w2, const float* __restrict__ dirs, int n,
+                         float* __restrict__ scores) {
+  using namespace tcgen;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ttl_smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sbase = smem_raw + (base - raw);
+  OracleSmem& sm = *reinterpret_cast<OracleSmem*>(sbase + OFF_H);
+  const uint32_t bar0 = base + OFF_BAR;
+  auto full = [&](int s) { return bar0 + 8u * s; };               // TMA -> MMA
+  auto empty = [&](int s) { return bar0 + 8u * (NST + s); };      // MMA -> TMA
+  auto acc1_full = [&](int b) { return bar0 + 8u * (2 * NST + b); };       // MMA -> tokens
+  auto acc1_empty = [&](int b) { return bar0 + 8u * (2 * NST + 2 + b); };  // tokens -> MMA (4 warps)
+  auto h_full = [&](int b) { return bar0 + 8u * (2 * NST + 4 + b); };      // tokens -> MMA (4 warps)
+  auto h_empty = [&](int b) { return bar0 + 8u * (2 * NST + 6 + b); };     // MMA -> tokens
+  const uint32_t x_ready = bar0 + 8u * (2 * NST + 8);                       // tokens -> MMA
+  const uint32_t acc2_full = bar0 + 8u * (2 * NST + 9);                     // MMA -> tokens
+  const uint32_t tmem_slot = bar0 + 8u * (2 * NST + 10);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sbase + OFF_BAR + 8 * (2 * NST + 10));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_layers = W.n_layers;
+  const int n_chunks = W.d_ff / CH;          // even (d_ff % 128 == 0)
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_w1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_w2)) : "memory");
+    for (int s = 0; s < NST; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc1_full(b), 1); mbar_init(acc1_empty(b), 4);
+      mbar_init(h_full(b), 4); mbar_init(h_empty(b), 1);
+    }
+    mbar_init(x_ready, 1);
+    mbar_init(acc2_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {  // ===== TMA producer =====
+      uint32_t gp = 0;   // chunk pairs issued so far
+      for (int s = blockIdx.x; s < n; s += gridDim.x)
+        for (int l = 0; l < n_layers; ++l)
+          for (int j = 0; j < n_chunks / 2; ++j, ++gp) {
+            const int st = gp % NST;
+            mbar_wait(empty(st), ((gp / NST) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(full(st), STAGE_BYTES);
+            const uint32_t dst = base + OFF_RING + st * STAGE_BYTES;
+            tma_load_2d(dst, &tma_w1, full(st), 0, l * (W.d_ff / 2) + 64 * j);
+            tma_load_2d(dst + 8192, &tma_w2, full(st), 128 * j, l * D_MODEL);
+            tma_load_2d(dst + 12288, &tma_w2, full(st), 128 * j + 64, l * D_MODEL);
+          }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc1 = umma_idesc_f16(128, CH, 0);
+      constexpr uint32_t idesc2 = umma_idesc_f16(128, D_MODEL, 0);
+      const uint64_t desc_x = umma_desc_sw128(base + OFF_XA);
+      uint32_t g = 0;       // chunks whose GEMM1 has been issued
+      uint32_t n_ffn = 0;
+      for (int s = blockIdx.x; s < n; s += gridDim.x)
+        for (int l = 0; l < n_layers; ++l, ++n_ffn) {
+          mbar_wait(x_ready, n_ffn & 1u);
+          tc_fence_after();
+          for (int c = 0; c <= n_chunks; ++c) {
+            if (c < n_chunks) {
+              const uint32_t b = g & 1u, u = g >> 1, gp = g >> 1;
+              const int st = gp % NST;
+              if ((c & 1) == 0) {
+                mbar_wait(full(st), (gp / NST) & 1u);
+                tc_fence_after();
+              }
+              mbar_wait(acc1_empty(b), (u & 1u) ^ 1u);
+              tc_fence_after();
+              const uint64_t desc_w1 = umma_desc_sw128(base + OFF_RING + st * STAGE_BYTES) + (uint64_t)(4 * (c & 1));
+#pragma unroll
+              for (int k = 0; k < D_MODEL / 16; ++k)
+                tc_mma_bf16(tmem_base + b * CH, desc_x + (uint64_t)(2 * k), desc_w1 + (uint64_t)(2 * k), idesc1,
+                            (uint32_t)(k != 0));
+              tc_commit(acc1_full(b));
+              ++g;
+            }
+            if (c >= 1) {
+              const uint32_t g2 = g - (c < n_chunks ? 2u : 1u);   // global index of chunk c-1
+              const uint32_t b = g2 & 1u, u = g2 >> 1, gp = g2 >> 1;
+              const int st = gp % NST;
+              mbar_wait(h_full(b), u & 1u);
+              tc_fence_after();
+              const uint64_t desc_h = umma_desc_sw128(base + OFF_H + b * 16384);
+              const uint64_t desc_w2 =
+                  umma_desc_sw128(base + OFF_RING + st * STAGE_BYTES + 8192 + ((c - 1) & 1) * 4096);
+#pragma unroll
+              for (int k = 0; k < CH / 16; ++k)
+                tc_mma_bf16(tmem_base + ACC2_COL, desc_h + (uint64_t)(2 * k), desc_w2 + (uint64_t)(2 * k), idesc2,
+                            (uint32_t)((c - 1) != 0 || k != 0));
+              tc_commit(h_empty(b));
+              if ((c - 1) & 1) tc_commit(empty(st));
+              if (c == n_chunks) tc_commit(acc2_full);
+            }
+          }
+        }
+    }
+  } else {  // ===== token threads =====
+    const int tid = threadIdx.x;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float* s_b1 = sm.w;        // linear1 bias of the layer, staged after the attention block
+    uint32_t g = 0, n_ffn = 0;
+    for (int s = blockIdx.x; s < n; s += gridDim.x) {
+      float x[D_MODEL];
+      embed_token(W, dirs, s, tid, x);
+      for (int l = 0; l < n_layers; ++l, ++n_ffn) {
+        attention_block(W, l, sm, tid, x);
+        // x (fp16) -> A operand of GEMM1; b1 -> shared memory
+        token_sync();    // every thread is done with sm.w (out_proj) and sm.k / sm.v
+        {
+          uint32_t pk[D_MODEL / 2];
+#pragma unroll
+          for (int i = 0; i < D_MODEL / 2; ++i) {
+            __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int cch = 0; cch < 4; ++cch)
+            *reinterpret_cast<uint4*>(sbase + OFF_XA + sw128_offset(tid, cch)) =
+                make_uint4(pk[4 * cch], pk[4 * cch + 1], pk[4 * cch + 2], pk[4 * cch + 3]);
+        }
+        stage(s_b1, W.lin1_b[l], W.d_ff, tid);
+        fence_proxy_async();
+        token_sync();
+        if (tid == 0) mbar_arrive(x_ready);
+        for (int c = 0; c < n_chunks; ++c, ++g) {
+          const uint32_t b = g & 1u, u = g >> 1;
+          mbar_wait(acc1_full(b), u & 1u);
+          tc_fence_after();
+          uint32_t v0[32], v1[32];
+          tc_ld32(lane_base + b * CH, v0);
+          tc_ld32(lane_base + b * CH + 32, v1);
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc1_empty(b));
+          uint32_t pk[CH / 2];
+          const float* bb = s_b1 + c * CH;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * j);
+            __half2 h0 = __floats2half2_rn(fmaxf(__uint_as_float(v0[4 * j + 0]) + b4.x, 0.f),
+                                           fmaxf(__uint_as_float(v0[4 * j + 1]) + b4.y, 0.f));
+            __half2 h1 = __floats2half2_rn(fmaxf(__uint_as_float(v0[4 * j + 2]) + b4.z, 0.f),
+                                           fmaxf(__uint_as_float(v0[4 * j + 3]) + b4.w, 0.f));
+            pk[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bb + 32 + 4 * j);
+            __half2 h0 = __floats2half2_rn(fmaxf(__uint_as_float(v1[4 * j + 0]) + b4.x, 0.f),
+                                           fmaxf(__uint_as_float(v1[4 * j + 1]) + b4.y, 0.f));
+            __half2 h1 = __floats2half2_rn(fmaxf(__uint_as_float(v1[4 * j + 2]) + b4.z, 0.f),
+                                           fmaxf(__uint_as_float(v1[4 * j + 3]) + b4.w, 0.f));
+            pk[16 + 2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[16 + 2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+          mbar_wait(h_empty(b), (u & 1u) ^ 1u);   // GEMM2 of the chunk that used H[b] before has retired
+          uint8_t* hrow = sbase + OFF_H + b * 16384;
+#pragma unroll
+          for (int cch = 0; cch < 8; ++cch)
+            *reinterpret_cast<uint4*>(hrow + sw128_offset(tid, cch)) =
+                make_uint4(pk[4 * cch], pk[4 * cch + 1], pk[4 * cch + 2], pk[4 * cch + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h_full(b));
+        }
+        // linear2 output: acc2 -> registers, residual, LayerNorm 2
+        mbar_wait(acc2_full, n_ffn & 1u);
+        tc_fence_after();
+        uint32_t o[32];
+        tc_ld32(lane_base + ACC2_COL, o);
+        tc_wait_ld();
+        tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < D_MODEL; ++i) x[i] += __uint_as_float(o[i]) + __ldg(W.lin2_b[l] + i);
+        layer_norm32(x, W.norm2_w[l], W.norm2_b[l]);
+      }
+      if (tid == 0) score_head(W, x, scores + s);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// fp32 [L][d_ff][32] linear1 weights -> fp16 [L][d_ff/2][64]: row 64j+r of a layer holds hidden
+// unit 128j+r in its first 32 columns and unit 128j+64+r in the last 32, so that one 64-row
+// SWIZZLE_128B TMA box carries two consecutive 64-unit chunks as K-offset 0 / 64 B operands.
+__global__ void pack_oracle_w1_kernel(ttl_oracle_weights W, __half* __restrict__ out) {
+  const int per_layer = W.d_ff * D_MODEL;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= per_layer * W.n_layers) return;
+  const int l = t / per_layer, e = t - l * per_layer;
+  const int row = e / 64, col = e - row * 64;
+  const int j = row / 64, r = row - j * 64;
+  const int unit = 128 * j + (col >= 32 ? 64 : 0) + r;
+  out[t] = __float2half_rn(__ldg(W.lin1_w[l] + (size_t)unit * D_MODEL + (col & 31)));
+}
+// fp32 [L][32][d_ff] linear2 weights -> fp16, same shape (K-major B operand of GEMM2 as is)
+__global__ void pack_oracle_w2_kernel(ttl_oracle_weights W, __half* __restrict__ out) {
+  const int per_layer = W.d_ff * D_MODEL;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= per_layer * W.n_layers) return;
+  const int l = t / per_layer, e = t - l * per_layer;
+  out[t] = __float2half_rn(__ldg(W.lin2_w[l] + e));
+}
+
 }  // namespace
+
+struct ttl_oracle_plan {
+  ttl_oracle_weights w;
+  __half* w1;            // packed linear1 weights (pack_oracle_w1_kernel)
+  __half* w2;            // fp16 linear2 weights
+  CUtensorMap map_w1, map_w2;
+};
 
 extern "C" {
 
@@ -356,6 +650,80 @@ int ttl_oracle_forward(const ttl_oracle_weights* w, const float* dirs, int32_t n
   const int grid = n < sms * 3 ? n : sms * 3;
   TTL_LAUNCH("oracle_forward_kernel", s,
              oracle_forward_kernel<<<grid, N_TOK, sizeof(OracleSmem), s>>>(*w, dirs, n, scores));
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+
+int64_t ttl_oracle_workspace_bytes(const ttl_oracle_weights* w) {
+  if (!w || w->n_layers < 1 || w->n_layers > 8 || w->d_model != D_MODEL || w->d_ff <= 0) return -1;
+  return (int64_t)2 * w->n_layers * w->d_ff * D_MODEL * 2;   // fp16 copies of linear1 and linear2
+}
+
+int ttl_oracle_plan_create(ttl_oracle_plan** out, const ttl_oracle_weights* w, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  if (!out || !w || !workspace) return TTL_ERR_BAD_ARG;
+  if (w->d_model != D_MODEL || w->n_tokens != N_TOK || w->n_layers < 1 || w->n_layers > 8 ||
+      (w->n_head != 1 && w->n_head != 2 && w->n_head != 4 && w->n_head != 8) || (w->d_ff % 128) ||
+      w->d_ff > 4096)
+    return TTL_ERR_UNSUPPORTED;
+  const int64_t need = ttl_oracle_workspace_bytes(w);
+  if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return TTL_ERR_BAD_ARG;
+  ttl_oracle_plan* p = new (std::nothrow) ttl_oracle_plan();
+  if (!p) return TTL_ERR_BAD_ARG;
+  p->w = *w;
+  p->w1 = static_cast<__half*>(workspace);
+  p->w2 = p->w1 + (size_t)w->n_layers * w->d_ff * D_MODEL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tot = w->n_layers * w->d_ff * D_MODEL;
+  TTL_LAUNCH("pack_oracle_w1_kernel", s, pack_oracle_w1_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(*w, p->w1));
+  TTL_LAUNCH("pack_oracle_w2_kernel", s, pack_oracle_w2_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(*w, p->w2));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { delete p; return (int)e; }
+  ttl_tc::EncodeTiledFn fn = ttl_tc::get_encode_fn();
+  if (!fn) { delete p; return TTL_ERR_DRIVER; }
+  {  // linear1, packed [L * d_ff / 2][64] fp16, box 64 rows x 64 columns
+    cuuint64_t dims[2] = {64, (cuuint64_t)w->n_layers * (w->d_ff / 2)};
+    cuuint64_t strides[1] = {64 * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    if (fn(&p->map_w1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->w1, dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete p; return TTL_ERR_DRIVER; }
+  }
+  {  // linear2 [L * 32][d_ff] fp16, box 32 rows x 64 columns
+    cuuint64_t dims[2] = {(cuuint64_t)w->d_ff, (cuuint64_t)w->n_layers * D_MODEL};
+    cuuint64_t strides[1] = {(cuuint64_t)w->d_ff * 2};
+    cuuint32_t box[2] = {64, D_MODEL};
+    cuuint32_t estr[2] = {1, 1};
+    if (fn(&p->map_w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->w2, dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete p; return TTL_ERR_DRIVER; }
+  }
+  *out = p;
+  return 0;
+}
+
+void ttl_oracle_plan_destroy(ttl_oracle_plan* plan) { delete plan; }
+
+int ttl_oracle_forward_tc(ttl_oracle_plan* p, const float* dirs, int32_t n, float* scores, void* stream) {
+  if (!p || !dirs || !scores) return TTL_ERR_BAD_ARG;
+  if (n <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(oracle_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tcgen::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = n < sms * 2 ? n : sms * 2;
+  TTL_LAUNCH("oracle_forward_tc_kernel", s,
+             oracle_forward_tc_kernel<<<grid, tcgen::THREADS, tcgen::SMEM_BYTES, s>>>(p->w, p->map_w1, p->map_w2,
+                                                                                     dirs, n, scores));
   TTL_CHECK_LAST();
   return 0;
 }

@@ -63,7 +63,9 @@ class BaseEnv(object):
         if self.oracle_checkpoint and (self.oracle_stopping_criterion
                                        or (self.compute_reward and self.oracle_bonus > 0)):
             from tracktolearn_b200.oracles.oracle import OracleSingleton
-            self._oracle = OracleSingleton(self.oracle_checkpoint, self.device)
+            # 'fp16' = the reference's CUDA arithmetic (autocast), 'fp32' = its CPU arithmetic
+            self._oracle = OracleSingleton(self.oracle_checkpoint, self.device,
+                                           precision=env_dto.get('oracle_precision', 'fp16'))
 
         self._uploaded = False
         self.load_subject()

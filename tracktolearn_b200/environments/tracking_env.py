@@ -181,9 +181,7 @@ class TrackingEnvironment(BaseEnv):
                 _lib.check(self._lib.ttl_oracle_features_rows(ctypes.byref(self._b), self._cur, n_up,
                                                               _lib.ptr(self._oracle_dirs), sp),
                            'ttl_oracle_features_rows')
-                _lib.check(self._lib.ttl_oracle_forward(ctypes.byref(self._oracle.weights.struct),
-                                                        _lib.ptr(self._oracle_dirs), n_up,
-                                                        _lib.ptr(self._oracle_scores), sp), 'ttl_oracle_forward')
+                self._oracle.forward_dirs(self._oracle_dirs, _lib.ptr(self._oracle_scores), n_up)
                 bonus = float(self.oracle_bonus) if self.compute_reward else 0.0
                 _lib.check(self._lib.ttl_env_step_finish(
                     ctypes.byref(self._volume), ctypes.byref(self._params), ctypes.byref(self._b), self._cur,

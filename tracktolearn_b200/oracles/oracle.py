@@ -2,8 +2,11 @@
 
 ``OracleSingleton(checkpoint, device).predict(streamlines) -> np.ndarray[N]`` like the reference;
 the resampling to 128 points (dipy ``set_number_of_points``), the ``np.diff`` and the transformer
-all run on the device (``ttl_oracle_features`` / ``ttl_oracle_forward``).  Scores are computed in
-fp32.  Every streamline is scored: the reference's own loop drops a trailing partial batch when
+all run on the device (``ttl_oracle_features`` / ``ttl_oracle_forward*``).  Two precision tiers:
+``'fp16'`` (default) is the reference's CUDA arithmetic -- it scores under ``torch.autocast`` fp16
+(oracle.py:9,76) -- with the feed-forward blocks on tcgen05 tensor cores (fp16 operands, fp32
+accumulators); ``'fp32'`` is the reference's CPU arithmetic on the FP32 pipes, used by the
+parity tests.  Every streamline is scored: the reference's own loop drops a trailing partial batch when
 N > 4096; we follow ``experiment/oracle_validator.py:40-47``'s chunked semantics.
 """
 import ctypes
@@ -72,17 +75,52 @@ class OracleSingleton(object):
             cls._self = super().__new__(cls)
         return cls._self
 
-    def __init__(self, checkpoint, device, batch_size=4096):
+    def __init__(self, checkpoint, device, batch_size=4096, precision='fp16'):
         ck = checkpoint if isinstance(checkpoint, dict) else torch.load(checkpoint, map_location='cpu')
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.TTLError('the oracle runs on a CUDA device only (got %s)' % (self.device,))
+        if precision not in ('fp16', 'fp32'):
+            raise ValueError("precision must be 'fp16' or 'fp32'")
         self._lib = _lib.load()
+        self._destroy_plan()
         self.weights = TransformerOracleWeights(ck, self.device)
         self.batch_size = batch_size
+        self.precision = precision
+        if precision == 'fp16':
+            w = self.weights.struct
+            nbytes = self._lib.ttl_oracle_workspace_bytes(ctypes.byref(w))
+            if nbytes < 0:
+                raise _lib.TTLError('ttl_oracle_workspace_bytes: unsupported oracle shape')
+            self._workspace = torch.zeros((nbytes + 1024,), dtype=torch.uint8, device=self.device)
+            base = (self._workspace.data_ptr() + 1023) // 1024 * 1024
+            plan = ctypes.c_void_p()
+            _lib.check(self._lib.ttl_oracle_plan_create(ctypes.byref(plan), ctypes.byref(w), ctypes.c_void_p(base),
+                                                        nbytes, _lib.stream_ptr(self.device)),
+                       'ttl_oracle_plan_create')
+            self._plan = plan
+
+    def _destroy_plan(self):
+        plan = getattr(self, '_plan', None)
+        if plan is not None:
+            self._lib.ttl_oracle_plan_destroy(plan)
+        self._plan = None
+        self._workspace = None
+
+    def forward_dirs(self, dirs, scores_ptr, n):
+        """TransformerOracle.forward on resampled directions [n,127,3] (device) -> scores at ``scores_ptr``."""
+        sp = _lib.stream_ptr(self.device)
+        if self.precision == 'fp16':
+            _lib.check(self._lib.ttl_oracle_forward_tc(self._plan, _lib.ptr(dirs), n, scores_ptr, sp),
+                       'ttl_oracle_forward_tc')
+        else:
+            _lib.check(self._lib.ttl_oracle_forward(ctypes.byref(self.weights.struct), _lib.ptr(dirs), n,
+                                                    scores_ptr, sp), 'ttl_oracle_forward')
 
     @classmethod
     def clear(cls):
+        if cls._self is not None and getattr(cls._self, '_lib', None) is not None:
+            cls._self._destroy_plan()
         cls._self = None
 
     # --------------------------------------------------------------------------- device
@@ -98,9 +136,7 @@ class OracleSingleton(object):
             dirs = torch.empty((s1 - s0, 127, 3), dtype=torch.float32, device=self.device)
             _lib.check(self._lib.ttl_oracle_features(_lib.ptr(points), ctypes.c_void_p(offsets.data_ptr() + 8 * s0),
                                                      s1 - s0, _lib.ptr(dirs), sp), 'ttl_oracle_features')
-            _lib.check(self._lib.ttl_oracle_forward(ctypes.byref(self.weights.struct), _lib.ptr(dirs), s1 - s0,
-                                                    ctypes.c_void_p(scores.data_ptr() + 4 * s0), sp),
-                       'ttl_oracle_forward')
+            self.forward_dirs(dirs, ctypes.c_void_p(scores.data_ptr() + 4 * s0), s1 - s0)
         return scores
 
     # --------------------------------------------------------------------------- host API
