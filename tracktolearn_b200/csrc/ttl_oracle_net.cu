@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 
 #include <cstddef>
+#include <cstdlib>
 #include <new>
 
 #include "ttl_common.cuh"
@@ -577,6 +578,515 @@ oracle_forward_tc_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensorM
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// fp16 tensor-core tier, full version: every matrix product of the encoder layer on tcgen05
+// ------------------------------------------------------------------------------------------
+// Per layer (token thread t = token t = TMEM lane t; one MMA-issuing thread; one TMA thread):
+//   QKV      [128x32].[32x96]   x (fp16) in T0, in_proj weights in the ring      -> TMEM 128..223
+//   tokens   +bias; Q (head-masked K=16 slices) -> T1, K -> T0, V^T -> VT (all fp16, SW128 tiles)
+//   per head h, per half j of the keys (same double-buffered pipeline as the feed-forward chunks):
+//     S      acc1[j] = Q_h . K_j^T                       (M128 N64 K16)
+//     tokens row max / exp2 / row sum in fp32; P (fp16) written IN PLACE over S in tensor memory
+//     PV     O[h][j] = P . V_j   (A operand from TMEM, M128 N16 K64)          -> TMEM 128..255
+//   tokens   combine the two halves (each was scaled by its own row max), 1/sum, o (fp16) -> T0
+//   out-proj [128x32].[32x32]                                                  -> TMEM 128..159
+//   tokens   +bias, residual, LayerNorm 1, x (fp16) -> T0
+//   FFN      per 64-wide chunk c: acc1[c&1] = x . W1_c^T; tokens: +b1, ReLU, fp16 in place;
+//            acc2 += H_c . W2_c^T with H_c read from tensor memory       -> TMEM 128..159
+//   tokens   +bias, residual, LayerNorm 2
+// The hidden activations and the attention probabilities never touch shared memory: the token
+// threads read the fp32 accumulator with tcgen05.ld and write the fp16 operand of the next product
+// back over it with tcgen05.st, so one chunk costs two mbarrier hand-offs and no proxy fence.
+// Shared memory per CTA (two CTAs per SM): T0 16 KB [x or K | o or x'], T1 16 KB Q slices, VT 8 KB,
+// weight ring 4 x 17 KB.  TMEM: 256 columns (acc1 2 x 64 | 128 shared by QKV, O, out-proj, acc2).
+namespace tc2 {
+using namespace ttl_tc;
+constexpr int CH = 64;
+constexpr int NST = 4;
+constexpr int STAGE_BYTES = 17408;
+constexpr int ST_W2 = 8192, ST_B1 = 16384;      // inside a feed-forward stage
+constexpr int ST_PRM = 12288;                   // inside an attention stage
+constexpr int PRM_FLOATS = 288;                 // in_proj_b 96 | out_proj_b 32 | norm1_w 32 | norm1_b 32 | lin2_b | norm2_w | norm2_b
+constexpr int P_INB = 0, P_OUTB = 96, P_N1W = 128, P_N1B = 160, P_L2B = 192, P_N2W = 224, P_N2B = 256;
+constexpr uint32_t FFN_TX = 16384 + 2 * CH * 4;
+constexpr uint32_t ATT_TX = 12288 + PRM_FLOATS * 4;
+constexpr int OFF_T0 = 0, OFF_T1 = 16384, OFF_VT = 32768, OFF_RING = 40960;
+constexpr int OFF_BAR = OFF_RING + NST * STAGE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 256;
+constexpr int COL_B = 128;                      // QKV result / O blocks / out-proj result / FFN output
+static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
+}  // namespace tc2
+
+// MUFU.EX2 (2 ulp); arguments here are <= 0, results feed fp16 probabilities
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 8 consecutive fp32 -> one 16-byte chunk of fp16
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+  return make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                    *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+}
+// x[32] (fp16) -> chunks chunk0..chunk0+3 of row `row` of a SW128 tile
+__device__ __forceinline__ void store_row32(uint8_t* tile, int row, int chunk0, const float x[D_MODEL]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(tile + ttl_tc::sw128_offset(row, chunk0 + c)) = pack8(x + 8 * c);
+}
+__device__ __forceinline__ void layer_norm32_s(float x[D_MODEL], const float* g, const float* b) {
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < D_MODEL; ++i) mean += x[i];
+  mean *= (1.f / D_MODEL);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < D_MODEL; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
+  var *= (1.f / D_MODEL);
+  const float inv = 1.f / sqrtf(var + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < D_MODEL; ++i) x[i] = (x[i] - mean) * inv * g[i] + b[i];
+}
+
+template <int NH>
+__global__ void __launch_bounds__(tc2::THREADS, 2)
+oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensorMap tma_w1,
+                          const __grid_constant__ CUtensorMap tma_w2, const __grid_constant__ CUtensorMap tma_wa,
+                          const float* __restrict__ b1_all, const float* __restrict__ prm_all,
+                          const float* __restrict__ dirs, int n, float* __restrict__ scores) {
+  using namespace tc2;
+  constexpr int DH = D_MODEL / NH;
+  constexpr int NSUB = 2 * NH;                       // (head, key half) pairs
+  constexpr int PV_N = NH == 1 ? 32 : 16;            // channels one PV product writes
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ttl_smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sbase = smem_raw + (base - raw);
+  const uint32_t bar0 = base + OFF_BAR;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (NST + s); };
+  auto acc1_full = [&](int b) { return bar0 + 8u * (2 * NST + b); };   // MMA -> tokens: S / GEMM1 result
+  auto h_full = [&](int b) { return bar0 + 8u * (2 * NST + 2 + b); };  // tokens -> MMA: fp16 operand in place (4 warps)
+  const uint32_t x_ready = bar0 + 8u * (2 * NST + 4);   // tokens -> MMA: a shared-memory operand tile is complete
+  const uint32_t done = bar0 + 8u * (2 * NST + 5);      // MMA -> tokens: a result is complete in TMEM
+  const uint32_t tmem_slot = bar0 + 8u * (2 * NST + 6);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sbase + OFF_BAR + 8 * (2 * NST + 6));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_layers = W.n_layers;
+  const int n_chunks = W.d_ff / CH;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_w1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_w2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_wa)) : "memory");
+    for (int s = 0; s < NST; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc1_full(b), 1); mbar_init(h_full(b), 4); }
+    mbar_init(x_ready, 1);
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {  // ===== TMA producer: per layer one attention stage, then d_ff/128 feed-forward stages =====
+      uint32_t gp = 0;
+      for (int s = blockIdx.x; s < n; s += gridDim.x)
+        for (int l = 0; l < n_layers; ++l) {
+          {
+            const int st = gp % NST;
+            mbar_wait(empty(st), ((gp / NST) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(full(st), ATT_TX);
+            const uint32_t dst = base + OFF_RING + st * STAGE_BYTES;
+            tma_load_2d(dst, &tma_wa, full(st), 0, l * 96);
+            bulk_load(dst + ST_PRM, prm_all + (size_t)l * PRM_FLOATS, PRM_FLOATS * 4, full(st));
+            ++gp;
+          }
+          for (int j = 0; j < n_chunks / 2; ++j, ++gp) {
+            const int st = gp % NST;
+            mbar_wait(empty(st), ((gp / NST) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(full(st), FFN_TX);
+            const uint32_t dst = base + OFF_RING + st * STAGE_BYTES;
+            tma_load_2d(dst, &tma_w1, full(st), 0, l * (W.d_ff / 2) + 64 * j);
+            tma_load_2d(dst + ST_W2, &tma_w2, full(st), 128 * j, l * D_MODEL);
+            tma_load_2d(dst + ST_W2 + 4096, &tma_w2, full(st), 128 * j + 64, l * D_MODEL);
+            bulk_load(dst + ST_B1, b1_all + (size_t)l * W.d_ff + 2 * CH * j, 2 * CH * 4, full(st));
+          }
+        }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t id_qkv = umma_idesc_f16(128, 96, 0);
+      constexpr uint32_t id_64 = umma_idesc_f16(128, 64, 0);
+      constexpr uint32_t id_pv = umma_idesc_f16(128, PV_N, 0);
+      constexpr uint32_t id_32 = umma_idesc_f16(128, 32, 0);
+      const uint64_t d_t0 = umma_desc_sw128(base + OFF_T0);
+      const uint64_t d_q = umma_desc_sw128(base + OFF_T1);
+      // The acc1 buffers are used strictly alternately (0,1,0,1,...) through attention and feed-forward
+      // phases alike; use k lives in buffer k & 1 and is that buffer's (k >> 1)-th use.
+      uint32_t gi = 0;     // next use whose first product (S or GEMM1) gets issued
+      uint32_t gw = 0;     // next use whose fp16 operand (P or H) the tokens hand back
+      uint32_t gp = 0, n_sig = 0;
+      auto wait_x = [&]() {
+        mbar_wait(x_ready, n_sig & 1u);
+        ++n_sig;
+        tc_fence_after();
+      };
+      auto wait_h = [&]() -> uint32_t {   // returns the TMEM address of the fp16 operand
+        const uint32_t b = gw & 1u;
+        mbar_wait(h_full(b), (gw >> 1) & 1u);
+        tc_fence_after();
+        ++gw;
+        return tmem_base + b * CH;
+      };
+      for (int s = blockIdx.x; s < n; s += gridDim.x)
+        for (int l = 0; l < n_layers; ++l) {
+          const int stA = gp % NST;
+          mbar_wait(full(stA), (gp / NST) & 1u);
+          tc_fence_after();
+          ++gp;
+          const uint64_t d_wa = umma_desc_sw128(base + OFF_RING + stA * STAGE_BYTES);
+          // ---- QKV ----
+          wait_x();
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            tc_mma_bf16(tmem_base + COL_B, d_t0 + (uint64_t)(2 * k), d_wa + (uint64_t)(2 * k), id_qkv, (uint32_t)(k != 0));
+          tc_commit(done);
+          // ---- attention: S(0), S(1); then per i: PV(i) from the fp16 P the tokens left in acc1[i&1],
+          //      followed by S(i+2) into the same buffer (tcgen05.mma executes in issue order) ----
+          wait_x();
+          auto issue_s = [&](int i) {
+            const int h = i >> 1, j = i & 1;
+            const uint32_t b = gi & 1u;
+            const uint64_t d_k = d_t0 + (uint64_t)(j * 512);       // key rows 64 j ...
+            if (NH == 1) {
+#pragma unroll
+              for (int t = 0; t < 2; ++t)
+                tc_mma_bf16(tmem_base + b * CH, d_q + (uint64_t)(2 * t), d_k + (uint64_t)(2 * t), id_64, (uint32_t)(t != 0));
+            } else {
+              const int p = (h * DH) / 16;
+              tc_mma_bf16(tmem_base + b * CH, d_q + (uint64_t)(2 * h), d_k + (uint64_t)(2 * p), id_64, 0u);
+            }
+            tc_commit(acc1_full(b));
+            ++gi;
+          };
+          issue_s(0);
+          issue_s(1);
+          for (int i = 0; i < NSUB; ++i) {
+            const int h = i >> 1, j = i & 1;
+            const uint32_t a_p = wait_h();
+            const int p = NH == 1 ? 0 : (h * DH) / 16;
+            const uint64_t d_v = umma_desc_sw128(base + OFF_VT + j * 4096 + p * 2048);
+            const uint32_t col = COL_B + (uint32_t)((h * 2 + j) * PV_N);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16_ts(tmem_base + col, a_p + 8u * k, d_v + (uint64_t)(2 * k), id_pv, (uint32_t)(k != 0));
+            if (i + 2 < NSUB) issue_s(i + 2);
+          }
+          tc_commit(done);
+          // ---- output projection ----
+          wait_x();
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            tc_mma_bf16(tmem_base + COL_B, d_t0 + (uint64_t)(4 + 2 * k), d_wa + (uint64_t)(4 + 2 * k), id_32, (uint32_t)(k != 0));
+          tc_commit(done);
+          // ---- feed forward ----
+          wait_x();
+          tc_commit(empty(stA));     // the tokens are done with the layer's parameters
+          const uint32_t gpF = gp;
+          auto issue_g1 = [&](int c) {
+            const uint32_t b = gi & 1u, pair = gpF + (uint32_t)(c >> 1);
+            const int st = pair % NST;
+            if ((c & 1) == 0) {
+              mbar_wait(full(st), (pair / NST) & 1u);
+              tc_fence_after();
+            }
+            const uint64_t d_w1 = umma_desc_sw128(base + OFF_RING + st * STAGE_BYTES) + (uint64_t)(4 * (c & 1));
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              tc_mma_bf16(tmem_base + b * CH, d_t0 + (uint64_t)(4 + 2 * k), d_w1 + (uint64_t)(2 * k), id_64, (uint32_t)(k != 0));
+            tc_commit(acc1_full(b));
+            ++gi;
+          };
+          issue_g1(0);
+          issue_g1(1);
+          for (int c = 0; c < n_chunks; ++c) {
+            const uint32_t a_h = wait_h();
+            const uint32_t pair = gpF + (uint32_t)(c >> 1);
+            const int st = pair % NST;
+            const uint64_t d_w2 = umma_desc_sw128(base + OFF_RING + st * STAGE_BYTES + ST_W2 + (c & 1) * 4096);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16_ts(tmem_base + COL_B, a_h + 8u * k, d_w2 + (uint64_t)(2 * k), id_32, (uint32_t)(c != 0 || k != 0));
+            if (c & 1) tc_commit(empty(st));   // both chunks of the stage have been consumed
+            if (c + 2 < n_chunks) issue_g1(c + 2);
+          }
+          gp += (uint32_t)(n_chunks / 2);
+          tc_commit(done);
+        }
+    }
+  } else {  // ===== token threads =====
+    const int tid = threadIdx.x;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint8_t* t0 = sbase + OFF_T0;
+    const float sm_scale = 1.4426950408889634f / sqrtf((float)DH);   // log2(e) / sqrt(dh)
+    uint32_t g = 0, gp = 0, n_done = 0;
+    auto signal = [&]() {
+      fence_proxy_async();
+      token_sync();
+      if (tid == 0) mbar_arrive(x_ready);
+    };
+    auto wait_done = [&]() {
+      mbar_wait(done, n_done & 1u);
+      ++n_done;
+      tc_fence_after();
+    };
+    for (int s = blockIdx.x; s < n; s += gridDim.x) {
+      float x[D_MODEL];
+      embed_token(W, dirs, s, tid, x);
+      for (int l = 0; l < n_layers; ++l) {
+        const int stA = gp % NST;
+        const uint32_t parA = (gp / NST) & 1u;
+        ++gp;
+        const float* prm = reinterpret_cast<const float*>(sbase + OFF_RING + stA * STAGE_BYTES + ST_PRM);
+        store_row32(t0, tid, 0, x);
+        signal();
+        mbar_wait(full(stA), parA);      // the layer's parameter block has landed
+        wait_done();
+        {  // ---- QKV epilogue: +bias, operand tiles of the attention products ----
+          uint32_t r[32];
+          float f[32];
+          tc_ld32(lane_base + COL_B, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) + prm[P_INB + i];
+          uint8_t* t1 = sbase + OFF_T1;
+          constexpr int NS = NH == 1 ? 2 : NH;
+#pragma unroll
+          for (int t = 0; t < NS; ++t) {
+            const int p = NH == 1 ? t : (t * DH) / 16;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int ch0 = 16 * p + 8 * e;
+              const bool keep = NH == 1 || (ch0 / DH == t);
+              *reinterpret_cast<uint4*>(t1 + sw128_offset(tid, 2 * t + e)) = keep ? pack8(f + ch0) : make_uint4(0, 0, 0, 0);
+            }
+          }
+          tc_ld32(lane_base + COL_B + 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) + prm[P_INB + 32 + i];
+          store_row32(t0, tid, 0, f);     // K over x: the QKV product has retired
+          tc_ld32(lane_base + COL_B + 64, r);
+          tc_wait_ld();
+          tc_fence_before();
+          uint8_t* vt = sbase + OFF_VT + (tid >> 6) * 4096 + (tid & 7) * 2;
+          const int kc = (tid & 63) >> 3;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            *reinterpret_cast<__half*>(vt + sw128_offset(c, kc)) = __float2half_rn(__uint_as_float(r[c]) + prm[P_INB + 64 + c]);
+        }
+        signal();
+        // ---- softmax over the key halves, head by head ----
+        float mx[NSUB], ls[NSUB];
+#pragma unroll
+        for (int i = 0; i < NSUB; ++i, ++g) {
+          const uint32_t b = g & 1u;
+          mbar_wait(acc1_full(b), (g >> 1) & 1u);
+          tc_fence_after();
+          uint32_t v0[32], v1[32];
+          tc_ld32(lane_base + b * CH, v0);
+          tc_ld32(lane_base + b * CH + 32, v1);
+          tc_wait_ld();
+          float m = __uint_as_float(v0[0]);
+#pragma unroll
+          for (int k = 1; k < 32; ++k) m = fmaxf(m, __uint_as_float(v0[k]));
+#pragma unroll
+          for (int k = 0; k < 32; ++k) m = fmaxf(m, __uint_as_float(v1[k]));
+          const float mc = m * sm_scale;
+          float sum = 0.f;
+          uint32_t pk[32];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v0[2 * k]), sm_scale, -mc));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v0[2 * k + 1]), sm_scale, -mc));
+            sum += p0 + p1;
+            __half2 hh = __floats2half2_rn(p0, p1);
+            pk[k] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v1[2 * k]), sm_scale, -mc));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v1[2 * k + 1]), sm_scale, -mc));
+            sum += p0 + p1;
+            __half2 hh = __floats2half2_rn(p0, p1);
+            pk[16 + k] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          mx[i] = m;
+          ls[i] = sum;
+          tc_st32(lane_base + b * CH, pk);      // P (fp16, 64 keys = 32 columns) over S
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h_full(b));
+        }
+        wait_done();
+        {  // ---- attention output: merge the halves, normalise, o (fp16) -> T0 ----
+          float o[D_MODEL];
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            const float m = fmaxf(mx[2 * h], mx[2 * h + 1]);
+            const float wa = fast_exp2((mx[2 * h] - m) * sm_scale), wb = fast_exp2((mx[2 * h + 1] - m) * sm_scale);
+            const float inv = 1.f / (ls[2 * h] * wa + ls[2 * h + 1] * wb);
+            const float ca = wa * inv, cb = wb * inv;
+            if (NH >= 4) {        // DH valid columns inside a 16-column block
+              constexpr int V = DH >= 8 ? 8 : DH;
+              uint32_t a[8], c[8];
+              const uint32_t off = (uint32_t)((h * DH) % 16);
+              tc_ld8(lane_base + COL_B + (2 * h) * PV_N + off, a);
+              tc_ld8(lane_base + COL_B + (2 * h + 1) * PV_N + off, c);
+              tc_wait_ld();
+#pragma unroll
+              for (int e = 0; e < V; ++e) o[h * DH + e] = __uint_as_float(a[e]) * ca + __uint_as_float(c[e]) * cb;
+            } else if (NH == 2) {
+              uint32_t a[16], c[16];
+              tc_ld16(lane_base + COL_B + (2 * h) * PV_N, a);
+              tc_ld16(lane_base + COL_B + (2 * h + 1) * PV_N, c);
+              tc_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[h * 16 + e] = __uint_as_float(a[e]) * ca + __uint_as_float(c[e]) * cb;
+            } else {
+              uint32_t a[32], c[32];
+              tc_ld32(lane_base + COL_B, a);
+              tc_ld32(lane_base + COL_B + 32, c);
+              tc_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __uint_as_float(a[e]) * ca + __uint_as_float(c[e]) * cb;
+            }
+          }
+          tc_fence_before();
+          store_row32(t0, tid, 4, o);
+        }
+        signal();
+        wait_done();
+        {  // ---- out-proj epilogue: +bias, residual, LayerNorm 1, x (fp16) -> T0 ----
+          uint32_t r[32];
+          tc_ld32(lane_base + COL_B, r);
+          tc_wait_ld();
+          tc_fence_before();
+#pragma unroll
+          for (int i = 0; i < D_MODEL; ++i) x[i] += __uint_as_float(r[i]) + prm[P_OUTB + i];
+          layer_norm32_s(x, prm + P_N1W, prm + P_N1B);
+          store_row32(t0, tid, 4, x);
+        }
+        signal();
+        // ---- feed forward ----
+        const uint32_t gpF = gp;
+        const __half2 zero2 = __float2half2_rn(0.f);
+        for (int c = 0; c < n_chunks; ++c, ++g) {
+          const uint32_t b = g & 1u, pair = gpF + (uint32_t)(c >> 1);
+          const int st = pair % NST;
+          if ((c & 1) == 0) mbar_wait(full(st), (pair / NST) & 1u);   // b1 of this chunk pair has landed
+          const float* bb = reinterpret_cast<const float*>(sbase + OFF_RING + st * STAGE_BYTES + ST_B1) + (c & 1) * CH;
+          mbar_wait(acc1_full(b), (g >> 1) & 1u);
+          tc_fence_after();
+          uint32_t v0[32], v1[32];
+          tc_ld32(lane_base + b * CH, v0);
+          tc_ld32(lane_base + b * CH + 32, v1);
+          tc_wait_ld();
+          uint32_t pk[CH / 2];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * j);
+            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1])), make_float2(b4.x, b4.y));
+            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3])), make_float2(b4.z, b4.w));
+            __half2 h0 = __hmax2(__float22half2_rn(s0), zero2), h1 = __hmax2(__float22half2_rn(s1), zero2);
+            pk[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bb + 32 + 4 * j);
+            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1])), make_float2(b4.x, b4.y));
+            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3])), make_float2(b4.z, b4.w));
+            __half2 h0 = __hmax2(__float22half2_rn(s0), zero2), h1 = __hmax2(__float22half2_rn(s1), zero2);
+            pk[16 + 2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[16 + 2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+          tc_st32(lane_base + b * CH, pk);      // H chunk (fp16, 64 units = 32 columns) over the accumulator
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h_full(b));
+        }
+        gp += (uint32_t)(n_chunks / 2);
+        wait_done();
+        {
+          uint32_t o[32];
+          tc_ld32(lane_base + COL_B, o);
+          tc_wait_ld();
+          tc_fence_before();
+#pragma unroll
+          for (int i = 0; i < D_MODEL; ++i) x[i] += __uint_as_float(o[i]) + __ldg(W.lin2_b[l] + i);
+          layer_norm32(x, W.norm2_w[l], W.norm2_b[l]);
+        }
+      }
+      if (tid == 0) score_head(W, x, scores + s);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// fp32 in_proj [96][32] and out_proj [32][32] -> fp16 [L][96][64]: row r = [in_proj_w[r][:] | out_proj_w[r][:] (r < 32)]
+__global__ void pack_oracle_wa_kernel(ttl_oracle_weights W, __half* __restrict__ out) {
+  const int per_layer = 96 * 64;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= per_layer * W.n_layers) return;
+  const int l = t / per_layer, e = t - l * per_layer;
+  const int r = e / 64, c = e - r * 64;
+  float v = 0.f;
+  if (c < 32) v = __ldg(W.in_proj_w[l] + r * D_MODEL + c);
+  else if (r < 32) v = __ldg(W.out_proj_w[l] + r * D_MODEL + (c - 32));
+  out[t] = __float2half_rn(v);
+}
+// per-layer parameter block (tc2::P_*) and a contiguous copy of the linear1 biases
+__global__ void pack_oracle_params_kernel(ttl_oracle_weights W, float* __restrict__ prm, float* __restrict__ b1) {
+  const int l = blockIdx.x;
+  for (int i = threadIdx.x; i < tc2::PRM_FLOATS; i += blockDim.x) {
+    float v;
+    if (i < 96) v = W.in_proj_b[l][i];
+    else if (i < 128) v = W.out_proj_b[l][i - 96];
+    else if (i < 160) v = W.norm1_w[l][i - 128];
+    else if (i < 192) v = W.norm1_b[l][i - 160];
+    else if (i < 224) v = W.lin2_b[l][i - 192];
+    else if (i < 256) v = W.norm2_w[l][i - 224];
+    else v = W.norm2_b[l][i - 256];
+    prm[l * tc2::PRM_FLOATS + i] = v;
+  }
+  for (int i = threadIdx.x; i < W.d_ff; i += blockDim.x) b1[(size_t)l * W.d_ff + i] = W.lin1_b[l][i];
+}
+
 // fp32 [L][d_ff][32] linear1 weights -> fp16 [L][d_ff/2][64]: row 64j+r of a layer holds hidden
 // unit 128j+r in its first 32 columns and unit 128j+64+r in the last 32, so that one 64-row
 // SWIZZLE_128B TMA box carries two consecutive 64-unit chunks as K-offset 0 / 64 B operands.
@@ -605,7 +1115,10 @@ struct ttl_oracle_plan {
   ttl_oracle_weights w;
   __half* w1;            // packed linear1 weights (pack_oracle_w1_kernel)
   __half* w2;            // fp16 linear2 weights
-  CUtensorMap map_w1, map_w2;
+  __half* wa;            // packed in_proj | out_proj weights (pack_oracle_wa_kernel)
+  float* prm;            // per-layer parameter blocks
+  float* b1;             // linear1 biases, contiguous
+  CUtensorMap map_w1, map_w2, map_wa;
 };
 
 extern "C" {
@@ -657,7 +1170,8 @@ int ttl_oracle_forward(const ttl_oracle_weights* w, const float* dirs, int32_t n
 
 int64_t ttl_oracle_workspace_bytes(const ttl_oracle_weights* w) {
   if (!w || w->n_layers < 1 || w->n_layers > 8 || w->d_model != D_MODEL || w->d_ff <= 0) return -1;
-  return (int64_t)2 * w->n_layers * w->d_ff * D_MODEL * 2;   // fp16 copies of linear1 and linear2
+  // fp16 copies of linear1 / linear2, packed attention weights, parameter blocks, linear1 biases
+  return (int64_t)2 * w->n_layers * w->d_ff * D_MODEL * 2 + (int64_t)w->n_layers * (96 * 64 * 2 + 2048 + w->d_ff * 4);
 }
 
 int ttl_oracle_plan_create(ttl_oracle_plan** out, const ttl_oracle_weights* w, void* workspace,
@@ -674,10 +1188,16 @@ int ttl_oracle_plan_create(ttl_oracle_plan** out, const ttl_oracle_weights* w, v
   p->w = *w;
   p->w1 = static_cast<__half*>(workspace);
   p->w2 = p->w1 + (size_t)w->n_layers * w->d_ff * D_MODEL;
+  p->wa = p->w2 + (size_t)w->n_layers * w->d_ff * D_MODEL;
+  p->prm = reinterpret_cast<float*>(p->wa + (size_t)w->n_layers * 96 * 64);
+  p->b1 = p->prm + (size_t)w->n_layers * 512;
   cudaStream_t s = (cudaStream_t)stream;
   const int tot = w->n_layers * w->d_ff * D_MODEL;
   TTL_LAUNCH("pack_oracle_w1_kernel", s, pack_oracle_w1_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(*w, p->w1));
   TTL_LAUNCH("pack_oracle_w2_kernel", s, pack_oracle_w2_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(*w, p->w2));
+  TTL_LAUNCH("pack_oracle_wa_kernel", s,
+             pack_oracle_wa_kernel<<<ttl_div_up(w->n_layers * 96 * 64, 256), 256, 0, s>>>(*w, p->wa));
+  TTL_LAUNCH("pack_oracle_params_kernel", s, pack_oracle_params_kernel<<<w->n_layers, 256, 0, s>>>(*w, p->prm, p->b1));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { delete p; return (int)e; }
   ttl_tc::EncodeTiledFn fn = ttl_tc::get_encode_fn();
@@ -700,6 +1220,15 @@ int ttl_oracle_plan_create(ttl_oracle_plan** out, const ttl_oracle_weights* w, v
            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete p; return TTL_ERR_DRIVER; }
   }
+  {  // in_proj | out_proj [L * 96][64] fp16, box 96 rows x 64 columns
+    cuuint64_t dims[2] = {64, (cuuint64_t)w->n_layers * 96};
+    cuuint64_t strides[1] = {64 * 2};
+    cuuint32_t box[2] = {64, 96};
+    cuuint32_t estr[2] = {1, 1};
+    if (fn(&p->map_wa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->wa, dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete p; return TTL_ERR_DRIVER; }
+  }
   *out = p;
   return 0;
 }
@@ -714,6 +1243,12 @@ int ttl_oracle_forward_tc(ttl_oracle_plan* p, const float* dirs, int32_t n, floa
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(oracle_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tcgen::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(oracle_forward_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(oracle_forward_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(oracle_forward_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -721,9 +1256,28 @@ int ttl_oracle_forward_tc(ttl_oracle_plan* p, const float* dirs, int32_t n, floa
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = n < sms * 2 ? n : sms * 2;
-  TTL_LAUNCH("oracle_forward_tc_kernel", s,
-             oracle_forward_tc_kernel<<<grid, tcgen::THREADS, tcgen::SMEM_BYTES, s>>>(p->w, p->map_w1, p->map_w2,
-                                                                                     dirs, n, scores));
+  static int ffn_only = -1;       // TTL_ORACLE_FFN_ONLY=1: attention on the FP32 pipes (first tensor-core version)
+  if (ffn_only < 0) { const char* e = getenv("TTL_ORACLE_FFN_ONLY"); ffn_only = (e && e[0] == '1') ? 1 : 0; }
+  const int nh = p->w.n_head;
+  if (ffn_only || nh == 8) {
+    // 8 heads of 4 channels do not fit the K = 16 slices of one Q tile: feed-forward blocks on tcgen05,
+    // attention in fp32 on the token threads
+    TTL_LAUNCH("oracle_forward_tc_kernel", s,
+               oracle_forward_tc_kernel<<<grid, tcgen::THREADS, tcgen::SMEM_BYTES, s>>>(p->w, p->map_w1, p->map_w2,
+                                                                                       dirs, n, scores));
+  } else if (nh == 4) {
+    TTL_LAUNCH("oracle_forward_tc2_kernel", s,
+               oracle_forward_tc2_kernel<4><<<grid, tc2::THREADS, tc2::SMEM_BYTES, s>>>(
+                   p->w, p->map_w1, p->map_w2, p->map_wa, p->b1, p->prm, dirs, n, scores));
+  } else if (nh == 2) {
+    TTL_LAUNCH("oracle_forward_tc2_kernel", s,
+               oracle_forward_tc2_kernel<2><<<grid, tc2::THREADS, tc2::SMEM_BYTES, s>>>(
+                   p->w, p->map_w1, p->map_w2, p->map_wa, p->b1, p->prm, dirs, n, scores));
+  } else {
+    TTL_LAUNCH("oracle_forward_tc2_kernel", s,
+               oracle_forward_tc2_kernel<1><<<grid, tc2::THREADS, tc2::SMEM_BYTES, s>>>(
+                   p->w, p->map_w1, p->map_w2, p->map_wa, p->b1, p->prm, dirs, n, scores));
+  }
   TTL_CHECK_LAST();
   return 0;
 }
