@@ -625,6 +625,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// (max(v.x, 0), max(v.y, 0)) -> packed fp16 pair, one F2FP with the .relu modifier
+__device__ __forceinline__ uint32_t pack_relu(float2 v) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v.y), "f"(v.x));
+  return d;
+}
 // 8 consecutive fp32 -> one 16-byte chunk of fp16
 __device__ __forceinline__ uint4 pack8(const float* v) {
   __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
@@ -669,12 +675,16 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
   const uint32_t bar0 = base + OFF_BAR;
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (NST + s); };
-  auto acc1_full = [&](int b) { return bar0 + 8u * (2 * NST + b); };   // MMA -> tokens: S / GEMM1 result
-  auto h_full = [&](int b) { return bar0 + 8u * (2 * NST + 2 + b); };  // tokens -> MMA: fp16 operand in place (4 warps)
-  const uint32_t x_ready = bar0 + 8u * (2 * NST + 4);   // tokens -> MMA: a shared-memory operand tile is complete
-  const uint32_t done = bar0 + 8u * (2 * NST + 5);      // MMA -> tokens: a result is complete in TMEM
-  const uint32_t tmem_slot = bar0 + 8u * (2 * NST + 6);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sbase + OFF_BAR + 8 * (2 * NST + 6));
+  auto acc1_full = [&](uint32_t b) { return bar0 + 8u * (2 * NST + b); };   // MMA -> tokens: S / GEMM1 result
+  auto h_full = [&](uint32_t b) { return bar0 + 8u * (2 * NST + 3 + b); };  // tokens -> MMA: fp16 operand in place (4 warps)
+  const uint32_t x_ready = bar0 + 8u * (2 * NST + 6);   // tokens -> MMA: a shared-memory operand tile is complete
+  const uint32_t done = bar0 + 8u * (2 * NST + 7);      // MMA -> tokens: a result is complete in TMEM
+  const uint32_t tmem_slot = bar0 + 8u * (2 * NST + 8);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sbase + OFF_BAR + 8 * (2 * NST + 8));
+  // acc1 buffers: columns 0, 64 (attention and feed-forward) and 192 (feed-forward only: the upper half
+  // of the shared region is free then), each the fp32 accumulator of a 64-wide product and, after the
+  // tokens' pass, its fp16 version in the first 32 columns.
+  auto acc1_col = [&](uint32_t b) { return b == 2u ? 192u : b * 64u; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_layers = W.n_layers;
@@ -685,7 +695,7 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_w2)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_wa)) : "memory");
     for (int s = 0; s < NST; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc1_full(b), 1); mbar_init(h_full(b), 4); }
+    for (int b = 0; b < 3; ++b) { mbar_init(acc1_full(b), 1); mbar_init(h_full(b), 4); }
     mbar_init(x_ready, 1);
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -703,22 +713,27 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 4) {
-    if (lane == 0) {  // ===== TMA producer: per layer one attention stage, then d_ff/128 feed-forward stages =====
-      uint32_t gp = 0;
-      for (int s = blockIdx.x; s < n; s += gridDim.x)
-        for (int l = 0; l < n_layers; ++l) {
-          {
-            const int st = gp % NST;
-            mbar_wait(empty(st), ((gp / NST) & 1u) ^ 1u);
+    // ===== TMA producer (whole warp, elected lane issues): per layer one attention stage, then d_ff/128
+    //       feed-forward stages =====
+    uint32_t gp = 0;
+    for (int s = blockIdx.x; s < n; s += gridDim.x)
+      for (int l = 0; l < n_layers; ++l) {
+        {
+          const int st = gp % NST;
+          mbar_wait_park(empty(st), ((gp / NST) & 1u) ^ 1u);
+          if (elect_one()) {
             mbar_arrive_expect_tx(full(st), ATT_TX);
             const uint32_t dst = base + OFF_RING + st * STAGE_BYTES;
             tma_load_2d(dst, &tma_wa, full(st), 0, l * 96);
             bulk_load(dst + ST_PRM, prm_all + (size_t)l * PRM_FLOATS, PRM_FLOATS * 4, full(st));
-            ++gp;
           }
-          for (int j = 0; j < n_chunks / 2; ++j, ++gp) {
-            const int st = gp % NST;
-            mbar_wait(empty(st), ((gp / NST) & 1u) ^ 1u);
+          __syncwarp();
+          ++gp;
+        }
+        for (int j = 0; j < n_chunks / 2; ++j, ++gp) {
+          const int st = gp % NST;
+          mbar_wait_park(empty(st), ((gp / NST) & 1u) ^ 1u);
+          if (elect_one()) {
             mbar_arrive_expect_tx(full(st), FFN_TX);
             const uint32_t dst = base + OFF_RING + st * STAGE_BYTES;
             tma_load_2d(dst, &tma_w1, full(st), 0, l * (W.d_ff / 2) + 64 * j);
@@ -726,125 +741,147 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
             tma_load_2d(dst + ST_W2 + 4096, &tma_w2, full(st), 128 * j + 64, l * D_MODEL);
             bulk_load(dst + ST_B1, b1_all + (size_t)l * W.d_ff + 2 * CH * j, 2 * CH * 4, full(st));
           }
+          __syncwarp();
         }
-    }
+      }
   } else if (warp == 5) {
-    if (lane == 0) {  // ===== MMA issuer =====
-      constexpr uint32_t id_qkv = umma_idesc_f16(128, 96, 0);
-      constexpr uint32_t id_64 = umma_idesc_f16(128, 64, 0);
-      constexpr uint32_t id_pv = umma_idesc_f16(128, PV_N, 0);
-      constexpr uint32_t id_32 = umma_idesc_f16(128, 32, 0);
-      const uint64_t d_t0 = umma_desc_sw128(base + OFF_T0);
-      const uint64_t d_q = umma_desc_sw128(base + OFF_T1);
-      // The acc1 buffers are used strictly alternately (0,1,0,1,...) through attention and feed-forward
-      // phases alike; use k lives in buffer k & 1 and is that buffer's (k >> 1)-th use.
-      uint32_t gi = 0;     // next use whose first product (S or GEMM1) gets issued
-      uint32_t gw = 0;     // next use whose fp16 operand (P or H) the tokens hand back
-      uint32_t gp = 0, n_sig = 0;
-      auto wait_x = [&]() {
-        mbar_wait(x_ready, n_sig & 1u);
-        ++n_sig;
+    // ===== MMA issuer (whole warp runs the loop and the waits; the elected lane issues) =====
+    constexpr uint32_t id_qkv = umma_idesc_f16(128, 96, 0);
+    constexpr uint32_t id_64 = umma_idesc_f16(128, 64, 0);
+    constexpr uint32_t id_pv = umma_idesc_f16(128, PV_N, 0);
+    constexpr uint32_t id_32 = umma_idesc_f16(128, 32, 0);
+    const uint64_t d_t0 = umma_desc_sw128(base + OFF_T0);
+    const uint64_t d_q = umma_desc_sw128(base + OFF_T1);
+    const uint64_t d_ring = umma_desc_sw128(base + OFF_RING);
+    const uint64_t d_vt = umma_desc_sw128(base + OFF_VT);
+    uint32_t par_h = 0;  // bit b: parity of the next h_full[b] completion
+    uint32_t gp = 0, n_sig = 0;
+    auto wait_x = [&]() {
+      mbar_wait(x_ready, n_sig & 1u);
+      ++n_sig;
+      tc_fence_after();
+    };
+    auto wait_h = [&](uint32_t b) {
+      mbar_wait(h_full(b), (par_h >> b) & 1u);
+      par_h ^= 1u << b;
+      tc_fence_after();
+    };
+    // S(i) = Q_h . K_j^T into acc1[j]   (i = 2 h + j)
+    auto issue_s = [&](int i) {
+      const int h = i >> 1, j = i & 1;
+      const uint64_t d_k = d_t0 + (uint64_t)(j * 512);       // key rows 64 j ...
+      if (NH == 1) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+          tc_mma_bf16(tmem_base + j * CH, d_q + (uint64_t)(2 * t), d_k + (uint64_t)(2 * t), id_64, (uint32_t)(t != 0));
+      } else {
+        const int p = (h * DH) / 16;
+        tc_mma_bf16(tmem_base + j * CH, d_q + (uint64_t)(2 * h), d_k + (uint64_t)(2 * p), id_64, 0u);
+      }
+      tc_commit(acc1_full(j));
+    };
+    for (int s = blockIdx.x; s < n; s += gridDim.x)
+      for (int l = 0; l < n_layers; ++l) {
+        const int stA = gp % NST;
+        mbar_wait(full(stA), (gp / NST) & 1u);
         tc_fence_after();
-      };
-      auto wait_h = [&]() -> uint32_t {   // returns the TMEM address of the fp16 operand
-        const uint32_t b = gw & 1u;
-        mbar_wait(h_full(b), (gw >> 1) & 1u);
-        tc_fence_after();
-        ++gw;
-        return tmem_base + b * CH;
-      };
-      for (int s = blockIdx.x; s < n; s += gridDim.x)
-        for (int l = 0; l < n_layers; ++l) {
-          const int stA = gp % NST;
-          mbar_wait(full(stA), (gp / NST) & 1u);
-          tc_fence_after();
-          ++gp;
-          const uint64_t d_wa = umma_desc_sw128(base + OFF_RING + stA * STAGE_BYTES);
-          // ---- QKV ----
-          wait_x();
+        ++gp;
+        const uint64_t d_wa = d_ring + (uint64_t)((stA * STAGE_BYTES) >> 4);
+        // ---- QKV ----
+        wait_x();
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             tc_mma_bf16(tmem_base + COL_B, d_t0 + (uint64_t)(2 * k), d_wa + (uint64_t)(2 * k), id_qkv, (uint32_t)(k != 0));
           tc_commit(done);
-          // ---- attention: S(0), S(1); then per i: PV(i) from the fp16 P the tokens left in acc1[i&1],
-          //      followed by S(i+2) into the same buffer (tcgen05.mma executes in issue order) ----
-          wait_x();
-          auto issue_s = [&](int i) {
-            const int h = i >> 1, j = i & 1;
-            const uint32_t b = gi & 1u;
-            const uint64_t d_k = d_t0 + (uint64_t)(j * 512);       // key rows 64 j ...
-            if (NH == 1) {
-#pragma unroll
-              for (int t = 0; t < 2; ++t)
-                tc_mma_bf16(tmem_base + b * CH, d_q + (uint64_t)(2 * t), d_k + (uint64_t)(2 * t), id_64, (uint32_t)(t != 0));
-            } else {
-              const int p = (h * DH) / 16;
-              tc_mma_bf16(tmem_base + b * CH, d_q + (uint64_t)(2 * h), d_k + (uint64_t)(2 * p), id_64, 0u);
-            }
-            tc_commit(acc1_full(b));
-            ++gi;
-          };
+        }
+        __syncwarp();
+        // ---- attention: S(0), S(1); then per i: PV(i) from the fp16 P the tokens left in acc1[i&1],
+        //      followed by S(i+2) into the same buffer (tcgen05.mma executes in issue order) ----
+        wait_x();
+        if (elect_one()) {
           issue_s(0);
           issue_s(1);
-          for (int i = 0; i < NSUB; ++i) {
-            const int h = i >> 1, j = i & 1;
-            const uint32_t a_p = wait_h();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NSUB; ++i) {
+          const int h = i >> 1, j = i & 1;
+          wait_h((uint32_t)j);
+          if (elect_one()) {
             const int p = NH == 1 ? 0 : (h * DH) / 16;
-            const uint64_t d_v = umma_desc_sw128(base + OFF_VT + j * 4096 + p * 2048);
+            const uint64_t d_v = d_vt + (uint64_t)((j * 4096 + p * 2048) >> 4);
             const uint32_t col = COL_B + (uint32_t)((h * 2 + j) * PV_N);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc_mma_f16_ts(tmem_base + col, a_p + 8u * k, d_v + (uint64_t)(2 * k), id_pv, (uint32_t)(k != 0));
+              tc_mma_f16_ts(tmem_base + col, tmem_base + j * CH + 8u * k, d_v + (uint64_t)(2 * k), id_pv, (uint32_t)(k != 0));
             if (i + 2 < NSUB) issue_s(i + 2);
+            if (i == NSUB - 1) tc_commit(done);
           }
-          tc_commit(done);
-          // ---- output projection ----
-          wait_x();
+          __syncwarp();
+        }
+        // ---- output projection ----
+        wait_x();
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             tc_mma_bf16(tmem_base + COL_B, d_t0 + (uint64_t)(4 + 2 * k), d_wa + (uint64_t)(4 + 2 * k), id_32, (uint32_t)(k != 0));
           tc_commit(done);
-          // ---- feed forward ----
-          wait_x();
-          tc_commit(empty(stA));     // the tokens are done with the layer's parameters
-          const uint32_t gpF = gp;
-          auto issue_g1 = [&](int c) {
-            const uint32_t b = gi & 1u, pair = gpF + (uint32_t)(c >> 1);
-            const int st = pair % NST;
-            if ((c & 1) == 0) {
-              mbar_wait(full(st), (pair / NST) & 1u);
-              tc_fence_after();
-            }
-            const uint64_t d_w1 = umma_desc_sw128(base + OFF_RING + st * STAGE_BYTES) + (uint64_t)(4 * (c & 1));
+        }
+        __syncwarp();
+        // ---- feed forward ----
+        wait_x();
+        const uint32_t gpF = gp;
+        // GEMM1(c) = x . W1_c^T into acc1[b]; the caller has waited for the stage of chunk c
+        auto issue_g1 = [&](int c, uint32_t b) {
+          const uint32_t st = (gpF + (uint32_t)(c >> 1)) % NST;
+          const uint64_t d_w1 = d_ring + (uint64_t)((st * STAGE_BYTES) >> 4) + (uint64_t)(4 * (c & 1));
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-              tc_mma_bf16(tmem_base + b * CH, d_t0 + (uint64_t)(4 + 2 * k), d_w1 + (uint64_t)(2 * k), id_64, (uint32_t)(k != 0));
-            tc_commit(acc1_full(b));
-            ++gi;
-          };
-          issue_g1(0);
-          issue_g1(1);
-          for (int c = 0; c < n_chunks; ++c) {
-            const uint32_t a_h = wait_h();
-            const uint32_t pair = gpF + (uint32_t)(c >> 1);
-            const int st = pair % NST;
-            const uint64_t d_w2 = umma_desc_sw128(base + OFF_RING + st * STAGE_BYTES + ST_W2 + (c & 1) * 4096);
+          for (int k = 0; k < 2; ++k)
+            tc_mma_bf16(tmem_base + acc1_col(b), d_t0 + (uint64_t)(4 + 2 * k), d_w1 + (uint64_t)(2 * k), id_64, (uint32_t)(k != 0));
+          tc_commit(acc1_full(b));
+        };
+        auto wait_stage = [&](int c) {   // first chunk of a pair: its weights must have landed
+          const uint32_t pair = gpF + (uint32_t)(c >> 1);
+          mbar_wait(full(pair % NST), (pair / NST) & 1u);
+          tc_fence_after();
+        };
+        wait_stage(0);
+        wait_stage(2);
+        if (elect_one()) {
+          tc_commit(empty(stA));     // the tokens are done with the layer's parameters
+          issue_g1(0, 0u);
+          issue_g1(1, 1u);
+          issue_g1(2, 2u);
+        }
+        __syncwarp();
+        uint32_t fb = 0;     // buffer of chunk c = c % 3
+        for (int c = 0; c < n_chunks; ++c) {
+          if (c + 3 < n_chunks && ((c + 3) & 1) == 0) wait_stage(c + 3);
+          wait_h(fb);
+          if (elect_one()) {
+            const uint32_t st = (gpF + (uint32_t)(c >> 1)) % NST;
+            const uint64_t d_w2 = d_ring + (uint64_t)((st * STAGE_BYTES + ST_W2 + (c & 1) * 4096) >> 4);
+            const uint32_t a_h = tmem_base + acc1_col(fb);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               tc_mma_f16_ts(tmem_base + COL_B, a_h + 8u * k, d_w2 + (uint64_t)(2 * k), id_32, (uint32_t)(c != 0 || k != 0));
             if (c & 1) tc_commit(empty(st));   // both chunks of the stage have been consumed
-            if (c + 2 < n_chunks) issue_g1(c + 2);
+            if (c + 3 < n_chunks) issue_g1(c + 3, fb);
+            if (c == n_chunks - 1) tc_commit(done);
           }
-          gp += (uint32_t)(n_chunks / 2);
-          tc_commit(done);
+          __syncwarp();
+          fb = fb == 2u ? 0u : fb + 1u;
         }
-    }
+        gp += (uint32_t)(n_chunks / 2);
+      }
   } else {  // ===== token threads =====
     const int tid = threadIdx.x;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint8_t* t0 = sbase + OFF_T0;
     const float sm_scale = 1.4426950408889634f / sqrtf((float)DH);   // log2(e) / sqrt(dh)
-    uint32_t g = 0, gp = 0, n_done = 0;
+    uint32_t par_a = 0;  // bit b: parity of the next acc1_full[b] completion
+    uint32_t gp = 0, n_done = 0;
     auto signal = [&]() {
       fence_proxy_async();
       token_sync();
@@ -904,38 +941,38 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
         // ---- softmax over the key halves, head by head ----
         float mx[NSUB], ls[NSUB];
 #pragma unroll
-        for (int i = 0; i < NSUB; ++i, ++g) {
-          const uint32_t b = g & 1u;
-          mbar_wait(acc1_full(b), (g >> 1) & 1u);
+        for (int i = 0; i < NSUB; ++i) {
+          const uint32_t b = (uint32_t)(i & 1);
+          mbar_wait(acc1_full(b), (par_a >> b) & 1u);
+          par_a ^= 1u << b;
           tc_fence_after();
           uint32_t v0[32], v1[32];
           tc_ld32(lane_base + b * CH, v0);
           tc_ld32(lane_base + b * CH + 32, v1);
           tc_wait_ld();
-          float m = __uint_as_float(v0[0]);
+          float m = fmaxf(__uint_as_float(v0[0]), __uint_as_float(v1[0]));
 #pragma unroll
-          for (int k = 1; k < 32; ++k) m = fmaxf(m, __uint_as_float(v0[k]));
-#pragma unroll
-          for (int k = 0; k < 32; ++k) m = fmaxf(m, __uint_as_float(v1[k]));
-          const float mc = m * sm_scale;
-          float sum = 0.f;
+          for (int k = 1; k < 32; ++k) m = fmaxf(m, fmaxf(__uint_as_float(v0[k]), __uint_as_float(v1[k])));
+          const float2 sc2 = make_float2(sm_scale, sm_scale), mc2 = make_float2(-m * sm_scale, -m * sm_scale);
+          float2 sum2 = make_float2(0.f, 0.f);
           uint32_t pk[32];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v0[2 * k]), sm_scale, -mc));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v0[2 * k + 1]), sm_scale, -mc));
-            sum += p0 + p1;
-            __half2 hh = __floats2half2_rn(p0, p1);
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(v0[2 * k]), __uint_as_float(v0[2 * k + 1])), sc2, mc2);
+            const float2 pp = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+            sum2 = __fadd2_rn(sum2, pp);
+            __half2 hh = __float22half2_rn(pp);
             pk[k] = *reinterpret_cast<uint32_t*>(&hh);
           }
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v1[2 * k]), sm_scale, -mc));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v1[2 * k + 1]), sm_scale, -mc));
-            sum += p0 + p1;
-            __half2 hh = __floats2half2_rn(p0, p1);
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(v1[2 * k]), __uint_as_float(v1[2 * k + 1])), sc2, mc2);
+            const float2 pp = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+            sum2 = __fadd2_rn(sum2, pp);
+            __half2 hh = __float22half2_rn(pp);
             pk[16 + k] = *reinterpret_cast<uint32_t*>(&hh);
           }
+          const float sum = sum2.x + sum2.y;
           mx[i] = m;
           ls[i] = sum;
           tc_st32(lane_base + b * CH, pk);      // P (fp16, 64 keys = 32 columns) over S
@@ -996,17 +1033,20 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
         signal();
         // ---- feed forward ----
         const uint32_t gpF = gp;
-        const __half2 zero2 = __float2half2_rn(0.f);
-        for (int c = 0; c < n_chunks; ++c, ++g) {
-          const uint32_t b = g & 1u, pair = gpF + (uint32_t)(c >> 1);
+        uint32_t fb = 0;       // buffer of chunk c = c % 3
+        for (int c = 0; c < n_chunks; ++c) {
+          const uint32_t b = fb, pair = gpF + (uint32_t)(c >> 1);
+          fb = fb == 2u ? 0u : fb + 1u;
           const int st = pair % NST;
           if ((c & 1) == 0) mbar_wait(full(st), (pair / NST) & 1u);   // b1 of this chunk pair has landed
           const float* bb = reinterpret_cast<const float*>(sbase + OFF_RING + st * STAGE_BYTES + ST_B1) + (c & 1) * CH;
-          mbar_wait(acc1_full(b), (g >> 1) & 1u);
+          mbar_wait(acc1_full(b), (par_a >> b) & 1u);
+          par_a ^= 1u << b;
           tc_fence_after();
+          const uint32_t col = acc1_col(b);
           uint32_t v0[32], v1[32];
-          tc_ld32(lane_base + b * CH, v0);
-          tc_ld32(lane_base + b * CH + 32, v1);
+          tc_ld32(lane_base + col, v0);
+          tc_ld32(lane_base + col + 32, v1);
           tc_wait_ld();
           uint32_t pk[CH / 2];
 #pragma unroll
@@ -1014,20 +1054,18 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
             const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * j);
             const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1])), make_float2(b4.x, b4.y));
             const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3])), make_float2(b4.z, b4.w));
-            __half2 h0 = __hmax2(__float22half2_rn(s0), zero2), h1 = __hmax2(__float22half2_rn(s1), zero2);
-            pk[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
-            pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            pk[2 * j] = pack_relu(s0);
+            pk[2 * j + 1] = pack_relu(s1);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = *reinterpret_cast<const float4*>(bb + 32 + 4 * j);
             const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1])), make_float2(b4.x, b4.y));
             const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3])), make_float2(b4.z, b4.w));
-            __half2 h0 = __hmax2(__float22half2_rn(s0), zero2), h1 = __hmax2(__float22half2_rn(s1), zero2);
-            pk[16 + 2 * j] = *reinterpret_cast<uint32_t*>(&h0);
-            pk[16 + 2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            pk[16 + 2 * j] = pack_relu(s0);
+            pk[16 + 2 * j + 1] = pack_relu(s1);
           }
-          tc_st32(lane_base + b * CH, pk);      // H chunk (fp16, 64 units = 32 columns) over the accumulator
+          tc_st32(lane_base + col, pk);         // H chunk (fp16, 64 units = 32 columns) over the accumulator
           tc_wait_st();
           tc_fence_before();
           __syncwarp();

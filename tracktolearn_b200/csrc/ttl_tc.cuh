@@ -23,25 +23,50 @@ static __device__ __forceinline__ uint64_t global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// PARK: pass a suspend-time hint so that the hardware parks the thread instead of spinning -- for
+// threads that run far ahead (TMA producers); latency-critical waits spin.
+template <bool PARK>
+static __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   uint64_t t0 = 0;
 #pragma unroll 1
   for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: park the thread instead of spinning
-        : "memory");
+    if (PARK) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity), "r"(0x989680u)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
     if (done) return;
-    if ((it & 15u) == 15u) {
+    if ((it & (PARK ? 15u : 1023u)) == (PARK ? 15u : 1023u)) {
       const uint64_t now = global_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 2000000000ull) __trap();   // 2 s
     }
   }
+}
+static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_t<false>(bar, parity); }
+static __device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) { mbar_wait_t<true>(bar, parity); }
+// Leader election for warp-uniform issue of tcgen05 / TMA instructions.  The whole warp runs the
+// issue loop convergently and only the elected lane executes the instruction: ptxas then keeps the
+// descriptors in uniform registers and emits back-to-back UTCHMMA; an `if (lane == 0)` region
+// instead makes it wrap every instruction in an ELECT / BRA.U.ANY loop (measured: ~60 % of the
+// issuing thread's time for 16-cycle MMAs).
+static __device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
 }
 static __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1) {
