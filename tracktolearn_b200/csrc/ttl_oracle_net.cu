@@ -591,26 +591,28 @@ oracle_forward_tc_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensorM
 //   tokens   combine the two halves (each was scaled by its own row max), 1/sum, o (fp16) -> T0
 //   out-proj [128x32].[32x32]                                                  -> TMEM 128..159
 //   tokens   +bias, residual, LayerNorm 1, x (fp16) -> T0
-//   FFN      per 64-wide chunk c: acc1[c&1] = x . W1_c^T; tokens: +b1, ReLU, fp16 in place;
-//            acc2 += H_c . W2_c^T with H_c read from tensor memory       -> TMEM 128..159
+//   FFN      per 64-wide chunk c: acc1[c%3] = [x | 1 1 0..] . [W1_c | b1_hi b1_lo 0..]^T (the bias rides
+//            in a third K=16 slice as an fp16 hi+lo pair); tokens: ReLU + fp16 in place (one F2FP.RELU
+//            per two units); acc2 += H_c . W2_c^T with H_c read from tensor memory -> TMEM 128..159
 //   tokens   +bias, residual, LayerNorm 2
 // The hidden activations and the attention probabilities never touch shared memory: the token
 // threads read the fp32 accumulator with tcgen05.ld and write the fp16 operand of the next product
 // back over it with tcgen05.st, so one chunk costs two mbarrier hand-offs and no proxy fence.
 // Shared memory per CTA (two CTAs per SM): T0 16 KB [x or K | o or x'], T1 16 KB Q slices, VT 8 KB,
-// weight ring 4 x 17 KB.  TMEM: 256 columns (acc1 2 x 64 | 128 shared by QKV, O, out-proj, acc2).
+// 4 KB constant [1 1 0..] operand, weight ring 3 x 20 KB.  TMEM: 256 columns (acc1 2 x 64 | 128 shared by QKV, O, out-proj, acc2).
 namespace tc2 {
 using namespace ttl_tc;
 constexpr int CH = 64;
-constexpr int NST = 4;
-constexpr int STAGE_BYTES = 17408;
-constexpr int ST_W2 = 8192, ST_B1 = 16384;      // inside a feed-forward stage
+constexpr int NST = 3;
+constexpr int STAGE_BYTES = 20480;
+constexpr int ST_W2 = 8192, ST_AUG = 16384;     // inside a feed-forward stage
+constexpr int AUG_PAIR_BYTES = 4096;            // bias operand tiles of one chunk pair (2 x [64 units x K16], no swizzle)
 constexpr int ST_PRM = 12288;                   // inside an attention stage
 constexpr int PRM_FLOATS = 288;                 // in_proj_b 96 | out_proj_b 32 | norm1_w 32 | norm1_b 32 | lin2_b | norm2_w | norm2_b
 constexpr int P_INB = 0, P_OUTB = 96, P_N1W = 128, P_N1B = 160, P_L2B = 192, P_N2W = 224, P_N2B = 256;
-constexpr uint32_t FFN_TX = 16384 + 2 * CH * 4;
+constexpr uint32_t FFN_TX = 16384 + AUG_PAIR_BYTES;
 constexpr uint32_t ATT_TX = 12288 + PRM_FLOATS * 4;
-constexpr int OFF_T0 = 0, OFF_T1 = 16384, OFF_VT = 32768, OFF_RING = 40960;
+constexpr int OFF_T0 = 0, OFF_T1 = 16384, OFF_VT = 32768, OFF_ONES = 40960, OFF_RING = 45056;
 constexpr int OFF_BAR = OFF_RING + NST * STAGE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 192;
@@ -662,7 +664,7 @@ template <int NH>
 __global__ void __launch_bounds__(tc2::THREADS, 2)
 oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensorMap tma_w1,
                           const __grid_constant__ CUtensorMap tma_w2, const __grid_constant__ CUtensorMap tma_wa,
-                          const float* __restrict__ b1_all, const float* __restrict__ prm_all,
+                          const uint8_t* __restrict__ aug_all, const float* __restrict__ prm_all,
                           const float* __restrict__ dirs, int n, float* __restrict__ scores) {
   using namespace tc2;
   constexpr int DH = D_MODEL / NH;
@@ -707,6 +709,12 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp < 4) {   // constant A-side slice of the bias trick: row t = [1 1 0 ...] (K = 16, no swizzle)
+    uint8_t* ones = sbase + OFF_ONES + (threadIdx.x >> 3) * 256 + (threadIdx.x & 7) * 16;
+    *reinterpret_cast<uint4*>(ones) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(ones + 128) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -739,7 +747,7 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
             tma_load_2d(dst, &tma_w1, full(st), 0, l * (W.d_ff / 2) + 64 * j);
             tma_load_2d(dst + ST_W2, &tma_w2, full(st), 128 * j, l * D_MODEL);
             tma_load_2d(dst + ST_W2 + 4096, &tma_w2, full(st), 128 * j + 64, l * D_MODEL);
-            bulk_load(dst + ST_B1, b1_all + (size_t)l * W.d_ff + 2 * CH * j, 2 * CH * 4, full(st));
+            bulk_load(dst + ST_AUG, aug_all + ((size_t)l * (n_chunks / 2) + j) * AUG_PAIR_BYTES, AUG_PAIR_BYTES, full(st));
           }
           __syncwarp();
         }
@@ -754,6 +762,7 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
     const uint64_t d_q = umma_desc_sw128(base + OFF_T1);
     const uint64_t d_ring = umma_desc_sw128(base + OFF_RING);
     const uint64_t d_vt = umma_desc_sw128(base + OFF_VT);
+    const uint64_t d_ones = umma_desc_noswz(base + OFF_ONES, 128, 256);
     uint32_t par_h = 0;  // bit b: parity of the next h_full[b] completion
     uint32_t gp = 0, n_sig = 0;
     auto wait_x = [&]() {
@@ -839,6 +848,9 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             tc_mma_bf16(tmem_base + acc1_col(b), d_t0 + (uint64_t)(4 + 2 * k), d_w1 + (uint64_t)(2 * k), id_64, (uint32_t)(k != 0));
+          tc_mma_bf16(tmem_base + acc1_col(b), d_ones,
+                      umma_desc_noswz(base + OFF_RING + st * STAGE_BYTES + ST_AUG + (c & 1) * (AUG_PAIR_BYTES / 2), 128, 256),
+                      id_64, 1u);     // + b1
           tc_commit(acc1_full(b));
         };
         auto wait_stage = [&](int c) {   // first chunk of a pair: its weights must have landed
@@ -1032,14 +1044,10 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
         }
         signal();
         // ---- feed forward ----
-        const uint32_t gpF = gp;
         uint32_t fb = 0;       // buffer of chunk c = c % 3
         for (int c = 0; c < n_chunks; ++c) {
-          const uint32_t b = fb, pair = gpF + (uint32_t)(c >> 1);
+          const uint32_t b = fb;
           fb = fb == 2u ? 0u : fb + 1u;
-          const int st = pair % NST;
-          if ((c & 1) == 0) mbar_wait(full(st), (pair / NST) & 1u);   // b1 of this chunk pair has landed
-          const float* bb = reinterpret_cast<const float*>(sbase + OFF_RING + st * STAGE_BYTES + ST_B1) + (c & 1) * CH;
           mbar_wait(acc1_full(b), (par_a >> b) & 1u);
           par_a ^= 1u << b;
           tc_fence_after();
@@ -1050,21 +1058,9 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
           tc_wait_ld();
           uint32_t pk[CH / 2];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * j);
-            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1])), make_float2(b4.x, b4.y));
-            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3])), make_float2(b4.z, b4.w));
-            pk[2 * j] = pack_relu(s0);
-            pk[2 * j + 1] = pack_relu(s1);
-          }
+          for (int j = 0; j < 16; ++j) pk[j] = pack_relu(make_float2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1])));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bb + 32 + 4 * j);
-            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1])), make_float2(b4.x, b4.y));
-            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3])), make_float2(b4.z, b4.w));
-            pk[16 + 2 * j] = pack_relu(s0);
-            pk[16 + 2 * j + 1] = pack_relu(s1);
-          }
+          for (int j = 0; j < 16; ++j) pk[16 + j] = pack_relu(make_float2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1])));
           tc_st32(lane_base + col, pk);         // H chunk (fp16, 64 units = 32 columns) over the accumulator
           tc_wait_st();
           tc_fence_before();
@@ -1108,8 +1104,10 @@ __global__ void pack_oracle_wa_kernel(ttl_oracle_weights W, __half* __restrict__
   else if (r < 32) v = __ldg(W.out_proj_w[l] + r * D_MODEL + (c - 32));
   out[t] = __float2half_rn(v);
 }
-// per-layer parameter block (tc2::P_*) and a contiguous copy of the linear1 biases
-__global__ void pack_oracle_params_kernel(ttl_oracle_weights W, float* __restrict__ prm, float* __restrict__ b1) {
+// per-layer parameter block (tc2::P_*) and the linear1 biases as B-operand tiles of the bias slice:
+// per chunk of 64 units a [64 x K16] fp16 tile in the no-swizzle core-matrix layout, unit n =
+// [hi(b1), lo(b1), 0 ...] with hi + lo = b1 to ~22 bits
+__global__ void pack_oracle_params_kernel(ttl_oracle_weights W, float* __restrict__ prm, uint8_t* __restrict__ aug) {
   const int l = blockIdx.x;
   for (int i = threadIdx.x; i < tc2::PRM_FLOATS; i += blockDim.x) {
     float v;
@@ -1122,7 +1120,16 @@ __global__ void pack_oracle_params_kernel(ttl_oracle_weights W, float* __restric
     else v = W.norm2_b[l][i - 256];
     prm[l * tc2::PRM_FLOATS + i] = v;
   }
-  for (int i = threadIdx.x; i < W.d_ff; i += blockDim.x) b1[(size_t)l * W.d_ff + i] = W.lin1_b[l][i];
+  for (int u = threadIdx.x; u < W.d_ff; u += blockDim.x) {
+    const float bv = W.lin1_b[l][u];
+    const __half hi = __float2half_rn(bv);
+    const __half lo = __float2half_rn(bv - __half2float(hi));
+    const int chunk = u / 64, r = u % 64;
+    uint8_t* t = aug + ((size_t)l * (W.d_ff / 64) + chunk) * 2048 + (r / 8) * 256 + (r % 8) * 16;
+    __half2 hl = __halves2half2(hi, lo);
+    *reinterpret_cast<uint4*>(t) = make_uint4(*reinterpret_cast<uint32_t*>(&hl), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(t + 128) = make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 // fp32 [L][d_ff][32] linear1 weights -> fp16 [L][d_ff/2][64]: row 64j+r of a layer holds hidden
@@ -1155,7 +1162,7 @@ struct ttl_oracle_plan {
   __half* w2;            // fp16 linear2 weights
   __half* wa;            // packed in_proj | out_proj weights (pack_oracle_wa_kernel)
   float* prm;            // per-layer parameter blocks
-  float* b1;             // linear1 biases, contiguous
+  uint8_t* aug;          // linear1 biases as bias-slice operand tiles (pack_oracle_params_kernel)
   CUtensorMap map_w1, map_w2, map_wa;
 };
 
@@ -1209,7 +1216,7 @@ int ttl_oracle_forward(const ttl_oracle_weights* w, const float* dirs, int32_t n
 int64_t ttl_oracle_workspace_bytes(const ttl_oracle_weights* w) {
   if (!w || w->n_layers < 1 || w->n_layers > 8 || w->d_model != D_MODEL || w->d_ff <= 0) return -1;
   // fp16 copies of linear1 / linear2, packed attention weights, parameter blocks, linear1 biases
-  return (int64_t)2 * w->n_layers * w->d_ff * D_MODEL * 2 + (int64_t)w->n_layers * (96 * 64 * 2 + 2048 + w->d_ff * 4);
+  return (int64_t)2 * w->n_layers * w->d_ff * D_MODEL * 2 + (int64_t)w->n_layers * (96 * 64 * 2 + 2048 + w->d_ff * 32);
 }
 
 int ttl_oracle_plan_create(ttl_oracle_plan** out, const ttl_oracle_weights* w, void* workspace,
@@ -1228,14 +1235,14 @@ int ttl_oracle_plan_create(ttl_oracle_plan** out, const ttl_oracle_weights* w, v
   p->w2 = p->w1 + (size_t)w->n_layers * w->d_ff * D_MODEL;
   p->wa = p->w2 + (size_t)w->n_layers * w->d_ff * D_MODEL;
   p->prm = reinterpret_cast<float*>(p->wa + (size_t)w->n_layers * 96 * 64);
-  p->b1 = p->prm + (size_t)w->n_layers * 512;
+  p->aug = reinterpret_cast<uint8_t*>(p->prm + (size_t)w->n_layers * 512);
   cudaStream_t s = (cudaStream_t)stream;
   const int tot = w->n_layers * w->d_ff * D_MODEL;
   TTL_LAUNCH("pack_oracle_w1_kernel", s, pack_oracle_w1_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(*w, p->w1));
   TTL_LAUNCH("pack_oracle_w2_kernel", s, pack_oracle_w2_kernel<<<ttl_div_up(tot, 256), 256, 0, s>>>(*w, p->w2));
   TTL_LAUNCH("pack_oracle_wa_kernel", s,
              pack_oracle_wa_kernel<<<ttl_div_up(w->n_layers * 96 * 64, 256), 256, 0, s>>>(*w, p->wa));
-  TTL_LAUNCH("pack_oracle_params_kernel", s, pack_oracle_params_kernel<<<w->n_layers, 256, 0, s>>>(*w, p->prm, p->b1));
+  TTL_LAUNCH("pack_oracle_params_kernel", s, pack_oracle_params_kernel<<<w->n_layers, 256, 0, s>>>(*w, p->prm, p->aug));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { delete p; return (int)e; }
   ttl_tc::EncodeTiledFn fn = ttl_tc::get_encode_fn();
@@ -1306,15 +1313,15 @@ int ttl_oracle_forward_tc(ttl_oracle_plan* p, const float* dirs, int32_t n, floa
   } else if (nh == 4) {
     TTL_LAUNCH("oracle_forward_tc2_kernel", s,
                oracle_forward_tc2_kernel<4><<<grid, tc2::THREADS, tc2::SMEM_BYTES, s>>>(
-                   p->w, p->map_w1, p->map_w2, p->map_wa, p->b1, p->prm, dirs, n, scores));
+                   p->w, p->map_w1, p->map_w2, p->map_wa, p->aug, p->prm, dirs, n, scores));
   } else if (nh == 2) {
     TTL_LAUNCH("oracle_forward_tc2_kernel", s,
                oracle_forward_tc2_kernel<2><<<grid, tc2::THREADS, tc2::SMEM_BYTES, s>>>(
-                   p->w, p->map_w1, p->map_w2, p->map_wa, p->b1, p->prm, dirs, n, scores));
+                   p->w, p->map_w1, p->map_w2, p->map_wa, p->aug, p->prm, dirs, n, scores));
   } else {
     TTL_LAUNCH("oracle_forward_tc2_kernel", s,
                oracle_forward_tc2_kernel<1><<<grid, tc2::THREADS, tc2::SMEM_BYTES, s>>>(
-                   p->w, p->map_w1, p->map_w2, p->map_wa, p->b1, p->prm, dirs, n, scores));
+                   p->w, p->map_w1, p->map_w2, p->map_wa, p->aug, p->prm, dirs, n, scores));
   }
   TTL_CHECK_LAST();
   return 0;

@@ -169,6 +169,18 @@ static __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// K-major operand tile WITHOUT swizzle: 8-row x 16-byte core matrices stored contiguously (128 B);
+// `lbo` = byte distance between the core matrices of consecutive 16-byte K chunks, `sbo` = byte
+// distance between consecutive 8-row groups.  Element (r, k) of a 16-bit tile sits at
+// (r / 8) * sbo + (r % 8) * 16 + (k / 8) * lbo + (k % 8) * 2.
+static __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // Byte offset of 16-byte chunk `c` of row `r` inside such a tile.
 static __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
