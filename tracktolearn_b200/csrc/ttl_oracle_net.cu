@@ -6,7 +6,7 @@
 // positional encoding, n_layers post-norm nn.TransformerEncoderLayer(d=32, n_head, ff=2048, relu),
 // sigmoid(Linear(32,1)) of token 0).
 //
-//   oracle_features_kernel  one thread per streamline, the exact sequential algorithm of dipy's
+//   oracle_features_kernel  one warp per streamline, bit-identical to the sequential algorithm of dipy's
 //                           c_set_number_of_points (segment differences in float, arc lengths and
 //                           interpolation in double) fused with the np.diff: no host resampling.
 //   oracle_forward_kernel   one CTA per streamline, one thread per token (128).  The residual
@@ -101,22 +101,111 @@ __device__ void resample_and_diff(const float* __restrict__ P, int N, float* __r
   D[3 * (kOraclePts - 2) + 2] = __fsub_rn(P[3 * (N - 1) + 2], res126[2]);
 }
 
-__global__ void __launch_bounds__(128) oracle_features_kernel(const float* __restrict__ points,
-                                                              const long long* __restrict__ offsets, int n,
-                                                              float* __restrict__ dirs) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  const long long o0 = offsets[s];
-  resample_and_diff(points + o0 * 3, (int)(offsets[s + 1] - o0), dirs + (size_t)s * (kOraclePts - 1) * 3);
+// Warp-per-streamline version of the same algorithm, bit-identical to resample_and_diff():
+//   1. lanes compute the segment lengths (double) in parallel;
+//   2. lane 0 accumulates them in the reference's order (the sums must round identically) and then
+//      builds the 128 targets nxt_i by repeated addition of total/127, as the reference loop does;
+//   3. every lane resolves 4 of the 128 output points: the loop's state machine reduces to "smallest
+//      k with cum[k] >= nxt_i" (emit P[k] when equal, else interpolate in segment k-1..k), found
+//      by binary search; targets >= total are never reached by the loop and stay zero;
+//   4. differences of consecutive points, the last point pinned to the original last point.
+// Streamlines longer than FEAT_CAP points take the sequential path on lane 0.
+constexpr int FEAT_CAP = 1024;
+constexpr int FEAT_WARPS = 4;
+struct FeatSmem {
+  double cum[FEAT_CAP];          // cum[0] = 0, cum[k] = arc length up to point k
+  double nxt[kOraclePts];
+  float res[kOraclePts][3];
+};
+
+__device__ __forceinline__ double seg_len(const float* __restrict__ P, int i) {
+  const double dx = (double)__fsub_rn(P[3 * i], P[3 * i - 3]);
+  const double dy = (double)__fsub_rn(P[3 * i + 1], P[3 * i - 2]);
+  const double dz = (double)__fsub_rn(P[3 * i + 2], P[3 * i - 1]);
+  return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+__device__ void resample_and_diff_warp(const float* __restrict__ P, int N, float* __restrict__ D, FeatSmem& sm, int lane) {
+  if (N <= 0 || N > FEAT_CAP) {
+    if (lane == 0) resample_and_diff(P, N, D);
+    return;
+  }
+  for (int i = 1 + lane; i < N; i += 32) sm.cum[i] = seg_len(P, i);
+  __syncwarp();
+  if (lane == 0) {
+    double c = 0.0;
+    sm.cum[0] = 0.0;
+    for (int i = 1; i < N; ++i) {
+      c = __dadd_rn(c, sm.cum[i]);
+      sm.cum[i] = c;
+    }
+    const double step = c / (double)(kOraclePts - 1);
+    double t = 0.0;
+    for (int i = 0; i < kOraclePts; ++i) {
+      sm.nxt[i] = t;
+      t += step;
+    }
+  }
+  __syncwarp();
+  const double total = sm.cum[N - 1];
+#pragma unroll
+  for (int q = 0; q < kOraclePts / 32; ++q) {
+    const int i = lane + 32 * q;
+    const double t = sm.nxt[i];
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    if (i == kOraclePts - 1) {
+      r0 = P[3 * (N - 1)]; r1 = P[3 * (N - 1) + 1]; r2 = P[3 * (N - 1) + 2];
+    } else if (t < total) {
+      int lo = 0, hi = N - 1;              // cum[hi] = total > t: the answer exists
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sm.cum[mid] >= t) hi = mid; else lo = mid + 1;
+      }
+      const int k = lo;
+      const double ck = sm.cum[k];
+      if (t == ck) {
+        r0 = P[3 * k]; r1 = P[3 * k + 1]; r2 = P[3 * k + 2];
+      } else {
+        const double ratio = 1.0 - ((ck - t) / (ck - sm.cum[k - 1]));
+        const float* a = P + 3 * (k - 1);
+        r0 = (float)__dadd_rn((double)a[0], __dmul_rn(ratio, (double)__fsub_rn(a[3], a[0])));
+        r1 = (float)__dadd_rn((double)a[1], __dmul_rn(ratio, (double)__fsub_rn(a[4], a[1])));
+        r2 = (float)__dadd_rn((double)a[2], __dmul_rn(ratio, (double)__fsub_rn(a[5], a[2])));
+      }
+    }
+    sm.res[i][0] = r0; sm.res[i][1] = r1; sm.res[i][2] = r2;
+  }
+  __syncwarp();
+  for (int j = lane; j < (kOraclePts - 1) * 3; j += 32) {
+    const int i = j / 3, d = j - 3 * i;
+    D[j] = __fsub_rn(sm.res[i + 1][d], sm.res[i][d]);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * FEAT_WARPS) oracle_features_kernel(const float* __restrict__ points,
+                                                                          const long long* __restrict__ offsets, int n,
+                                                                          float* __restrict__ dirs) {
+  extern __shared__ __align__(16) uint8_t feat_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FeatSmem& sm = reinterpret_cast<FeatSmem*>(feat_raw)[warp];
+  for (int s = blockIdx.x * FEAT_WARPS + warp; s < n; s += gridDim.x * FEAT_WARPS) {
+    const long long o0 = offsets[s];
+    resample_and_diff_warp(points + o0 * 3, (int)(offsets[s + 1] - o0), dirs + (size_t)s * (kOraclePts - 1) * 3, sm, lane);
+  }
 }
 
 // The alive streamlines of a tracking batch, straight from the streamline buffer (what
 // OracleStoppingCriterion / OracleReward score every step, stopping_criteria.py:113-154).
-__global__ void __launch_bounds__(128) oracle_features_rows_kernel(ttl_batch b, int cur, float* __restrict__ dirs) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= b.ctrl[cur]) return;
-  const int row = b.alive[cur][r];
-  resample_and_diff(b.points + (size_t)row * b.max_pts * 3, b.npts[row], dirs + (size_t)r * (kOraclePts - 1) * 3);
+__global__ void __launch_bounds__(32 * FEAT_WARPS) oracle_features_rows_kernel(ttl_batch b, int cur, float* __restrict__ dirs) {
+  extern __shared__ __align__(16) uint8_t feat_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FeatSmem& sm = reinterpret_cast<FeatSmem*>(feat_raw)[warp];
+  const int n = b.ctrl[cur];
+  for (int r = blockIdx.x * FEAT_WARPS + warp; r < n; r += gridDim.x * FEAT_WARPS) {
+    const int row = b.alive[cur][r];
+    resample_and_diff_warp(b.points + (size_t)row * b.max_pts * 3, b.npts[row], dirs + (size_t)r * (kOraclePts - 1) * 3, sm, lane);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1168,12 +1257,36 @@ struct ttl_oracle_plan {
 
 extern "C" {
 
+static int feat_grid(int n) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = ttl_div_up(n, FEAT_WARPS);
+  return blocks < sms * 8 ? blocks : sms * 8;
+}
+static int feat_attr() {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(oracle_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(FEAT_WARPS * sizeof(FeatSmem)));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(oracle_features_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(FEAT_WARPS * sizeof(FeatSmem)));
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  return 0;
+}
+
 int ttl_oracle_features(const float* points, const int64_t* offsets, int32_t n, float* dirs, void* stream) {
   if (!points || !offsets || !dirs) return TTL_ERR_BAD_ARG;
   if (n <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  int rc = feat_attr();
+  if (rc) return rc;
   TTL_LAUNCH("oracle_features_kernel", s,
-             oracle_features_kernel<<<ttl_div_up(n, 128), 128, 0, s>>>(points, (const long long*)offsets, n, dirs));
+             oracle_features_kernel<<<feat_grid(n), 32 * FEAT_WARPS, FEAT_WARPS * sizeof(FeatSmem), s>>>(
+                 points, (const long long*)offsets, n, dirs));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -1182,8 +1295,10 @@ int ttl_oracle_features_rows(const ttl_batch* b, int32_t cur, int32_t n_upper, f
   if (!b || !dirs || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
   if (n_upper <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  int rc = feat_attr();
+  if (rc) return rc;
   TTL_LAUNCH("oracle_features_rows_kernel", s,
-             oracle_features_rows_kernel<<<ttl_div_up(n_upper, 128), 128, 0, s>>>(*b, cur, dirs));
+             oracle_features_rows_kernel<<<feat_grid(n_upper), 32 * FEAT_WARPS, FEAT_WARPS * sizeof(FeatSmem), s>>>(*b, cur, dirs));
   TTL_CHECK_LAST();
   return 0;
 }
