@@ -48,6 +48,18 @@ STATE_KERNEL_BYTES_PER_ROW = 4680 + 2460 + 1200 + 12
 WORKLOAD = 'whole-brain synthetic 145x174x145 1.25mm order-8 fODF, npv=20, n_actor=50000'
 CPU_SAMPLE_ROWS = 4096
 BURN_IN = 128
+CONFIG = 2
+
+
+def set_config(n):
+    """BASELINE.json configs[1] (default, the configuration the metric is quoted on) or configs[2]
+    (0.5 mm-iso 290^3 volume, 798 steps max, ~1M seeds per GPU) for the steady-state legs."""
+    global SHAPE, VOXEL_MM, NPV, STEP_MM, WORKLOAD, CONFIG
+    CONFIG = n
+    if n == 3:
+        SHAPE, VOXEL_MM, NPV = (290, 290, 290), 0.5, 5
+        STEP_MM = VOXEL_MM / TRAINED_VOXEL * TRAINED_STEP
+        WORKLOAD = '0.5mm-iso synthetic 290x290x290 order-8 fODF, npv=5 (~1M seeds), n_actor=50000'
 
 
 def peaks():
@@ -411,7 +423,8 @@ def main_gpu(args):
                        'state_rows': ('bf16 actor operand only; the fp32 API tensor is not materialised in the '
                                       'device loop (SURVEY 7 step 7)' if args.bf16_state_only
                                       else 'fp32 API tensor + bf16 actor operand'),
-                       'l2': 'inputs larger than L2: 702 MB SH volume + 2x123 MB state rows + 210 MB activations',
+                       'l2': 'inputs larger than L2: %d MB SH volume + 2x123 MB state rows + 210 MB activations'
+                             % (SHAPE[0] * SHAPE[1] * SHAPE[2] * 48 * 4 // 1000000),
                        'parallelism': 'seeds sharded, volume replicated, no data-path collective'},
             'e2e': {'value': e2e_value, 'unit': 'streamline-steps/s',
                     'h2d_bytes_per_step': h2d / max(1, e2e_steps), 'd2h_bytes_per_step': d2h / max(1, e2e_steps),
@@ -443,7 +456,10 @@ if __name__ == '__main__':
                     help='also materialise the fp32 state rows every step (the reference API tensor)')
     ap.add_argument('--graph', action='store_true', help='replay the 6 kernels of a step from a CUDA graph')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
+    ap.add_argument('--config', type=int, default=2, choices=[2, 3],
+                    help='2: BASELINE.json configs[1] (default); 3: configs[2], the 290^3 0.5 mm volume')
     a = ap.parse_args()
+    set_config(a.config)
     if a.warmup < 3:
         a.warmup = 3
     sys.exit(main_reference(a) if a.impl == 'reference' else main_gpu(a))

@@ -75,21 +75,37 @@ class SACAuto(RLAlgorithm):
         losses_log = []
         A = env._n_alive_host
         S = env.get_state_size()
-        while A > 0:
-            state = env.current_state()[:A]
-            action, _, _ = actor.forward_device(state, 1.0, n_rows=A, want_logp=False)
-            env.step_device(action)
-            next_state = torch.empty((A, S), dtype=torch.float32, device=env.device)
-            _lib.check(env._lib.ttl_env_gather_step_state(ctypes.byref(env._b), env._cur, A, _lib.ptr(next_state),
-                                                          S, _lib.stream_ptr(env.device)), 'ttl_env_gather_step_state')
-            reward = env._batch.reward[:A] if env.compute_reward else torch.zeros((A,), device=env.device)
-            done = env._batch.stop[:A]
-            self.replay_buffer.add(state, action, next_state, reward, done)
-            running_reward += float(reward.sum().item()) if env.compute_reward else 0.0
-            if self.t >= self.start_timesteps:
+        import torch.distributed as dist
+        dp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        while True:
+            if A > 0:
+                state = env.current_state()[:A]
+                action, _, _ = actor.forward_device(state, 1.0, n_rows=A, want_logp=False)
+                env.step_device(action)
+                next_state = torch.empty((A, S), dtype=torch.float32, device=env.device)
+                _lib.check(env._lib.ttl_env_gather_step_state(ctypes.byref(env._b), env._cur, A, _lib.ptr(next_state),
+                                                              S, _lib.stream_ptr(env.device)), 'ttl_env_gather_step_state')
+                reward = env._batch.reward[:A] if env.compute_reward else torch.zeros((A,), device=env.device)
+                done = env._batch.stop[:A]
+                self.replay_buffer.add(state, action, next_state, reward, done)
+                running_reward += float(reward.sum().item()) if env.compute_reward else 0.0
+            ready = self.t >= self.start_timesteps
+            if dp:
+                # replicas must issue the same sequence of gradient all-reduces: update only when every
+                # rank has enough transitions, and keep updating (from the local replay shard) until
+                # the longest episode among the ranks has ended
+                flag = torch.tensor([float(A), -float(ready)], device=env.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                any_alive, ready = float(flag[0]) > 0, float(flag[1]) < 0
+            else:
+                any_alive = A > 0
+            if ready and (A > 0 or dp) and any_alive:
                 losses_log.append(self.update(self.replay_buffer.sample(self.batch_size)))
-            self.t += A
-            env.harvest_device()
-            A = env.n_alive()
-            episode_length += 1
+            if A > 0:
+                self.t += A
+                env.harvest_device()
+                A = env.n_alive()
+                episode_length += 1
+            if not any_alive:
+                break
         return running_reward, losses_log, episode_length, {}

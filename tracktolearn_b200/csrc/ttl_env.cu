@@ -118,16 +118,22 @@ __device__ double mask_spline_value(const ttl_volume& v, float px, float py, flo
   return out;
 }
 
-// The same value computed by the 4 lanes that share a streamline: lane `sub` multiplies out the
-// 16 taps of x-slab `sub`, then the running sum is handed from lane to lane so the 64 additions
-// happen in exactly scipy's order (slab 0 first, z fastest).  All 4 lanes return the value.
+__device__ __forceinline__ double shfl_d(unsigned mask, double x, int src) {
+  return __shfl_sync(mask, x, src);
+}
+
+// The same value computed by the 4 lanes that share a streamline.  The lanes split the work: lane a
+// (a < 3) evaluates the four B-spline weights of axis a (6 fp64 divisions each) and broadcasts them,
+// lane `sub` multiplies out the 16 taps of x-slab `sub`, then the running sum is handed from lane
+// to lane so the 64 additions happen in exactly scipy's order (slab 0 first, z fastest).
+// All 4 lanes return the value.
 __device__ double mask_spline_value_quad(const ttl_volume& v, float px, float py, float pz, int sub,
                                          unsigned quad_mask, int lane) {
   const double c[3] = {(double)__fsub_rn(px, 0.5f), (double)__fsub_rn(py, 0.5f),
                        (double)__fsub_rn(pz, 0.5f)};
   const int dims[3] = {v.MX, v.MY, v.MZ};
   int start[3];
-  double w[3][4];
+  double frac[3];
   bool edge = false;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -135,12 +141,21 @@ __device__ double mask_spline_value_quad(const ttl_volume& v, float px, float py
     const double fl = floor(c[a]);
     start[a] = (int)fl - 1;
     edge |= (start[a] < 0) || (start[a] + 3 >= dims[a]);
-    bspline3(c[a] - fl, w[a]);
+    frac[a] = c[a] - fl;
+  }
+  const int quad_base = lane & ~(kLanesPerRow - 1);
+  // my axis' weights (lane 3 recomputes axis 2; its copy is not used)
+  double wm[4];
+  bspline3(sub == 0 ? frac[0] : (sub == 1 ? frac[1] : frac[2]), wm);
+  double wx = 0.0, wy[4], wz[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const double x = shfl_d(quad_mask, wm[t], quad_base + 0);
+    wx = (sub == t) ? x : wx;
+    wy[t] = shfl_d(quad_mask, wm[t], quad_base + 1);
+    wz[t] = shfl_d(quad_mask, wm[t], quad_base + 2);
   }
   const int xi = edge ? mirror_idx(start[0] + sub, dims[0]) : start[0] + sub;
-  double wx = w[0][0];
-#pragma unroll
-  for (int t = 1; t < 4; ++t) wx = (sub == t) ? w[0][t] : wx;
   int yi[4], zi[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -152,23 +167,27 @@ __device__ double mask_spline_value_quad(const ttl_volume& v, float px, float py
   for (int j = 0; j < 4; ++j) {
     const double* line = v.mask_coef + ((size_t)xi * v.MY + yi[j]) * v.MZ;
 #pragma unroll
+    for (int k = 0; k < 4; ++k) prod[4 * j + k] = __ldg(line + zi[k]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
-      double t = __ldg(line + zi[k]);
+      double t = prod[4 * j + k];
       t = __dmul_rn(t, wx);
-      t = __dmul_rn(t, w[1][j]);
-      t = __dmul_rn(t, w[2][k]);
+      t = __dmul_rn(t, wy[j]);
+      t = __dmul_rn(t, wz[k]);
       prod[4 * j + k] = t;
     }
   }
   double acc = 0.0;
-  const int quad_base = lane & ~(kLanesPerRow - 1);
 #pragma unroll
   for (int s4 = 0; s4 < 4; ++s4) {
     if (sub == s4) {
 #pragma unroll
       for (int t = 0; t < 16; ++t) acc = __dadd_rn(acc, prod[t]);
     }
-    acc = __shfl_sync(quad_mask, acc, quad_base + s4);
+    acc = shfl_d(quad_mask, acc, quad_base + s4);
   }
   return acc;
 }
@@ -386,18 +405,22 @@ __global__ void __launch_bounds__(kK1Threads) propagate_stop_kernel(
       dz = __dadd_rn(dz, noise[3 * (size_t)r + 2]);
     }
     const double nrm = __dsqrt_rn(dot3d(dx, dy, dz, dx, dy, dz));
-    dx = __dmul_rn(__ddiv_rn(dx, nrm), prm.step_vox);
-    dy = __dmul_rn(__ddiv_rn(dy, nrm), prm.step_vox);
-    dz = __dmul_rn(__ddiv_rn(dz, nrm), prm.step_vox);
-    qx = (float)__dadd_rn((double)px, dx);
-    qy = (float)__dadd_rn((double)py, dy);
-    qz = (float)__dadd_rn((double)pz, dz);
+    // lane a of the quad scales and adds component a (one fp64 division per lane instead of three)
+    const double da = sub == 0 ? dx : (sub == 1 ? dy : dz);
+    const double pa = (double)(sub == 0 ? px : (sub == 1 ? py : pz));
+    const double sa = __dmul_rn(__ddiv_rn(da, nrm), prm.step_vox);
+    const float qa = (float)__dadd_rn(pa, sa);
+    const int quad_base = lane & ~(kLanesPerRow - 1);
+    qx = __shfl_sync(quad_mask, qa, quad_base + 0);
+    qy = __shfl_sync(quad_mask, qa, quad_base + 1);
+    qz = __shfl_sync(quad_mask, qa, quad_base + 2);
     if (L == 1) {  // tracking_env.py:165-178: flip if the first step would stop
       const float two[6] = {px, py, pz, qx, qy, qz};
       if (stopping_flags_quad(v, prm, two, 2, sub, quad_mask, lane) != 0) {
-        qx = (float)__dadd_rn((double)px, -dx);
-        qy = (float)__dadd_rn((double)py, -dy);
-        qz = (float)__dadd_rn((double)pz, -dz);
+        const float fa = (float)__dadd_rn(pa, -sa);
+        qx = __shfl_sync(quad_mask, fa, quad_base + 0);
+        qy = __shfl_sync(quad_mask, fa, quad_base + 1);
+        qz = __shfl_sync(quad_mask, fa, quad_base + 2);
       }
     }
   } else {

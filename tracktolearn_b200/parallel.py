@@ -37,10 +37,24 @@ def _device_for_backend():
     return torch.device('cpu')
 
 
+_PINNED = {}
+
+
+def _pinned(nbytes):
+    """Grow-only pinned staging buffer (a fresh 1 GB cudaHostAlloc per gather costs more than the
+    transfer it serves)."""
+    cur = _PINNED.get('buf')
+    if cur is None or cur.numel() < nbytes:
+        cur = torch.empty((int(nbytes * 1.25) + 4096,), dtype=torch.uint8, pin_memory=True)
+        _PINNED['buf'] = cur
+    return cur
+
+
 def gather_tractogram(local, dst=0):
     """Gather packed tractograms on rank `dst` in rank order.  Returns the merged Tractogram on
-    `dst` and None elsewhere.  Three variable-size all-gathers worth of data, done as one
-    all_gather of the sizes followed by padded all_gathers (NCCL has no gatherv)."""
+    `dst` and None elsewhere.  One all_gather of the sizes, then every rank sends exactly its rows
+    straight into its slice of rank `dst`'s buffer (batched point-to-point: NVLink device-to-device
+    under NCCL, one pinned D2H on `dst`; plain CPU tensors under gloo)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -51,29 +65,43 @@ def gather_tractogram(local, dst=0):
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
     all_sizes = torch.stack(all_sizes).cpu().numpy()
-    max_sl, max_pts = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
 
-    def padded_gather(arr, rows, width, dtype):
-        buf = torch.zeros((rows, width), dtype=dtype, device=dev)
-        if len(arr):
-            buf[:len(arr)] = torch.as_tensor(np.ascontiguousarray(arr).reshape(len(arr), width)).to(dev, dtype=dtype)
-        out = [torch.zeros_like(buf) for _ in range(world)]
-        dist.all_gather(out, buf)
-        return [o.cpu().numpy() for o in out] if rank == dst else None
+    def gather_rows(arr, counts, width, dtype):
+        mine = torch.as_tensor(np.ascontiguousarray(arr).reshape(-1, width)).to(dev, dtype=dtype).contiguous()
+        ops, buf = [], None
+        if rank == dst:
+            buf = torch.empty((int(counts.sum()), width), dtype=dtype, device=dev)
+            o = 0
+            for r in range(world):
+                c = int(counts[r])
+                if r == dst:
+                    buf[o:o + c].copy_(mine)
+                elif c > 0:
+                    ops.append(dist.P2POp(dist.irecv, buf[o:o + c], r))
+                o += c
+        elif int(counts[rank]) > 0:
+            ops.append(dist.P2POp(dist.isend, mine, dst))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if rank != dst:
+            return None
+        if buf.is_cuda:
+            host = _pinned(buf.numel() * buf.element_size())[:buf.numel() * buf.element_size()].view(dtype)
+            host = host.view(buf.shape)
+            host.copy_(buf)
+            return host.numpy().copy()
+        return buf.numpy()
 
-    pts = padded_gather(local.data, max_pts, 3, torch.float32)
-    lens = padded_gather(np.diff(local.offsets).astype(np.int64), max_sl, 1, torch.int64)
-    seeds = padded_gather(np.asarray(local.data_per_streamline.get('seeds', np.zeros((n_sl, 3)))),
-                          max_sl, 3, torch.float64)
-    flags = padded_gather(np.asarray(local.data_per_streamline.get('flags', np.zeros(n_sl))).astype(np.int64),
-                          max_sl, 1, torch.int64)
+    n_per, p_per = all_sizes[:, 0], all_sizes[:, 1]
+    data = gather_rows(local.data, p_per, 3, torch.float32)
+    lens = gather_rows(np.diff(local.offsets).astype(np.int64), n_per, 1, torch.int64)
+    seeds = gather_rows(np.asarray(local.data_per_streamline.get('seeds', np.zeros((n_sl, 3)))), n_per, 3,
+                        torch.float64)
+    flags = gather_rows(np.asarray(local.data_per_streamline.get('flags', np.zeros(n_sl))).astype(np.int64),
+                        n_per, 1, torch.int64)
     if rank != dst:
         return None
-    data = np.concatenate([pts[r][:all_sizes[r, 1]] for r in range(world)])
-    all_lens = np.concatenate([lens[r][:all_sizes[r, 0], 0] for r in range(world)])
-    offsets = np.concatenate(([0], np.cumsum(all_lens))).astype(np.int64)
-    return Tractogram(
-        data=data, offsets=offsets,
-        data_per_streamline={
-            'seeds': np.concatenate([seeds[r][:all_sizes[r, 0]] for r in range(world)]),
-            'flags': np.concatenate([flags[r][:all_sizes[r, 0], 0] for r in range(world)])})
+    offsets = np.concatenate(([0], np.cumsum(lens[:, 0]))).astype(np.int64)
+    return Tractogram(data=data, offsets=offsets,
+                      data_per_streamline={'seeds': seeds, 'flags': flags[:, 0]})

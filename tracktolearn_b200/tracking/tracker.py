@@ -55,8 +55,9 @@ class Tracker(object):
             return
         rows = self.rows_per_pass
         if rows is None:
-            # streamline buffer budget: rows * (max_nb_steps+1) * 12 bytes <= ~6 GB
-            rows = max(self.n_actor, int(6e9 // ((env.max_nb_steps + 1) * 12)))
+            # streamline buffer budget: rows * (max_nb_steps+1) * 12 bytes <= ~24 GB of the 180 GB of
+            # HBM3e (1M seeds at 799 points = 9.6 GB is one pass, hence one low-occupancy tail)
+            rows = max(self.n_actor, int(24e9 // ((env.max_nb_steps + 1) * 12)))
         for start in range(0, n_seeds, rows):
             yield start, min(start + rows, n_seeds), self.n_actor
 
