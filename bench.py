@@ -62,6 +62,25 @@ def set_config(n):
         WORKLOAD = '0.5mm-iso synthetic 290x290x290 order-8 fODF, npv=5 (~1M seeds), n_actor=50000'
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the step's kernels from
+    the committed `ncu --set full` capture of this same command (profiles/README.md); None when the
+    summary file is absent."""
+    path = os.path.join(ROOT, 'profiles', 'r1_step_kernels_ncu_summary.json')
+    if not os.path.exists(path):
+        return {}
+
+    def mbytes(txt):
+        v, unit = txt.split()[:2]
+        return float(v) * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
+    per = {}
+    with open(path) as f:
+        for e in json.load(f):
+            name = e['kernel'].split('<')[0]
+            per.setdefault(name, []).append(mbytes(e['dram__bytes_read.sum']) + mbytes(e['dram__bytes_write.sum']))
+    return {k: sum(v) / len(v) for k, v in per.items()}
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -366,13 +385,16 @@ def main_gpu(args):
     dn = [prof.get(k, (0, 0.0)) for k in ('dense_bf16_kernel', 'dense_bf16_head_kernel')]
     dense_launches = sum(n for n, _ in dn)
     dense_total_ms = sum(ms for _, ms in dn)
+    traffic = ncu_traffic()
+    traffic_src = 'profiles/r1_step_kernels_ncu_summary.json (ncu --set full of this command, bytes per launch)'
     roofline = None
     if dense_launches:
         steps_prof = dense_launches / 3.0
         achieved = DENSE_FLOP_PER_ROW * rows_prof * steps_prof / (dense_total_ms * 1e-3) / 1e12
         roofline = {'kernel': 'dense_bf16_kernel (tcgen05 actor layers, 3 launches/step, last one with fused head)',
                     'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'],
-                    'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
+                    'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_tflops_sustained'],
+                    'traffic': traffic.get('dense_bf16_2cta_kernel'), 'traffic_source': traffic_src,
                     'avg_launch_us': 1000.0 * dense_total_ms / dense_launches,
                     'flop_per_launch': DENSE_FLOP_PER_ROW * rows_prof / 3.0,
                     'peak_source': pk['source'] + ', sustained bf16 figure (kernel timed inside a long step)'}
@@ -392,11 +414,14 @@ def main_gpu(args):
         a_step = step_bytes * rows_prof / (step_ms * 1e-3) / 1e9
         roofline_step = {
             'build_state_kernel': {'bound': 'hbm', 'achieved': a_state, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                                   'frac': a_state / pk['hbm_gbs'], 'traffic': None,
+                                   'frac': a_state / pk['hbm_gbs'], 'traffic': traffic.get('build_state_kernel'),
+                                   'algorithmic_bytes_per_launch': state_bytes * rows_prof,
                                    'bytes_per_row': state_bytes},
             'env_step (propagate_stop+build_state)': {
                 'bound': 'hbm', 'achieved': a_step, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                'frac': a_step / pk['hbm_gbs'], 'traffic': None, 'bytes_per_row': step_bytes},
+                'frac': a_step / pk['hbm_gbs'],
+                'traffic': (traffic.get('build_state_kernel', 0) + traffic.get('propagate_stop_kernel', 0)) or None,
+                'algorithmic_bytes_per_launch': step_bytes * rows_prof, 'bytes_per_row': step_bytes},
             'peak_source': pk['source']}
 
     cpu_baseline = None

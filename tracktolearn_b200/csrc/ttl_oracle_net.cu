@@ -688,7 +688,7 @@ oracle_forward_tc_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensorM
 // threads read the fp32 accumulator with tcgen05.ld and write the fp16 operand of the next product
 // back over it with tcgen05.st, so one chunk costs two mbarrier hand-offs and no proxy fence.
 // Shared memory per CTA (two CTAs per SM): T0 16 KB [x or K | o or x'], T1 16 KB Q slices, VT 8 KB,
-// 4 KB constant [1 1 0..] operand, weight ring 3 x 20 KB.  TMEM: 256 columns (acc1 2 x 64 | 128 shared by QKV, O, out-proj, acc2).
+// weight ring 3 x 20 KB.  TMEM: 256 columns (acc1 2 x 64 | 128 shared by QKV, O, out-proj, acc2).
 namespace tc2 {
 using namespace ttl_tc;
 constexpr int CH = 64;
@@ -701,12 +701,13 @@ constexpr int PRM_FLOATS = 288;                 // in_proj_b 96 | out_proj_b 32 
 constexpr int P_INB = 0, P_OUTB = 96, P_N1W = 128, P_N1B = 160, P_L2B = 192, P_N2W = 224, P_N2B = 256;
 constexpr uint32_t FFN_TX = 16384 + AUG_PAIR_BYTES;
 constexpr uint32_t ATT_TX = 12288 + PRM_FLOATS * 4;
-constexpr int OFF_T0 = 0, OFF_T1 = 16384, OFF_VT = 32768, OFF_ONES = 40960, OFF_RING = 45056;
+constexpr int OFF_T0 = 0, OFF_T1 = 16384, OFF_VT = 32768, OFF_RING = 40960;
 constexpr int OFF_BAR = OFF_RING + NST * STAGE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;
 constexpr int COL_B = 128;                      // QKV result / O blocks / out-proj result / FFN output
+constexpr int COL_X = 160, COL_ONES = 176;      // FFN phase: x (fp16, 16 columns) and the [1 1 0..] slice (8 columns)
 static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 }  // namespace tc2
 
@@ -798,12 +799,6 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp < 4) {   // constant A-side slice of the bias trick: row t = [1 1 0 ...] (K = 16, no swizzle)
-    uint8_t* ones = sbase + OFF_ONES + (threadIdx.x >> 3) * 256 + (threadIdx.x & 7) * 16;
-    *reinterpret_cast<uint4*>(ones) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(ones + 128) = make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -851,7 +846,6 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
     const uint64_t d_q = umma_desc_sw128(base + OFF_T1);
     const uint64_t d_ring = umma_desc_sw128(base + OFF_RING);
     const uint64_t d_vt = umma_desc_sw128(base + OFF_VT);
-    const uint64_t d_ones = umma_desc_noswz(base + OFF_ONES, 128, 256);
     uint32_t par_h = 0;  // bit b: parity of the next h_full[b] completion
     uint32_t gp = 0, n_sig = 0;
     auto wait_x = [&]() {
@@ -934,12 +928,15 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
         auto issue_g1 = [&](int c, uint32_t b) {
           const uint32_t st = (gpF + (uint32_t)(c >> 1)) % NST;
           const uint64_t d_w1 = d_ring + (uint64_t)((st * STAGE_BYTES) >> 4) + (uint64_t)(4 * (c & 1));
+          // A operand from tensor memory: x (fp16, 16 columns at COL_X) and the [1 1 0..] bias slice
+          // (8 columns at COL_ONES); small SS-form MMAs are bound by the shared-memory read of A
+          // (measured 48 cycles for N = 64, benchmarks/micro/umma_latency.cu), TS-form runs at 32
 #pragma unroll
           for (int k = 0; k < 2; ++k)
-            tc_mma_bf16(tmem_base + acc1_col(b), d_t0 + (uint64_t)(4 + 2 * k), d_w1 + (uint64_t)(2 * k), id_64, (uint32_t)(k != 0));
-          tc_mma_bf16(tmem_base + acc1_col(b), d_ones,
-                      umma_desc_noswz(base + OFF_RING + st * STAGE_BYTES + ST_AUG + (c & 1) * (AUG_PAIR_BYTES / 2), 128, 256),
-                      id_64, 1u);     // + b1
+            tc_mma_f16_ts(tmem_base + acc1_col(b), tmem_base + COL_X + 8u * k, d_w1 + (uint64_t)(2 * k), id_64, (uint32_t)(k != 0));
+          tc_mma_f16_ts(tmem_base + acc1_col(b), tmem_base + COL_ONES,
+                        umma_desc_noswz(base + OFF_RING + st * STAGE_BYTES + ST_AUG + (c & 1) * (AUG_PAIR_BYTES / 2), 128, 256),
+                        id_64, 1u);     // + b1
           tc_commit(acc1_full(b));
         };
         auto wait_stage = [&](int c) {   // first chunk of a pair: its weights must have landed
@@ -1129,7 +1126,18 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
 #pragma unroll
           for (int i = 0; i < D_MODEL; ++i) x[i] += __uint_as_float(r[i]) + prm[P_OUTB + i];
           layer_norm32_s(x, prm + P_N1W, prm + P_N1B);
-          store_row32(t0, tid, 4, x);
+          // x (fp16) and the constant bias slice -> tensor memory, the A operands of GEMM1
+          uint32_t xp[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+            xp[i] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          tc_st16(lane_base + COL_X, xp);
+          const uint32_t ones[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          tc_st8(lane_base + COL_ONES, ones);
+          tc_wait_st();
+          tc_fence_before();
         }
         signal();
         // ---- feed forward ----
