@@ -386,24 +386,27 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer (both CTAs) =====
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cluster_id; tile < total; tile += n_clusters) {
-        const int m_blk = tile / n_n, n_blk = tile - m_blk * n_n;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(empty(stage), phase ^ 1u);
+    // ===== TMA producer (both CTAs).  The whole warp runs the loop and the waits; the elected lane
+    //       issues (ttl_tc.cuh, elect_one: no per-instruction ELECT / BRA.U.ANY loop) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total; tile += n_clusters) {
+      const int m_blk = tile / n_n, n_blk = tile - m_blk * n_n;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(empty(stage), phase ^ 1u);
+        if (elect_one()) {
           const uint32_t leader_full = mapa_shared(full(stage), 0);
           if (cta == 0) mbar_arrive_expect_tx(full(stage), 2 * STAGE2_BYTES);
           const uint32_t sa = base + stage * STAGE2_BYTES;
           tma_load_2d_2cta(sa, &tma_a, leader_full, kb * BK, m_blk * 2 * BM + (int)cta * BM);
           tma_load_2d_2cta(sa + A_BYTES, &tma_b, leader_full, kb * BK, n_blk * BN + (int)cta * (BN / 2));
-          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && cta == 0) {  // ===== MMA issuer (leader only) =====
+    if (cta == 0) {  // ===== MMA issuer (leader CTA only; warp-uniform, elected lane issues) =====
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       constexpr uint32_t idesc = umma_idesc_2cta();
@@ -414,16 +417,19 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full(stage), phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * STAGE2_BYTES;
-          const uint64_t da = umma_desc(sa), db = umma_desc(sa + A_BYTES);
+          if (elect_one()) {
+            const uint32_t sa = base + stage * STAGE2_BYTES;
+            const uint64_t da = umma_desc(sa), db = umma_desc(sa + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc_mma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                             (uint32_t)((kb | k) != 0));
-          tc_commit_2cta(empty(stage));   // frees this stage in BOTH CTAs
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                               (uint32_t)((kb | k) != 0));
+            tc_commit_2cta(empty(stage));   // frees this stage in BOTH CTAs
+            if (kb == kblocks - 1) tc_commit_2cta(tfull(acc));       // accumulators complete in both CTAs
+          }
+          __syncwarp();
           if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
         }
-        tc_commit_2cta(tfull(acc));       // accumulators complete in both CTAs
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     }
