@@ -806,8 +806,12 @@ __device__ __forceinline__ int survivors_before(const ttl_batch& b, int r, int n
   return b.grp_prefix[g] + __popc(__ballot_sync(0xffffffffu, counts));
 }
 
-__global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volume v, ttl_params prm,
-                                                                       ttl_batch b, int cur, int warp_smem) {
+// FAST = 1: the bf16-only device mode (ttl_batch.bf16_layout == 1) compiled on its own with a register
+// budget (85) that lets one lane keep all 24 of its LDG.128 gathers in flight; in the general kernel
+// ptxas keeps 4 in flight to stay at 47 registers.
+template <int FAST>
+__global__ void __launch_bounds__(kStateWarps * 32, FAST ? 6 : 1) build_state_kernel(ttl_volume v, ttl_params prm,
+                                                                                     ttl_batch b, int cur, int warp_smem) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * warp_smem);
@@ -843,7 +847,10 @@ __global__ void __launch_bounds__(kStateWarps * 32) build_state_kernel(ttl_volum
                            ? reinterpret_cast<__nv_bfloat16*>(b.state_bf16[cur ^ 1]) + (size_t)dst * b.ld_bf16
                            : nullptr;
   float* o32 = b.state[cur ^ 1] ? b.state[cur ^ 1] + (size_t)dst * b.ld_state : nullptr;
-  build_state_row(v, prm, P, L, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
+  if (FAST)
+    build_state_row_c45_bf16(v, prm, P, L, o16, b.ld_bf16, smem_f, lane);
+  else
+    build_state_row(v, prm, P, L, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
 }
 
 // reset: alive[0] = identity, state goes to state[0]
@@ -958,7 +965,9 @@ constexpr int kStateSmem = kStateWarps * kWarpSmemBytes;
 int state_kernels_ready() {
   static bool done = false;
   if (done) return 0;
-  cudaError_t e = cudaFuncSetAttribute(build_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  cudaError_t e = cudaFuncSetAttribute(build_state_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(build_state_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(reset_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
@@ -1048,9 +1057,14 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   rc = state_kernels_ready();
   if (rc) return rc;
   const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;
-  TTL_LAUNCH("build_state_kernel", s,
-             build_state_kernel<<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
-                 *vol, *prm, *b, cur, warp_smem));
+  if (b->bf16_layout == 1)
+    TTL_LAUNCH("build_state_kernel", s,
+               build_state_kernel<1><<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
+                   *vol, *prm, *b, cur, warp_smem));
+  else
+    TTL_LAUNCH("build_state_kernel", s,
+               build_state_kernel<0><<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
+                   *vol, *prm, *b, cur, warp_smem));
   TTL_CHECK_LAST();
   return 0;
 }
@@ -1091,9 +1105,14 @@ int ttl_env_step_finish(const ttl_volume* vol, const ttl_params* prm, const ttl_
   rc = state_kernels_ready();
   if (rc) return rc;
   const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;
-  TTL_LAUNCH("build_state_kernel", s,
-             build_state_kernel<<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
-                 *vol, *prm, *b, cur, warp_smem));
+  if (b->bf16_layout == 1)
+    TTL_LAUNCH("build_state_kernel", s,
+               build_state_kernel<1><<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
+                   *vol, *prm, *b, cur, warp_smem));
+  else
+    TTL_LAUNCH("build_state_kernel", s,
+               build_state_kernel<0><<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
+                   *vol, *prm, *b, cur, warp_smem));
   TTL_CHECK_LAST();
   return 0;
 }
