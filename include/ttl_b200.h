@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TTL_ABI_VERSION 1
+#define TTL_ABI_VERSION 2
 
 /* StoppingFlags, environments/stopping_criteria.py:10-20 */
 #define TTL_STOPPING_MASK 1
@@ -105,6 +105,13 @@ typedef struct ttl_batch {
                               first-layer weights are permuted to match, ttl_actor_plan_set_layout).
                               state[] may be NULL with layout 1: the fp32 rows are then not
                               materialised */
+  float* rank_rec[2];      /* ping-pong [n_slots+16][8] fp32 words, one 32-byte record per rank of
+                              alive[k]: {row (int bits), points so far (int bits), tip xyz, the point
+                              before the tip xyz (zeros when there is none)}.  Written by reset and by
+                              the state kernel of every step; the next step reads it instead of
+                              chasing alive[] -> npts[] -> points[] (tracking_env.py:181-188 re-slices
+                              the streamline buffer for the same purpose) */
+  float* step_tip;         /* [n_slots+16][4] per rank of alive[cur]: the point added this step */
 } ttl_batch;
 
 /* ---- one-time / load-time helpers ------------------------------------------------------ */
@@ -135,6 +142,18 @@ int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch*
 int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
                  const float* actions, int32_t lda, const double* noise, int32_t n_upper,
                  void* stream);
+
+/* ttl_env_step with the actions taken straight from the actor's fused head (the pointers that
+ * ttl_actor_head_partial returns after a forward with action == NULL): action = tanh(mu), the
+ * deterministic policy that tracking uses (prob = 0: tracker.py:28, ttl_track.py:172-175;
+ * offpolicy.py:126-128 with std * 0).  head_partial [n_alive][n_tiles][8] fp32 per-column-tile
+ * partial sums of the 6-wide output layer, head_bias [6].  The sums are taken in tile order like the
+ * actor's own finishing pass, so this entry point and ttl_actor_forward* + ttl_env_step give the
+ * same bits; it saves one launch and the action round trip per step.  No noise input: the noisy
+ * environment with sigma > 0 goes through ttl_env_step. */
+int ttl_env_step_head(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                      const float* head_partial, int32_t n_tiles, const float* head_bias,
+                      int32_t n_upper, void* stream);
 
 /* The same step split in two so that TractOracle-Net can be consulted in between
  * (OracleStoppingCriterion, stopping_criteria.py:113-154: stop where the score < 0.5 once the
@@ -217,6 +236,12 @@ int ttl_actor_forward_packed(ttl_actor_plan* plan, const void* state_bf16, int32
                              int32_t rows_alloc, const int32_t* n_rows_dev, int32_t n_rows_max,
                              float probabilistic, const float* eps, float* action, float* logp,
                              float* pre, int32_t layout, void* stream);
+/* With action == NULL (and logp == pre == NULL) ttl_actor_forward_packed stops after the last
+ * tensor-core layer when the 6-wide output layer is fused into it: the per-tile partial sums of
+ * mu / log_std stay in the plan's scratch and this call returns where (see ttl_env_step_head).
+ * TTL_ERR_UNSUPPORTED when the plan's output layer is not fused. */
+int ttl_actor_head_partial(const ttl_actor_plan* plan, const float** partial, int32_t* n_tiles,
+                           const float** bias);
 /* Prepares the plan for ttl_batch.bf16_layout == 1: packs a copy of the first layer's weights
  * whose columns follow [n_points*CP | rest] (zero columns for the CP - C padding channels). */
 int ttl_actor_plan_set_layout(ttl_actor_plan* plan, int32_t C, int32_t CP, int32_t n_points, void* stream);

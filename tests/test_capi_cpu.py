@@ -22,7 +22,7 @@ def test_library_builds_and_exports_declared_symbols():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.ttl_abi_version() == 1
+    assert lib.ttl_abi_version() == 2
     assert lib.ttl_launch_count() >= 0
 
 

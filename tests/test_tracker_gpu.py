@@ -111,6 +111,27 @@ def test_bf16_only_state_mode_tracks_the_same_streamlines():
     assert (a.data_per_streamline['flags'] == b.data_per_streamline['flags'])[same].all()
 
 
+def test_fused_head_step_is_bit_identical_to_action_round_trip():
+    """Device loop with the env step reading tanh(mu) from the actor's fused output layer
+    (ttl_env_step_head) vs actor -> action buffer -> ttl_env_step: same streamlines, bit for bit,
+    in both state modes."""
+    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    n = len(seeds)
+    for fp32_state in (True, False):
+        out = []
+        for fuse in (True, False):
+            alg.fuse_head = fuse
+            st = env.reset_streaming(0, n, 256, fp32_state=fp32_state)
+            alg.validation_episode(st, env, 0.0)
+            assert alg._runner.fuse_head == fuse
+            out.append(env.get_streamlines())
+        a, b = out
+        np.testing.assert_array_equal(a.lengths, b.lengths)
+        np.testing.assert_array_equal(a.data, b.data)
+        np.testing.assert_array_equal(a.data_per_streamline['flags'], b.data_per_streamline['flags'])
+    alg.fuse_head = True
+
+
 def test_training_episode_rollout_replay_and_update():
     """A3 / config 4: DDPG._episode-style rollout with the tensor-core actor sampling at
     probabilistic=1, transitions pushed to the device replay buffer, one SAC update per env step,

@@ -182,6 +182,36 @@ class MaxEntropyActor(object):
         self._keep = (state, eps)
         return action, logp, pre
 
+    def forward_head_partial(self, state_bf16, n_rows, n_rows_dev=None, layout=None):
+        """Deterministic policy (prob = 0) for the device loop: runs the tensor-core layers over the
+        env's bf16 state rows and leaves the 6-wide output layer as per-tile partial sums in the
+        plan's scratch.  Returns (partial_ptr, n_tiles, bias_ptr) for ``env.step_device_head``, or
+        None when this actor cannot do it (fp32 tier, output layer not fused)."""
+        if self.precision != 'bf16' or state_bf16 is None:
+            return None
+        rows = int(n_rows)
+        self._ensure_plan(rows)
+        partial, n_tiles, bias = ctypes.c_void_p(), ctypes.c_int32(), ctypes.c_void_p()
+        rc = self._lib.ttl_actor_head_partial(self._plan, ctypes.byref(partial), ctypes.byref(n_tiles),
+                                              ctypes.byref(bias))
+        if rc != 0:
+            return None
+        lay = 0
+        if layout is not None and layout[0] == 1:
+            lay = 1
+            if self._plan_layout != tuple(layout):
+                _lib.check(self._lib.ttl_actor_plan_set_layout(
+                    self._plan, int(layout[1]), int(layout[2]), int(layout[3]),
+                    _lib.stream_ptr(self.device)), 'ttl_actor_plan_set_layout')
+                self._plan_layout = tuple(layout)
+        if rows > 0:
+            _lib.check(self._lib.ttl_actor_forward_packed(
+                self._plan, _lib.ptr(state_bf16), int(state_bf16.stride(0)), int(state_bf16.shape[0]),
+                _lib.ptr(n_rows_dev), rows, 0.0, None, None, None, None, lay,
+                _lib.stream_ptr(self.device)), 'ttl_actor_forward_packed')
+        self._keep = (state_bf16, None)
+        return partial.value, int(n_tiles.value), bias.value
+
     def __call__(self, state, probabilistic):
         """Reference: MaxEntropyActor.forward (offpolicy.py:94-140) -> (pi_action, logp_pi)."""
         action, logp, _ = self.forward_device(state, probabilistic)

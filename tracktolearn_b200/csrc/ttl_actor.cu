@@ -447,28 +447,38 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       float hp[HEAD_OUT > 0 ? HEAD_OUT : 1];
 #pragma unroll
       for (int o = 0; o < (HEAD_OUT > 0 ? HEAD_OUT : 1); ++o) hp[o] = 0.f;
-#pragma unroll 1
+      // Software-pipelined over the 8 column chunks of 32: the tcgen05.ld of chunk ch+1 is in flight
+      // while chunk ch gets its bias / ReLU / bf16 packing and leaves as 32-byte stores (whole
+      // sectors; 16-byte stores left every sector half written until the next instruction).
+      const int n_ch = min(BN / 32, (n_pad - n_blk * BN + 31) / 32);   // warp-uniform
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const bool wide_st = ((ldc & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0);
+      uint32_t v[2][32];
+      if (n_ch > 0 && !(relu & 4)) tc_ld32(t_row, v[0]);
+      // (the head variant carries 192 extra FMAs per chunk: unrolled by two it keeps v[] in registers
+      // without an 8x copy of that body)
+#pragma unroll(HEAD_OUT > 0 ? 2 : BN / 32)
       for (int ch = 0; ch < BN / 32; ++ch) {
+        if (ch >= n_ch || (relu & 4)) break;
         const int col0 = n_blk * BN + ch * 32;
-        if (col0 >= n_pad) break;  // warp-uniform
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
-        tc_wait_ld();
+        uint32_t (&cur)[32] = v[ch & 1];
+        tc_wait_ld_regs(cur);
+        if (ch + 1 < n_ch) tc_ld32(t_row + (uint32_t)((ch + 1) * 32), v[(ch + 1) & 1]);
         float x[32];
         if (bias_in_smem) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j);
-            x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-            x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-            x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-            x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+            x[4 * j + 0] = __uint_as_float(cur[4 * j + 0]) + b4.x;
+            x[4 * j + 1] = __uint_as_float(cur[4 * j + 1]) + b4.y;
+            x[4 * j + 2] = __uint_as_float(cur[4 * j + 2]) + b4.z;
+            x[4 * j + 3] = __uint_as_float(cur[4 * j + 3]) + b4.w;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __ldg(bias + col0 + j);
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(cur[j]) + __ldg(bias + col0 + j);
         }
-        if (relu) {
+        if (relu & 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
         }
@@ -485,17 +495,22 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
               hp[o] = fmaf(x[4 * j + 3], w4.w, hp[o]);
             }
           }
-        } else if (row_ok) {
+        } else if (row_ok && !(relu & 2)) {
           uint32_t packed[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
             packed[j] = *reinterpret_cast<uint32_t*>(&h);
           }
-          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+          if (wide_st) {
+            st_global_v8(crow + col0, packed);
+            st_global_v8(crow + col0 + 16, packed + 8);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(crow + col0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
         }
       }
       if (HEAD_OUT > 0 && row_ok) {
@@ -940,6 +955,7 @@ int run_bf16_layers(ttl_actor_plan* p, const CUtensorMap& map_a0, const int32_t*
                                fused ? w.w[nl - 1] : nullptr, k_last, fused ? p->head_partial : nullptr);
     if (rc) return rc;
   }
+  if (p->fuse_head && !action) return 0;   // the caller reads the partial sums (ttl_actor_head_partial)
   if (p->fuse_head) {
     TTL_LAUNCH("head_finish_kernel", s,
                head_finish_kernel<<<ttl_div_up(n_rows_max, 256), 256, 0, s>>>(
@@ -1075,7 +1091,8 @@ int ttl_actor_forward_packed(ttl_actor_plan* p, const void* state_bf16, int32_t 
                              const int32_t* n_rows_dev, int32_t n_rows_max, float probabilistic,
                              const float* eps, float* action, float* logp, float* pre, int32_t layout,
                              void* stream) {
-  if (!p || !state_bf16 || !action || n_rows_max > p->max_rows || n_rows_max > rows_alloc) return TTL_ERR_BAD_ARG;
+  if (!p || !state_bf16 || n_rows_max > p->max_rows || n_rows_max > rows_alloc) return TTL_ERR_BAD_ARG;
+  if (!action && (logp || pre || eps || !p->fuse_head)) return TTL_ERR_BAD_ARG;
   if (layout != 0 && !(layout == 1 && p->has_alt)) return TTL_ERR_BAD_ARG;
   if (ld != p->k_pad[0] || (reinterpret_cast<uintptr_t>(state_bf16) & 15)) return TTL_ERR_BAD_ARG;
   if (probabilistic != 0.f && !eps) return TTL_ERR_BAD_ARG;
@@ -1095,6 +1112,17 @@ int ttl_actor_forward_packed(ttl_actor_plan* p, const void* state_bf16, int32_t 
   }
   return run_bf16_layers(p, *map, n_rows_dev, n_rows_max, probabilistic, eps, action, logp, pre,
                          (cudaStream_t)stream, layout == 1);
+}
+
+int ttl_actor_head_partial(const ttl_actor_plan* p, const float** partial, int32_t* n_tiles,
+                           const float** bias) {
+  if (!p || !partial || !n_tiles || !bias) return TTL_ERR_BAD_ARG;
+  if (!p->fuse_head) return TTL_ERR_UNSUPPORTED;
+  const int nl = p->w.n_layers;
+  *partial = p->head_partial;
+  *n_tiles = ttl_div_up(p->n_pad[nl - 2], BN);
+  *bias = p->w.b[nl - 1];
+  return 0;
 }
 
 int ttl_actor_plan_set_layout(ttl_actor_plan* p, int32_t C, int32_t CP, int32_t n_points, void* stream) {

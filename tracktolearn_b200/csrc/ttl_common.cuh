@@ -37,6 +37,37 @@ void ttl_prof_end(cudaStream_t s);
 
 static inline int ttl_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------
+// The kernels of one tracking step form a chain on one stream.  Launched with the programmatic
+// stream-serialization attribute, kernel N+1 is set up (and its CTAs become resident as kernel N's
+// drain) while kernel N is still running; it blocks in ttl_grid_dep_wait() until kernel N has
+// completed and its writes are visible.  Every kernel of the chain waits before its first global
+// access and releases its dependents right after, so by induction all earlier kernels are complete
+// when a wait returns.  Both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void ttl_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ttl_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// 1 (default): step kernels are launched with the attribute; ttl_pdl_enable(0) turns it off.
+extern std::atomic<int> g_ttl_pdl;
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ttl_launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_ttl_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 __device__ __forceinline__ uint32_t ttl_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

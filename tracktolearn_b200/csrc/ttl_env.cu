@@ -279,6 +279,28 @@ __device__ float alignment_reward(const ttl_volume& v, const float* P, int L) {
   return r;
 }
 
+// Per-rank record of an alive list (ttl_batch.rank_rec): {row, points so far, tip, point before the
+// tip (zeros when there is none)}.  One aligned 32-byte load gives a step kernel everything it would
+// otherwise chase through alive[] -> npts[] -> points[] (three dependent random loads).
+struct RankRec {
+  int row, L;
+  float tx, ty, tz, px, py, pz;
+};
+__device__ __forceinline__ void write_rank_rec(float* base, int rank, int row, int L, float tx, float ty,
+                                               float tz, float px, float py, float pz) {
+  float4* d = reinterpret_cast<float4*>(base) + 2 * (size_t)rank;
+  d[0] = make_float4(__int_as_float(row), __int_as_float(L), tx, ty);
+  d[1] = make_float4(tz, px, py, pz);
+}
+__device__ __forceinline__ RankRec read_rank_rec(const float* base, int rank) {
+  const float4* d = reinterpret_cast<const float4*>(base) + 2 * (size_t)rank;
+  const float4 a = __ldg(d), c = __ldg(d + 1);
+  RankRec r;
+  r.row = __float_as_int(a.x); r.L = __float_as_int(a.y);
+  r.tx = a.z; r.ty = a.w; r.tz = c.x; r.px = c.y; r.py = c.z; r.pz = c.w;
+  return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // K0: reset
 // ------------------------------------------------------------------------------------------
@@ -310,6 +332,7 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
   P[0] = (float)seeds[3 * i + 0];
   P[1] = (float)seeds[3 * i + 1];
   P[2] = (float)seeds[3 * i + 2];
+  if (i < n0) write_rank_rec(b.rank_rec[0], i, i, 1, P[0], P[1], P[2], 0.f, 0.f, 0.f);
   b.flags[i] = 0;
   b.lengths[i] = 1;
   b.npts[i] = 1;
@@ -323,7 +346,7 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
 __device__ void compaction_bookkeeping(const ttl_batch& b, const ttl_params& prm, int cur, int n_alive,
                                        int stopped) {
   __shared__ int s_is_last;
-  __shared__ int s_part[kK1Threads];
+  __shared__ int s_part[kK1Threads / 32];
   const int grp_stops = __syncthreads_count(stopped);
   if (threadIdx.x == 0) {
     b.grp_stops[blockIdx.x] = grp_stops;
@@ -334,31 +357,62 @@ __device__ void compaction_bookkeeping(const ttl_batch& b, const ttl_params& prm
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
+  // Thread t owns the contiguous groups [g0, g1).  Up to kScanUnroll groups per thread are loaded
+  // as independent L2 reads and kept in registers (50 000 slots: 1563 groups, 13 per thread), so
+  // the serial tail of the step is one load latency + one block scan.
+  constexpr int kScanUnroll = 16;
   const int ngrp = gridDim.x;
   const int per = (ngrp + kK1Threads - 1) / kK1Threads;
   const int g0 = min(ngrp, (int)threadIdx.x * per), g1 = min(ngrp, g0 + per);
+  int surv[kScanUnroll];
   int keep = 0;
-  for (int g = g0; g < g1; ++g) {
-    const int rows = max(0, min(kGroup, n_alive - g * kGroup));
-    keep += rows - __ldcg(b.grp_stops + g);
+  if (per <= kScanUnroll) {
+#pragma unroll
+    for (int u = 0; u < kScanUnroll; ++u) {
+      const int g = g0 + u;
+      surv[u] = g < g1 ? __ldcg(b.grp_stops + g) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kScanUnroll; ++u) {
+      const int g = g0 + u;
+      surv[u] = g < g1 ? max(0, min(kGroup, n_alive - g * kGroup)) - surv[u] : 0;
+      keep += surv[u];
+    }
+  } else {
+    for (int g = g0; g < g1; ++g) keep += max(0, min(kGroup, n_alive - g * kGroup)) - __ldcg(b.grp_stops + g);
   }
-  s_part[threadIdx.x] = keep;
+  // block-wide inclusive scan of `keep`: shuffles inside the warp, warp totals through shared memory
+  int incl = keep;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((int)(threadIdx.x & 31) >= off) incl += a;
+  }
+  if ((threadIdx.x & 31) == 31) s_part[threadIdx.x >> 5] = incl;
   __syncthreads();
-  for (int off = 1; off < kK1Threads; off <<= 1) {
-    int a = 0;
-    if ((int)threadIdx.x >= off) a = s_part[threadIdx.x - off];
-    __syncthreads();
-    s_part[threadIdx.x] += a;
-    __syncthreads();
+  int warp_off = 0, total_keep_all = 0;
+#pragma unroll
+  for (int w = 0; w < kK1Threads / 32; ++w) {
+    const int tw = s_part[w];
+    if (w < (int)(threadIdx.x >> 5)) warp_off += tw;
+    total_keep_all += tw;
   }
-  int pos = s_part[threadIdx.x] - keep;
-  for (int g = g0; g < g1; ++g) {
-    b.grp_prefix[g] = pos;
-    const int rows = max(0, min(kGroup, n_alive - g * kGroup));
-    pos += rows - __ldcg(b.grp_stops + g);
+  int pos = warp_off + incl - keep;
+  if (per <= kScanUnroll) {
+#pragma unroll
+    for (int u = 0; u < kScanUnroll; ++u) {
+      const int g = g0 + u;
+      if (g < g1) b.grp_prefix[g] = pos;
+      pos += surv[u];
+    }
+  } else {
+    for (int g = g0; g < g1; ++g) {
+      b.grp_prefix[g] = pos;
+      pos += max(0, min(kGroup, n_alive - g * kGroup)) - __ldcg(b.grp_stops + g);
+    }
   }
   if (threadIdx.x == kK1Threads - 1) {
-    const int total_keep = s_part[kK1Threads - 1];
+    const int total_keep = total_keep_all;
     const int cursor = b.ctrl[6];
     int n_new = 0;
     if (prm.refill) n_new = max(0, min(b.n_slots - total_keep, b.n - cursor));
@@ -378,9 +432,22 @@ __device__ void compaction_bookkeeping(const ttl_batch& b, const ttl_params& prm
 // ------------------------------------------------------------------------------------------
 // K1: propagate + stopping criteria + reward, one thread per alive streamline
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kK1Threads) propagate_stop_kernel(
-    ttl_volume v, ttl_params prm, ttl_batch b, int cur, const float* __restrict__ actions,
-    int lda, const double* __restrict__ noise, int defer) {
+// Where the actions come from.  partial != NULL: straight from the actor's fused head
+// (ttl_actor_head_partial): action = tanh(sum_t partial[r][t][0..2] + bias[0..2]), the deterministic
+// policy (prob = 0) -- the same additions in the same order as the actor's own head_finish kernel,
+// so both routes give the same bits; this one saves a launch and a round trip through HBM.
+struct ActionSrc {
+  const float* actions;   // [n_alive][lda] fp32
+  int lda;
+  const float* partial;   // [n_alive][n_tiles][8] fp32 per-n-tile partial sums of the 6-wide head
+  int n_tiles;
+  const float* bias;      // head bias
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(kK1Threads, MINB) propagate_stop_kernel(
+    ttl_volume v, ttl_params prm, ttl_batch b, int cur, ActionSrc src,
+    const double* __restrict__ noise, int defer) {
   // 4 lanes per streamline: they redo the cheap scalar work together and split the spline taps
   const int lane = threadIdx.x & 31, sub = threadIdx.x & (kLanesPerRow - 1);
   const unsigned quad_mask = 0xFu << (lane & ~(kLanesPerRow - 1));
@@ -388,12 +455,28 @@ __global__ void __launch_bounds__(kK1Threads) propagate_stop_kernel(
   const int n_alive = b.ctrl[cur];
   int stopped = 0;
   if (r < n_alive) {
-  const int i = b.alive[cur][r];
-  const int L = b.npts[i];  // points so far in this row
+  // everything this rank needs arrives with two independent loads (record + action)
+  const RankRec rec = read_rank_rec(b.rank_rec[cur], r);
+  float ax, ay, az;
+  if (src.partial) {
+    const float4* hp = reinterpret_cast<const float4*>(src.partial + (size_t)r * src.n_tiles * 8);
+    ax = 0.f; ay = 0.f; az = 0.f;
+    for (int t = 0; t < src.n_tiles; ++t) {
+      const float4 pt = __ldg(hp + 2 * t);
+      ax += pt.x; ay += pt.y; az += pt.z;
+    }
+    ax = tanhf(ax + __ldg(src.bias + 0));
+    ay = tanhf(ay + __ldg(src.bias + 1));
+    az = tanhf(az + __ldg(src.bias + 2));
+  } else {
+    ax = src.actions[(size_t)r * src.lda + 0];
+    ay = src.actions[(size_t)r * src.lda + 1];
+    az = src.actions[(size_t)r * src.lda + 2];
+  }
+  const int i = rec.row;
+  const int L = rec.L;  // points so far in this row
   float* P = b.points + (size_t)i * b.max_pts * 3;
-  const float px = P[(L - 1) * 3 + 0], py = P[(L - 1) * 3 + 1], pz = P[(L - 1) * 3 + 2];
-  const float ax = actions[(size_t)r * lda + 0], ay = actions[(size_t)r * lda + 1],
-              az = actions[(size_t)r * lda + 2];
+  const float px = rec.tx, py = rec.ty, pz = rec.tz;
 
   float qx, qy, qz;  // the new point
   if (prm.dir_f64) {
@@ -442,9 +525,7 @@ __global__ void __launch_bounds__(kK1Threads) propagate_stop_kernel(
   float last3[9];
   last3[6] = qx; last3[7] = qy; last3[8] = qz;
   last3[3] = px; last3[4] = py; last3[5] = pz;
-  last3[0] = L >= 2 ? P[(L - 2) * 3 + 0] : 0.f;
-  last3[1] = L >= 2 ? P[(L - 2) * 3 + 1] : 0.f;
-  last3[2] = L >= 2 ? P[(L - 2) * 3 + 2] : 0.f;
+  last3[0] = rec.px; last3[1] = rec.py; last3[2] = rec.pz;   // zeros while L < 2
   int f = 0;
   if (Ln >= prm.max_nb_steps) f |= TTL_STOPPING_LENGTH;
   if (Ln >= 3 && too_curvy(last3, prm.theta_rad)) f |= TTL_STOPPING_CURVATURE;
@@ -457,6 +538,7 @@ __global__ void __launch_bounds__(kK1Threads) propagate_stop_kernel(
   }
   if (sub == 0) {
     P[L * 3 + 0] = qx; P[L * 3 + 1] = qy; P[L * 3 + 2] = qz;
+    reinterpret_cast<float4*>(b.step_tip)[r] = make_float4(qx, qy, qz, 0.f);
     b.npts[i] = Ln;
     b.step_flags[r] = f;
     b.stop[r] = f != 0;
@@ -558,9 +640,9 @@ __device__ __forceinline__ float4 ldg_nc_v4(const float4* p) {
 
 // phase 0 shared by both paths: lane i (and i+32) owns corner i = 8*p + c of the 7-point
 // neighbourhood (order env.py:210-213: 0, +x, +y, +z, -x, -y, -z): voxel index and weight.
-__device__ __forceinline__ void corner_table(const ttl_volume& v, const ttl_params& prm, const float* tip,
+__device__ __forceinline__ void corner_table(const ttl_volume& v, const ttl_params& prm, float3 tip,
                                              float* s_w, int* s_vox, int lane) {
-  const float tx = tip[0], ty = tip[1], tz = tip[2];
+  const float tx = tip.x, ty = tip.y, tz = tip.z;
   const float rad = (float)prm.step_vox;  // env.py:207-213, float32 neighbourhood vectors
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
@@ -587,12 +669,33 @@ __device__ __forceinline__ void corner_table(const ttl_volume& v, const ttl_para
   }
 }
 
+// Lane i (and i+32) asks the memory system for the two 128-byte lines of its corner voxel (a
+// 192-byte voxel always straddles exactly two lines): all ~52 distinct lines of a row are in
+// flight at once without holding a register each, and the LDG.128 gathers that follow wait one
+// latency instead of one per batch of loads.  level 1: into L1, 2: into L2.
+__device__ __forceinline__ void prefetch_corners(const ttl_volume& v, const int* s_vox, int lane, int level) {
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int i = lane + 32 * rep;
+    if (i < 56) {
+      const char* a = reinterpret_cast<const char*>(v.sh) + (size_t)s_vox[i] * v.CP * 4;
+      if (level == 1) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 128));
+      } else {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
+      }
+    }
+  }
+}
+
 // Builds one state row for the streamline whose points start at P (L points) and writes
 //   out_f32 [0, n_f32)   fp32: 7*C SH values | 3*n_dirs previous directions | zero padding
 //   out_bf16 [0, n_bf16) the same values rounded to bf16 (actor operand), zero padded
 // smem_f: this warp's private staging area (kWarpSmemBytes).  All 32 lanes participate.
 // Generic channel count: lane l produces elements l, l+32, ... with scalar gathers.
-__device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
+__device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& prm, const float* P, int L, float3 tip,
                                         float* __restrict__ out_f32, int n_f32,
                                         __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f,
                                         int lane) {
@@ -600,7 +703,7 @@ __device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& p
   int* s_vox = reinterpret_cast<int*>(smem_f + 64);
   float* s_pts = smem_f + 128;
   const int C = v.C, CP = v.CP;
-  corner_table(v, prm, P + (size_t)(L - 1) * 3, s_w, s_vox, lane);
+  corner_table(v, prm, tip, s_w, s_vox, lane);
   const int nd = prm.n_dirs;
   const int npts = min(L, nd + 1);
   const float* src = P + (size_t)(L - npts) * 3;
@@ -641,7 +744,7 @@ __device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& p
 // warps fit on an SM.  The finished row leaves through shared memory as 16-byte stores.
 // (A cp.async-staged variant that parked all 56 corner voxels in shared memory first was
 // measured at 172 us/step at 50 000 rows: 12.5 KB/warp capped the SM at 16 warps.)
-__device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
+__device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, const float* P, int L, float3 tip,
                                     float* __restrict__ out_f32, int n_f32,
                                     __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f, int lane) {
   constexpr int C = 45, CP4 = 12, S = 7 * C;
@@ -649,7 +752,7 @@ __device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, 
   int* s_vox = reinterpret_cast<int*>(smem_f + 64);     // [56] voxel index
   float* s_pts = smem_f + 128;                          // [(n_dirs+1)*3]
   float* s_row = smem_f + 128 + kMaxDirPts * 3;         // [640] output row
-  corner_table(v, prm, P + (size_t)(L - 1) * 3, s_w, s_vox, lane);
+  corner_table(v, prm, tip, s_w, s_vox, lane);
   const int nd = prm.n_dirs;
   const int npts = min(L, nd + 1);
   const float* src = P + (size_t)(L - npts) * 3;
@@ -723,12 +826,14 @@ __device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, 
 // as the actor's first-layer operand.  Point p owns columns [48p, 48p+48) so every (point, chunk)
 // work item converts its float4 to 4 bf16 and stores 8 aligned bytes from registers; previous
 // directions follow at column 336.  No row staging: 512 B of shared memory per warp.
-__device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& prm, const float* P, int L,
-                                         __nv_bfloat16* __restrict__ out, int n_bf16, float* smem_f, int lane) {
+__device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& prm, const float* P, int L, float3 tip,
+                                         __nv_bfloat16* __restrict__ out, int n_bf16, float* smem_f, int lane,
+                                         int pf = 0) {
   constexpr int CP = 48, CP4 = 12, S = 7 * CP;
   float* s_w = smem_f;
   int* s_vox = reinterpret_cast<int*>(smem_f + 64);
-  corner_table(v, prm, P + (size_t)(L - 1) * 3, s_w, s_vox, lane);
+  corner_table(v, prm, tip, s_w, s_vox, lane);
+  if (pf) prefetch_corners(v, s_vox, lane, pf);   // own entries: no __syncwarp needed first
   __syncwarp();
   const float4* vol4 = reinterpret_cast<const float4*>(v.sh);
   // all 24 gathers of this lane's three work items are issued before the first is consumed
@@ -785,18 +890,19 @@ __device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& 
   }
 }
 
+// tip = P[L-1] (passed by value so a caller that already holds it skips the dependent load)
 __device__ __forceinline__ void build_state_row(const ttl_volume& v, const ttl_params& prm, const float* P,
-                                                int L, float* __restrict__ out_f32, int n_f32,
+                                                int L, float3 tip, float* __restrict__ out_f32, int n_f32,
                                                 __nv_bfloat16* __restrict__ out_bf16, int n_bf16,
                                                 float* smem_f, int lane, int layout = 0) {
   if (layout == 1) {   // host guarantees C == 45, CP == 48, no fp32 row
-    build_state_row_c45_bf16(v, prm, P, L, out_bf16, n_bf16, smem_f, lane);
+    build_state_row_c45_bf16(v, prm, P, L, tip, out_bf16, n_bf16, smem_f, lane);
     return;
   }
   if (v.C == 45 && v.CP == 48 && max(n_f32, n_bf16) <= kMaxStateLd)
-    build_state_row_c45(v, prm, P, L, out_f32, n_f32, out_bf16, n_bf16, smem_f, lane);
+    build_state_row_c45(v, prm, P, L, tip, out_f32, n_f32, out_bf16, n_bf16, smem_f, lane);
   else
-    build_state_row_generic(v, prm, P, L, out_f32, n_f32, out_bf16, n_bf16, smem_f, lane);
+    build_state_row_generic(v, prm, P, L, tip, out_f32, n_f32, out_bf16, n_bf16, smem_f, lane);
 }
 
 // rank r of the old alive list -> (number of survivors before r); all lanes return the value.
@@ -811,21 +917,30 @@ __device__ __forceinline__ int survivors_before(const ttl_batch& b, int r, int n
 // ptxas keeps 4 in flight to stay at 47 registers.
 template <int FAST>
 __global__ void __launch_bounds__(kStateWarps * 32, FAST ? 6 : 1) build_state_kernel(ttl_volume v, ttl_params prm,
-                                                                                     ttl_batch b, int cur, int warp_smem) {
+                                                                                     ttl_batch b, int cur, int warp_smem,
+                                                                                     int pf) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * warp_smem);
   const int r = blockIdx.x * kStateWarps + warp;
   const int n_old = b.ctrl[3];
   if (r >= n_old) return;
+  // independent loads first: stop flags / group prefix (rank), this rank's record and new point
+  const RankRec rec = read_rank_rec(b.rank_rec[cur], r);
+  const float4 q = __ldg(reinterpret_cast<const float4*>(b.step_tip) + r);
   const int keep_before = survivors_before(b, r, n_old, lane);
   const bool stopped = b.stop[r] != 0;
   int row, dst, L;
+  float3 tip = make_float3(q.x, q.y, q.z);
   if (!stopped) {
-    row = b.alive[cur][r];
+    row = rec.row;
     dst = keep_before;
-    L = b.npts[row];
-    if (lane == 0) { b.alive[cur ^ 1][dst] = row; b.dest[r] = dst; }
+    L = rec.L + 1;
+    if (lane == 0) {
+      b.alive[cur ^ 1][dst] = row;
+      b.dest[r] = dst;
+      write_rank_rec(b.rank_rec[cur ^ 1], dst, row, L, q.x, q.y, q.z, rec.tx, rec.ty, rec.tz);
+    }
   } else {
     const int total_keep = b.ctrl[8];
     const int j = r - keep_before;        // how many stopped before this rank
@@ -834,10 +949,15 @@ __global__ void __launch_bounds__(kStateWarps * 32, FAST ? 6 : 1) build_state_ke
     if (j < b.ctrl[9]) {                  // streaming refill: this freed slot takes a fresh seed
       row = b.ctrl[10] + j;
       L = 1;
-      if (lane == 0) b.alive[cur ^ 1][dst] = row;
+      const float* S = b.points + (size_t)row * b.max_pts * 3;
+      tip = make_float3(S[0], S[1], S[2]);
+      if (lane == 0) {
+        b.alive[cur ^ 1][dst] = row;
+        write_rank_rec(b.rank_rec[cur ^ 1], dst, row, 1, tip.x, tip.y, tip.z, 0.f, 0.f, 0.f);
+      }
     } else if (prm.state_stopped) {       // parity mode: state of the streamline that just stopped
-      row = b.alive[cur][r];
-      L = b.npts[row];
+      row = rec.row;
+      L = rec.L + 1;
     } else {
       return;
     }
@@ -848,9 +968,9 @@ __global__ void __launch_bounds__(kStateWarps * 32, FAST ? 6 : 1) build_state_ke
                            : nullptr;
   float* o32 = b.state[cur ^ 1] ? b.state[cur ^ 1] + (size_t)dst * b.ld_state : nullptr;
   if (FAST)
-    build_state_row_c45_bf16(v, prm, P, L, o16, b.ld_bf16, smem_f, lane);
+    build_state_row_c45_bf16(v, prm, P, L, tip, o16, b.ld_bf16, smem_f, lane, pf);
   else
-    build_state_row(v, prm, P, L, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
+    build_state_row(v, prm, P, L, tip, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
 }
 
 // reset: alive[0] = identity, state goes to state[0]
@@ -866,7 +986,8 @@ __global__ void __launch_bounds__(kStateWarps * 32) reset_state_kernel(ttl_volum
                            ? reinterpret_cast<__nv_bfloat16*>(b.state_bf16[0]) + (size_t)r * b.ld_bf16
                            : nullptr;
   float* o32 = b.state[0] ? b.state[0] + (size_t)r * b.ld_state : nullptr;
-  build_state_row(v, prm, P, 1, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
+  build_state_row(v, prm, P, 1, make_float3(P[0], P[1], P[2]), o32, b.ld_state, o16, b.ld_bf16, smem_f, lane,
+                  b.bf16_layout);
 }
 
 // stand-alone _format_state for arbitrary streamlines [n][L][3]
@@ -879,7 +1000,9 @@ __global__ void __launch_bounds__(kStateWarps * 32) format_state_kernel(ttl_volu
   const int r = blockIdx.x * kStateWarps + warp;
   if (r >= n) return;
   const int S = 7 * v.C + 3 * prm.n_dirs;
-  build_state_row(v, prm, points + (size_t)r * L * 3, L, out + (size_t)r * ld_out, S, nullptr, 0, smem_f, lane);
+  const float* P = points + (size_t)r * L * 3;
+  const float* T = P + (size_t)(L - 1) * 3;
+  build_state_row(v, prm, P, L, make_float3(T[0], T[1], T[2]), out + (size_t)r * ld_out, S, nullptr, 0, smem_f, lane);
 }
 
 __global__ void stopping_flags_kernel(ttl_volume v, ttl_params prm, const float* points, int n, int L,
@@ -988,6 +1111,10 @@ int check_common(const ttl_volume* vol, const ttl_params* prm) {
 // bf16_layout 1 needs the order-8 volume and room for 7*48 + 3*n_dirs columns; without fp32 rows
 // the bf16 rows must exist
 int check_layout(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b) {
+  if (!b->rank_rec[0] || !b->rank_rec[1] || !b->step_tip) return TTL_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(b->rank_rec[0]) | reinterpret_cast<uintptr_t>(b->rank_rec[1]) |
+       reinterpret_cast<uintptr_t>(b->step_tip)) & 15)
+    return TTL_ERR_BAD_ARG;
   if (b->bf16_layout == 0) return (b->state[0] && b->state[1]) ? 0 : TTL_ERR_BAD_ARG;
   if (b->bf16_layout != 1) return TTL_ERR_BAD_ARG;
   if (vol->C != 45 || vol->CP != 48) return TTL_ERR_UNSUPPORTED;
@@ -1039,32 +1166,108 @@ int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch*
   return 0;
 }
 
-int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
-                 const float* actions, int32_t lda, const double* noise, int32_t n_upper,
-                 void* stream) {
-  int rc = check_common(vol, prm);
+// propagate_stop_kernel is latency-bound (a short dependent chain per streamline and ~90 registers
+// of fp64 spline state): how many 128-thread CTAs share an SM decides how many waves 50 000 rows
+// take.  Instantiations for 5 (94 registers, what ptxas picks unconstrained), 6 (80) and 8 (64, a
+// few spilled doubles) CTAs per SM; TTL_K1_MINB selects one for experiments, default below.
+static int k1_min_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TTL_K1_MINB");
+    v = e ? atoi(e) : 6;
+    if (v != 5 && v != 6 && v != 8) v = 6;
+  }
+  return v;
+}
+
+static void launch_propagate(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int cur,
+                             const ActionSrc& src, const double* noise, int defer, int n_upper, cudaStream_t s) {
+  const int grid = ttl_div_up(n_upper, kGroup);
+  switch (k1_min_blocks()) {
+    case 5:
+      TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<5><<<grid, kK1Threads, 0, s>>>(*vol, *prm, *b, cur, src, noise, defer));
+      break;
+    case 8:
+      TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<8><<<grid, kK1Threads, 0, s>>>(*vol, *prm, *b, cur, src, noise, defer));
+      break;
+    default:
+      TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<6><<<grid, kK1Threads, 0, s>>>(*vol, *prm, *b, cur, src, noise, defer));
+  }
+}
+
+static int state_prefetch_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TTL_STATE_PREFETCH");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
+  }
+  return v;
+}
+
+static int launch_build_state(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int cur,
+                              int n_upper, cudaStream_t s) {
+  int rc = state_kernels_ready();
   if (rc) return rc;
-  if (!b || !actions || lda < 3 || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
-  if (prm->compute_reward && !vol->peaks && prm->alignment_weighting > 0) return TTL_ERR_BAD_ARG;
-  if (prm->refill && prm->state_stopped) return TTL_ERR_BAD_ARG;
-  rc = check_layout(vol, prm, b);
-  if (rc) return rc;
-  if (n_upper <= 0) return 0;
-  if (n_upper > b->n_slots) n_upper = b->n_slots;
-  if (ttl_div_up(n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->grp_prefix) return TTL_ERR_BAD_ARG;
-  cudaStream_t s = (cudaStream_t)stream;
-  TTL_LAUNCH("propagate_stop_kernel", s, propagate_stop_kernel<<<ttl_div_up(n_upper, kGroup), kK1Threads, 0, s>>>(*vol, *prm, *b, cur, actions, lda, noise, 0));
-  rc = state_kernels_ready();
-  if (rc) return rc;
+  // the bf16-only path keeps just the corner table in shared memory: a small allocation leaves
+  // the SM's 228 KB to L1, which is what dedupes the overlapping trilinear corners
   const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;
   if (b->bf16_layout == 1)
     TTL_LAUNCH("build_state_kernel", s,
                build_state_kernel<1><<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
-                   *vol, *prm, *b, cur, warp_smem));
+                   *vol, *prm, *b, cur, warp_smem, state_prefetch_level()));
   else
     TTL_LAUNCH("build_state_kernel", s,
                build_state_kernel<0><<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
-                   *vol, *prm, *b, cur, warp_smem));
+                   *vol, *prm, *b, cur, warp_smem, 0));
+  return 0;
+}
+
+static int check_step_args(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                           int32_t* n_upper) {
+  int rc = check_common(vol, prm);
+  if (rc) return rc;
+  if (!b || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
+  if (prm->compute_reward && !vol->peaks && prm->alignment_weighting > 0) return TTL_ERR_BAD_ARG;
+  if (prm->refill && prm->state_stopped) return TTL_ERR_BAD_ARG;
+  rc = check_layout(vol, prm, b);
+  if (rc) return rc;
+  if (*n_upper > b->n_slots) *n_upper = b->n_slots;
+  if (*n_upper > 0 && (ttl_div_up(*n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->grp_prefix ||
+                       !b->rank_rec[0] || !b->rank_rec[1] || !b->step_tip))
+    return TTL_ERR_BAD_ARG;
+  return 0;
+}
+
+int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                 const float* actions, int32_t lda, const double* noise, int32_t n_upper,
+                 void* stream) {
+  if (!actions || lda < 3) return TTL_ERR_BAD_ARG;
+  int rc = check_step_args(vol, prm, b, cur, &n_upper);
+  if (rc) return rc;
+  if (n_upper <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const ActionSrc src = {actions, lda, nullptr, 0, nullptr};
+  launch_propagate(vol, prm, b, cur, src, noise, 0, n_upper, s);
+  rc = launch_build_state(vol, prm, b, cur, n_upper, s);
+  if (rc) return rc;
+  TTL_CHECK_LAST();
+  return 0;
+}
+
+int ttl_env_step_head(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
+                      const float* head_partial, int32_t n_tiles, const float* head_bias,
+                      int32_t n_upper, void* stream) {
+  if (!head_partial || !head_bias || n_tiles < 1 || (reinterpret_cast<uintptr_t>(head_partial) & 15))
+    return TTL_ERR_BAD_ARG;
+  int rc = check_step_args(vol, prm, b, cur, &n_upper);
+  if (rc) return rc;
+  if (n_upper <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const ActionSrc src = {nullptr, 0, head_partial, n_tiles, head_bias};
+  launch_propagate(vol, prm, b, cur, src, nullptr, 0, n_upper, s);
+  rc = launch_build_state(vol, prm, b, cur, n_upper, s);
+  if (rc) return rc;
   TTL_CHECK_LAST();
   return 0;
 }
@@ -1072,20 +1275,13 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
 int ttl_env_step_begin(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
                        const float* actions, int32_t lda, const double* noise, int32_t n_upper,
                        void* stream) {
-  int rc = check_common(vol, prm);
-  if (rc) return rc;
-  if (!b || !actions || lda < 3 || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
-  if (prm->compute_reward && !vol->peaks && prm->alignment_weighting > 0) return TTL_ERR_BAD_ARG;
-  if (prm->refill && prm->state_stopped) return TTL_ERR_BAD_ARG;
-  rc = check_layout(vol, prm, b);
+  if (!actions || lda < 3) return TTL_ERR_BAD_ARG;
+  int rc = check_step_args(vol, prm, b, cur, &n_upper);
   if (rc) return rc;
   if (n_upper <= 0) return 0;
-  if (n_upper > b->n_slots) n_upper = b->n_slots;
-  if (ttl_div_up(n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->grp_prefix) return TTL_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  TTL_LAUNCH("propagate_stop_kernel", s,
-             propagate_stop_kernel<<<ttl_div_up(n_upper, kGroup), kK1Threads, 0, s>>>(*vol, *prm, *b, cur, actions,
-                                                                                    lda, noise, 1));
+  const ActionSrc src = {actions, lda, nullptr, 0, nullptr};
+  launch_propagate(vol, prm, b, cur, src, noise, 1, n_upper, s);
   TTL_CHECK_LAST();
   return 0;
 }
@@ -1102,17 +1298,8 @@ int ttl_env_step_finish(const ttl_volume* vol, const ttl_params* prm, const ttl_
   TTL_LAUNCH("oracle_apply_kernel", s,
              oracle_apply_kernel<<<ttl_div_up(n_upper, kGroup), kK1Threads, 0, s>>>(
                  *prm, *b, cur, scores, use_stop, min_pts_stop, min_pts_reward, bonus));
-  rc = state_kernels_ready();
+  rc = launch_build_state(vol, prm, b, cur, n_upper, s);
   if (rc) return rc;
-  const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;
-  if (b->bf16_layout == 1)
-    TTL_LAUNCH("build_state_kernel", s,
-               build_state_kernel<1><<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
-                   *vol, *prm, *b, cur, warp_smem));
-  else
-    TTL_LAUNCH("build_state_kernel", s,
-               build_state_kernel<0><<<ttl_div_up(n_upper, kStateWarps), kStateWarps * 32, kStateWarps * warp_smem, s>>>(
-                   *vol, *prm, *b, cur, warp_smem));
   TTL_CHECK_LAST();
   return 0;
 }

@@ -62,6 +62,11 @@ class _BatchBuffers(object):
         self.max_groups = (slots + 31) // 32 + 1
         self.grp_stops = torch.zeros((self.max_groups,), **i32)
         self.grp_prefix = torch.zeros((self.max_groups,), **i32)
+        # per-rank records {row, npts, tip, previous point} of the two alive lists and the points added
+        # by the step in flight (ttl_batch.rank_rec / step_tip)
+        self.rank_rec = [torch.zeros((pad, 8), dtype=torch.float32, device=device),
+                         torch.zeros((pad, 8), dtype=torch.float32, device=device)]
+        self.step_tip = torch.zeros((pad, 4), dtype=torch.float32, device=device)
 
     def as_struct(self, n, n_slots):
         b = _lib.Batch(n=n, n_slots=n_slots, capacity=self.rows, max_pts=self.max_pts,
@@ -75,6 +80,9 @@ class _BatchBuffers(object):
                        grp_stops=self.grp_stops.data_ptr(), grp_prefix=self.grp_prefix.data_ptr())
         b.state_bf16[0] = self.state_bf16[0].data_ptr()
         b.state_bf16[1] = self.state_bf16[1].data_ptr()
+        b.rank_rec[0] = self.rank_rec[0].data_ptr()
+        b.rank_rec[1] = self.rank_rec[1].data_ptr()
+        b.step_tip = self.step_tip.data_ptr()
         b.alive[0] = self.alive[0].data_ptr()
         b.alive[1] = self.alive[1].data_ptr()
         if self.fp32_state:
@@ -188,6 +196,22 @@ class TrackingEnvironment(BaseEnv):
                     _lib.ptr(self._oracle_scores), int(bool(self.oracle_stopping_criterion)),
                     int(self.min_nb_steps * 5), int(self.min_nb_steps), bonus, n_up, sp), 'ttl_env_step_finish')
         self._keep = (actions, noise)
+        self.length += 1
+        self._pending_harvest = True
+
+    def step_device_head(self, head):
+        """``step_device`` with the actions read straight from the actor's fused output layer
+        (``head`` = what ``actor.forward_head_partial`` returned): tanh(mu), the deterministic policy.
+        One launch less per step; same bits as forward_device + step_device."""
+        if self._pending_harvest:
+            raise RuntimeError('step() called twice without harvest()')
+        if self._oracle is not None:
+            raise RuntimeError('step_device_head does not consult the oracle; use step_device')
+        partial, n_tiles, bias = head
+        _lib.check(self._lib.ttl_env_step_head(
+            ctypes.byref(self._volume), ctypes.byref(self._params), ctypes.byref(self._b), self._cur,
+            partial, int(n_tiles), bias, int(self._n_alive_host), _lib.stream_ptr(self.device)),
+            'ttl_env_step_head')
         self.length += 1
         self._pending_harvest = True
 
