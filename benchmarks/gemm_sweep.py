@@ -19,8 +19,8 @@ def main():
     sp = _lib.stream_ptr(dev)
     m, n = 50000, 1024
     out = {}
-    mode = int(os.environ.get('GEMM_DBG', '1'))
-    for k in (128, 640, 1024, 2048):
+    mode = 1
+    for k in (128, 256, 512, 640, 768, 1024, 1536, 2048):
         sets = []
         for _ in range(3):
             A = torch.randn((m, k), device=dev).to(torch.bfloat16)

@@ -112,6 +112,15 @@ typedef struct ttl_batch {
                               chasing alive[] -> npts[] -> points[] (tracking_env.py:181-188 re-slices
                               the streamline buffer for the same purpose) */
   float* step_tip;         /* [n_slots+16][4] per rank of alive[cur]: the point added this step */
+  const int32_t* order;    /* NULL, or a permutation [n] of the rows: the order in which seeds take slots
+                              (slot k of reset gets row order[k]; refills continue from there).  Rows
+                              keep their identity -- results, flags and the output order are per row --
+                              so this only decides which streamlines sit next to each other in the alive
+                              list.  The streaming tracker passes the seeds' voxel raster order: the
+                              reference shuffles its seeds (tracker.py:94), which makes every warp of
+                              the gather touch unrelated voxels; neighbours in the list then share
+                              cache lines.  Must be NULL for the reference protocol (ascending
+                              continue_idx, tracking_env.py:123). */
 } ttl_batch;
 
 /* ---- one-time / load-time helpers ------------------------------------------------------ */
@@ -306,6 +315,11 @@ int64_t ttl_launch_count(void);
  * stream; ttl_prof_report waits for them, writes {"kernel": [launches, total_ms], ...} (JSON)
  * into buf_host and clears the record.  Returns the bytes the full report needs. */
 void ttl_prof_enable(int32_t on);
+/* The kernels of a tracking step (actor layers, propagate/stop, state rows) are launched with the
+ * programmatic stream-serialization attribute so that each is set up while its predecessor drains
+ * (every one of them waits for its predecessor's completion before its first global access).
+ * On by default; 0 switches back to plain stream-ordered launches. */
+void ttl_pdl_enable(int32_t on);
 int32_t ttl_prof_report(char* buf_host, int32_t buflen);
 
 #ifdef __cplusplus

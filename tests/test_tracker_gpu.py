@@ -132,6 +132,31 @@ def test_fused_head_step_is_bit_identical_to_action_round_trip():
     alg.fuse_head = True
 
 
+def test_locality_order_does_not_change_any_streamline():
+    """Streaming tracker with the seeds entering the slots in voxel raster order (ttl_batch.order) vs
+    in row order: every row holds the same streamline, bit for bit, and the output order is the
+    rows' (shuffled) order in both."""
+    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    n = len(seeds)
+    out = []
+    for loc in (False, True):
+        st = env.reset_streaming(0, n, 256, fp32_state=False, locality=loc)
+        assert (env._order_dev is not None) == loc
+        if loc:
+            order = env._order_dev.cpu().numpy()
+            assert sorted(order.tolist()) == list(range(n))
+            first = env._batch.alive[0][:256].cpu().numpy()
+            np.testing.assert_array_equal(first, order[:256])
+        alg.validation_episode(st, env, 0.0)
+        out.append(env.get_streamlines())
+        assert env.streamline_steps() == int((env.lengths - 1).sum())
+    a, b = out
+    np.testing.assert_array_equal(a.lengths, b.lengths)
+    np.testing.assert_array_equal(a.data, b.data)
+    np.testing.assert_array_equal(a.data_per_streamline['flags'], b.data_per_streamline['flags'])
+    np.testing.assert_array_equal(a.data_per_streamline['seeds'], b.data_per_streamline['seeds'])
+
+
 def test_training_episode_rollout_replay_and_update():
     """A3 / config 4: DDPG._episode-style rollout with the tensor-core actor sampling at
     probabilistic=1, transitions pushed to the device replay buffer, one SAC update per env step,

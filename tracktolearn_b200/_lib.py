@@ -32,7 +32,7 @@ class Batch(ctypes.Structure):
                 ('npts', c_vp), ('dones', c_vp), ('alive', c_vp * 2), ('ctrl', c_vp), ('stop', c_vp), ('dest', c_vp),
                 ('step_flags', c_vp), ('reward', c_vp), ('state', c_vp * 2),
                 ('state_bf16', c_vp * 2), ('ld_bf16', c_i32), ('max_groups', c_i32), ('grp_stops', c_vp),
-                ('grp_prefix', c_vp), ('bf16_layout', c_i32), ('rank_rec', c_vp * 2), ('step_tip', c_vp)]
+                ('grp_prefix', c_vp), ('bf16_layout', c_i32), ('rank_rec', c_vp * 2), ('step_tip', c_vp), ('order', c_vp)]
 
 
 class ActorWeights(ctypes.Structure):
@@ -54,6 +54,7 @@ SIGNATURES = {
     'ttl_abi_version': (c_i32, []),
     'ttl_launch_count': (c_i64, []),
     'ttl_prof_enable': (None, [c_i32]),
+    'ttl_pdl_enable': (None, [c_i32]),
     'ttl_prof_report': (c_i32, [ctypes.c_char_p, c_i32]),
     'ttl_pad_channels': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
     'ttl_env_reset': (c_i32, [P(Volume), P(Params), P(Batch), c_vp, c_vp]),
@@ -104,6 +105,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get('TTL_PDL', '1') == '0':      # A/B measurements: plain stream-ordered launches
+        lib.ttl_pdl_enable(0)
     _lib = lib
     return lib
 

@@ -347,11 +347,6 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = cluster_ctarank();       // 0 = leader
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  int m = m_dev ? *m_dev : m_max;
-  m = min(m, m_max);
-  const int n_m = (m + 2 * BM - 1) / (2 * BM), n_n = (n_pad + BN - 1) / BN;
-  const int total = n_m * n_n, kblocks = k_pad / BK;
-
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
@@ -368,6 +363,15 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  // Everything above is independent of earlier kernels (barriers, tensor memory, descriptor prefetch)
+  // and overlaps the predecessor's tail under programmatic dependent launch; from here on we read
+  // what it wrote (row count, activations, freshly packed weights).
+  ttl_grid_dep_wait();
+  int m = m_dev ? *m_dev : m_max;
+  m = min(m, m_max);
+  const int n_m = (m + 2 * BM - 1) / (2 * BM), n_n = (n_pad + BN - 1) / BN;
+  const int total = n_m * n_n, kblocks = k_pad / BK;
+
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - raw));
   float* s_head = s_bias + EXTRA_SMEM_BIAS / 4;
   const bool bias_in_smem = n_pad <= EXTRA_SMEM_BIAS / 4;
@@ -453,17 +457,12 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       const int n_ch = min(BN / 32, (n_pad - n_blk * BN + 31) / 32);   // warp-uniform
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       const bool wide_st = ((ldc & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0);
-      uint32_t v[2][32];
-      if (n_ch > 0 && !(relu & 4)) tc_ld32(t_row, v[0]);
-      // (the head variant carries 192 extra FMAs per chunk: unrolled by two it keeps v[] in registers
-      // without an 8x copy of that body)
-#pragma unroll(HEAD_OUT > 0 ? 2 : BN / 32)
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        if (ch >= n_ch || (relu & 4)) break;
+      uint32_t va[32], vb[32];   // two named buffers: indexing one array by ch & 1 sent it to local memory
+      // one chunk: wait for `cur`, start the load of the next chunk into `nxt`, then convert and store
+      auto do_chunk = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int ch) {
         const int col0 = n_blk * BN + ch * 32;
-        uint32_t (&cur)[32] = v[ch & 1];
         tc_wait_ld_regs(cur);
-        if (ch + 1 < n_ch) tc_ld32(t_row + (uint32_t)((ch + 1) * 32), v[(ch + 1) & 1]);
+        if (ch + 1 < n_ch) tc_ld32(t_row + (uint32_t)((ch + 1) * 32), nxt);
         float x[32];
         if (bias_in_smem) {
 #pragma unroll
@@ -478,7 +477,7 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(cur[j]) + __ldg(bias + col0 + j);
         }
-        if (relu & 1) {
+        if (relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
         }
@@ -495,7 +494,7 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
               hp[o] = fmaf(x[4 * j + 3], w4.w, hp[o]);
             }
           }
-        } else if (row_ok && !(relu & 2)) {
+        } else if (row_ok) {
           uint32_t packed[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -512,6 +511,14 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
               dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
           }
         }
+      };
+      if (n_ch > 0) tc_ld32(t_row, va);
+#pragma unroll(HEAD_OUT > 0 ? 1 : BN / 64)
+      for (int ch = 0; ch < BN / 32; ch += 2) {
+        if (ch >= n_ch) break;
+        do_chunk(va, vb, ch);
+        if (ch + 1 >= n_ch) break;
+        do_chunk(vb, va, ch + 1);
       }
       if (HEAD_OUT > 0 && row_ok) {
         float o8[8];
@@ -838,13 +845,14 @@ int launch_dense_bf16(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     const int grid = 2 * clusters;
     if (head_w) {
       TTL_LAUNCH("dense_bf16_head_kernel", s,
-                 dense_bf16_2cta_kernel<HEAD_OUT_FUSED><<<grid, GEMM_THREADS,
-                                                          GEMM2_SMEM + EXTRA_SMEM_BIAS + HEAD_OUT_FUSED * n_pad * 4, s>>>(
-                     ta, tb2, bias, C, ldc, m_dev, m_max, n_pad, k_pad, relu, head_w, head_k, head_partial));
+                 ttl_launch_chain(dense_bf16_2cta_kernel<HEAD_OUT_FUSED>, grid, GEMM_THREADS,
+                                  GEMM2_SMEM + EXTRA_SMEM_BIAS + HEAD_OUT_FUSED * n_pad * 4, s, ta, tb2, bias, C, ldc,
+                                  m_dev, m_max, n_pad, k_pad, relu, head_w, head_k, head_partial));
     } else {
       TTL_LAUNCH("dense_bf16_kernel", s,
-                 dense_bf16_2cta_kernel<0><<<grid, GEMM_THREADS, GEMM2_SMEM + EXTRA_SMEM_BIAS, s>>>(
-                     ta, tb2, bias, C, ldc, m_dev, m_max, n_pad, k_pad, relu, nullptr, 0, nullptr));
+                 ttl_launch_chain(dense_bf16_2cta_kernel<0>, grid, GEMM_THREADS, GEMM2_SMEM + EXTRA_SMEM_BIAS, s, ta,
+                                  tb2, bias, C, ldc, m_dev, m_max, n_pad, k_pad, relu, (const float*)nullptr, 0,
+                                  (float*)nullptr));
     }
     TTL_CHECK_LAST();
     return 0;

@@ -42,8 +42,9 @@ static inline int ttl_div_up(long long a, long long b) { return (int)((a + b - 1
 // stream-serialization attribute, kernel N+1 is set up (and its CTAs become resident as kernel N's
 // drain) while kernel N is still running; it blocks in ttl_grid_dep_wait() until kernel N has
 // completed and its writes are visible.  Every kernel of the chain waits before its first global
-// access and releases its dependents right after, so by induction all earlier kernels are complete
-// when a wait returns.  Both instructions are no-ops in a kernel launched without the attribute.
+// access, so by induction all earlier kernels are complete when a wait returns; dependents are
+// released at exit, except by the state kernel (see build_state_kernel).  Both instructions are
+// no-ops in a kernel launched without the attribute.
 __device__ __forceinline__ void ttl_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void ttl_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -9,6 +9,8 @@
 
 #include "ttl_common.cuh"
 
+std::atomic<int> g_ttl_pdl{1};
+
 namespace {
 struct Pending { const char* name; cudaEvent_t a, b; };
 bool g_on = false;
@@ -42,6 +44,7 @@ void ttl_prof_end(cudaStream_t s) {
 extern "C" {
 
 void ttl_prof_enable(int32_t on) { g_on = on != 0; }
+void ttl_pdl_enable(int32_t on) { g_ttl_pdl.store(on != 0); }
 
 // Synchronises the recorded events, writes {"kernel": [launches, total_ms], ...} as JSON into
 // buf (NUL-terminated, truncated to buflen) and clears the record.  Returns bytes needed.

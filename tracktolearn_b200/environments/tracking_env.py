@@ -14,6 +14,7 @@ Two ways to drive it:
     host; ``n_alive()`` reads the alive count back when the loop wants to know.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -109,10 +110,12 @@ class TrackingEnvironment(BaseEnv):
             self._batch = bb
         return bb
 
-    def _start(self, initial_points, n_slots=None, fp32_state=True):
+    def _start(self, initial_points, n_slots=None, fp32_state=True, locality=False):
         """``n_slots`` < N turns on the streaming tracker: only n_slots streamlines are alive
         at once and slots freed by stopped ones take the next seeds in the same step.
-        ``fp32_state=False``: only the bf16 actor operand is produced (no fp32 state tensor)."""
+        ``fp32_state=False``: only the bf16 actor operand is produced (no fp32 state tensor).
+        ``locality``: seeds take slots in voxel raster order instead of row order (ttl_batch.order);
+        rows, results and the output order are unchanged."""
         if not fp32_state and (self._n_coefs != 45 or 7 * 48 + 3 * self.n_dirs > (self.get_state_size() + 63) // 64 * 64):
             fp32_state = True      # the bf16-only layout is specialised for the order-8 volume
         self.initial_points = initial_points
@@ -134,6 +137,14 @@ class TrackingEnvironment(BaseEnv):
         seeds_dev = (torch.from_numpy(seeds_host).pin_memory().to(self.device, non_blocking=True)
                      if not isinstance(initial_points, torch.Tensor)
                      else initial_points.to(self.device, dtype=torch.float64, non_blocking=True))
+        self._order_dev = None
+        if locality and N > 1:
+            # voxel of every seed (centre origin: voxel i spans [i-.5, i+.5]), raster key, stable sort
+            vox = torch.floor(seeds_dev + 0.5).to(torch.int64)
+            key = (vox[:, 0] * int(self._volume.Y) + vox[:, 1]) * int(self._volume.Z) + vox[:, 2]
+            self._order_dev = torch.argsort(key, stable=True).to(torch.int32)
+            self._b.order = self._order_dev.data_ptr()
+            self._continue_idx_cache = None
         _lib.check(self._lib.ttl_env_reset(ctypes.byref(self._volume), ctypes.byref(self._params),
                                            ctypes.byref(self._b), _lib.ptr(seeds_dev),
                                            _lib.stream_ptr(self.device)), 'ttl_env_reset')
@@ -147,12 +158,17 @@ class TrackingEnvironment(BaseEnv):
         """Reference: tracking_env.py:91-133."""
         return self._start(self.seeds[start:end])
 
-    def reset_streaming(self, start, end, n_slots, fp32_state=True):
+    def reset_streaming(self, start, end, n_slots, fp32_state=True, locality=True):
         """Like ``reset`` but at most ``n_slots`` streamlines are tracked at once; the others
         wait in the batch and take over slots as streamlines stop (device-side refill).
         With ``fp32_state=False`` the fp32 state tensor is not materialised: the step kernel
-        writes the actor's bf16 operand only (``current_state_bf16()``)."""
-        return self._start(self.seeds[start:end], n_slots=n_slots, fp32_state=fp32_state)
+        writes the actor's bf16 operand only (``current_state_bf16()``).
+        ``locality`` (default): seeds enter the slots in voxel raster order, so streamlines that are
+        neighbours in the alive list start in the same or adjacent voxels and their trilinear
+        gathers share cache lines (the reference shuffles the seeds, tracker.py:94; the rows -- and
+        with them every per-seed result and the output order -- stay in the shuffled order)."""
+        return self._start(self.seeds[start:end], n_slots=n_slots, fp32_state=fp32_state,
+                           locality=locality and os.environ.get('TTL_LOCALITY', '1') != '0')
 
     def nreset(self, n_seeds):
         """Reference: tracking_env.py:47-89."""
