@@ -66,7 +66,7 @@ def ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the step's kernels from
     the committed `ncu --set full` capture of this same command (profiles/README.md); None when the
     summary file is absent."""
-    path = os.path.join(ROOT, 'profiles', 'r1_step_v4_ncu_summary.json')
+    path = os.path.join(ROOT, 'profiles', 'r1_step_v6_ncu_summary.json')
     if not os.path.exists(path):
         return {}
 
@@ -389,7 +389,7 @@ def main_gpu(args):
     dense_launches = sum(n for n, _ in dn)
     dense_total_ms = sum(ms for _, ms in dn)
     traffic = ncu_traffic()
-    traffic_src = 'profiles/r1_step_v4_ncu_summary.json (ncu --set full of this command, bytes per launch)'
+    traffic_src = 'profiles/r1_step_v6_ncu_summary.json (ncu --set full of this command, bytes per launch)'
     roofline = None
     if dense_launches:
         steps_prof = dense_launches / 3.0
@@ -407,8 +407,11 @@ def main_gpu(args):
     # algorithmic bytes per row; without the fp32 API tensor the state write is the
     # 1280-byte bf16 operand instead of the 2460-byte fp32 row
     state_write = 1280 if args.bf16_state_only else 2460 + 1280
-    state_bytes = 4680 + state_write + 1200 + 12
-    step_bytes = 4680 + state_write + 1200 + 512 + 48
+    # previous directions: 100 fp32 points re-read (API mode), or the previous row's 600-byte bf16
+    # direction block shifted by one direction (device mode)
+    dirs_read = 600 if args.bf16_state_only else 1200
+    state_bytes = 4680 + state_write + dirs_read + 12
+    step_bytes = 4680 + state_write + dirs_read + 512 + 48
     state_ms = avg_ms('build_state_kernel')
     step_ms = sum(avg_ms(k) or 0.0 for k in ('propagate_stop_kernel', 'build_state_kernel'))
     roofline_step = None
@@ -447,7 +450,10 @@ def main_gpu(args):
                        'n_actor': N_ACTOR, 'seeds_per_gpu': n_seeds, 'step_mm': STEP_MM,
                        'max_nb_steps': int(env.max_nb_steps), 'actor': '615-' + HIDDEN + '-6 (synthetic, tracking-like)',
                        'env': 'NoisyTrackingEnvironment noise=0 (float64 directions)',
-                       'streaming_refill': True, 'alive_at_end': alive_end, 'burn_in_steps': BURN_IN,
+                       'streaming_refill': True,
+                       'slot_order': 'seeds enter the slots in voxel raster order (rows / output keep the shuffled order)'
+                       if os.environ.get('TTL_LOCALITY', '1') != '0' else 'row (shuffled) order',
+                       'launch': 'programmatic dependent launch' if os.environ.get('TTL_PDL', '1') != '0' else 'plain', 'alive_at_end': alive_end, 'burn_in_steps': BURN_IN,
                        'state_rows': ('bf16 actor operand only; the fp32 API tensor is not materialised in the '
                                       'device loop (SURVEY 7 step 7)' if args.bf16_state_only
                                       else 'fp32 API tensor + bf16 actor operand'),

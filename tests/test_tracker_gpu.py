@@ -132,6 +132,39 @@ def test_fused_head_step_is_bit_identical_to_action_round_trip():
     alg.fuse_head = True
 
 
+def test_bf16_direction_block_is_the_rounded_point_differences():
+    """Device mode builds the previous-direction block of a state row by shifting the previous row's
+    block (bf16) and putting the newest direction in front.  After a number of steps with refills it
+    must equal, bit for bit, bf16(points[L-1-k] - points[L-2-k]) recomputed from the fp32 streamline
+    buffer (env.py:549-563), zero padded."""
+    from tracktolearn_b200.algorithms.rl import StepRunner
+    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    n = len(seeds)
+    env.reset_streaming(0, n, 256, fp32_state=False)
+    runner = StepRunner(env, alg.agent.actor, 0.0, use_graph=False)
+    checked_long = False
+    for step in range(1, 41):
+        runner.step()
+        if step not in (1, 2, 7, 40):
+            continue
+        n_alive = env.n_alive()
+        assert n_alive > 0
+        bb = env._batch
+        rows = bb.alive[env._cur][:n_alive].cpu().numpy()
+        npts = bb.npts.cpu().numpy()[rows]
+        pts = bb.points.cpu().numpy()[rows]
+        got = bb.state_bf16[env._cur][:n_alive].float().cpu().numpy()
+        want = np.zeros((n_alive, 304), dtype=np.float32)
+        for a in range(n_alive):
+            L = int(npts[a])
+            d = np.diff(pts[a, :L], axis=0)[::-1][:100]          # newest first
+            want[a, :d.size] = d.reshape(-1)
+        want = torch.from_numpy(want).to(torch.bfloat16).float().numpy()
+        np.testing.assert_array_equal(got[:, 336:640], want)
+        checked_long = checked_long or int(npts.max()) > 10
+    assert checked_long
+
+
 def test_locality_order_does_not_change_any_streamline():
     """Streaming tracker with the seeds entering the slots in voxel raster order (ttl_batch.order) vs
     in row order: every row holds the same streamline, bit for bit, and the output order is the

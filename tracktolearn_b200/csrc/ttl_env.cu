@@ -833,7 +833,8 @@ __device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, 
 // directions follow at column 336.  No row staging: 512 B of shared memory per warp.
 __device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& prm, const float* P, int L, float3 tip,
                                          __nv_bfloat16* __restrict__ out, int n_bf16, float* smem_f, int lane,
-                                         int pf = 0) {
+                                         int pf = 0, const __nv_bfloat16* __restrict__ old_dirs = nullptr,
+                                         float3 prev_tip = make_float3(0.f, 0.f, 0.f)) {
   constexpr int CP = 48, CP4 = 12, S = 7 * CP;
   float* s_w = smem_f;
   int* s_vox = reinterpret_cast<int*>(smem_f + 64);
@@ -878,8 +879,39 @@ __device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& 
           make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
     }
   }
-  // previous directions, newest first, zero padded (env.py:549-563): two elements per lane
+  // previous directions, newest first, zero padded (env.py:549-563)
   const int nd3 = prm.n_dirs * 3;
+  if (old_dirs != nullptr && nd3 == 300 && n_bf16 - S == 304) {
+    // The direction block of this row is the previous row's block moved back by one direction with
+    // the newest one in front: a 6-byte shift of 600 bytes of bf16 instead of re-reading 101 fp32
+    // points and redoing 300 subtractions (each value was rounded to bf16 when it was the newest;
+    // copying it is the same as recomputing it).  A fresh streamline (L == 1) has no directions.
+    const uint4* o4 = reinterpret_cast<const uint4*>(old_dirs);
+    uint4* d4 = reinterpret_cast<uint4*>(out + S);
+    const float dxf = __fsub_rn(tip.x, prev_tip.x), dyf = __fsub_rn(tip.y, prev_tip.y),
+                dzf = __fsub_rn(tip.z, prev_tip.z);
+    __nv_bfloat162 hxy = __floats2bfloat162_rn(dxf, dyf), hz0 = __floats2bfloat162_rn(dzf, 0.f);
+    const uint32_t w_xy = *reinterpret_cast<uint32_t*>(&hxy), w_z = *reinterpret_cast<uint32_t*>(&hz0);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int q = lane + 32 * it;
+      if (q < 38) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (L > 1) {
+          const uint4 cur4 = __ldg(o4 + q);
+          const uint4 prv4 = q > 0 ? __ldg(o4 + q - 1) : make_uint4(0u, 0u, 0u, 0u);
+          o.x = __byte_perm(prv4.z, prv4.w, 0x5432);
+          o.y = __byte_perm(prv4.w, cur4.x, 0x5432);
+          o.z = __byte_perm(cur4.x, cur4.y, 0x5432);
+          o.w = __byte_perm(cur4.y, cur4.z, 0x5432);
+          if (q == 0) { o.x = w_xy; o.y = (w_z & 0xffffu) | (cur4.x << 16); }
+          if (q == 37) { o.z = 0u; o.w = 0u; }     // columns 300..303: row padding
+        }
+        d4[q] = o;
+      }
+    }
+    return;
+  }
   const float* last = P + (size_t)(L - 1) * 3;   // element j = last[c - 3k] - last[c - 3k - 3]
   for (int j = 2 * lane; j < n_bf16 - S; j += 64) {
     float val[2];
@@ -979,8 +1011,14 @@ __global__ void __launch_bounds__(kStateWarps * 32, FAST ? 6 : 1) build_state_ke
                            ? reinterpret_cast<__nv_bfloat16*>(b.state_bf16[cur ^ 1]) + (size_t)dst * b.ld_bf16
                            : nullptr;
   float* o32 = b.state[cur ^ 1] ? b.state[cur ^ 1] + (size_t)dst * b.ld_state : nullptr;
-  if (FAST)
-    build_state_row_c45_bf16(v, prm, P, L, tip, o16, b.ld_bf16, smem_f, lane, pf);
+  if (FAST) {
+    // survivors (and, in parity mode, rows that just stopped) extend the direction block of the row
+    // the actor has just read; a refilled slot starts from zeros (L == 1)
+    const __nv_bfloat16* old_dirs =
+        reinterpret_cast<const __nv_bfloat16*>(b.state_bf16[cur]) + (size_t)r * b.ld_bf16 + 7 * 48;
+    build_state_row_c45_bf16(v, prm, P, L, tip, o16, b.ld_bf16, smem_f, lane, pf, (pf & 8) ? nullptr : old_dirs,
+                             make_float3(rec.tx, rec.ty, rec.tz));
+  }
   else
     build_state_row(v, prm, P, L, tip, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
 }
@@ -1213,7 +1251,7 @@ static int state_prefetch_level() {
   if (v < 0) {
     const char* e = getenv("TTL_STATE_PREFETCH");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 2) v = 0;
+    if (v < 0 || v > 15) v = 0;
   }
   return v;
 }
