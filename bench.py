@@ -233,14 +233,34 @@ def main_reference(args):
         'e2e': {'value': value, 'unit': 'streamline-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner on stdout from C): point fd 1 at stderr for the run and keep the real stdout for the line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main_gpu(args):
+    quiet_stdout()
     import torch
     import torch.distributed as dist
     from tracktolearn_b200 import _lib, synthetic
@@ -473,7 +493,7 @@ def main_gpu(args):
             'cpu_baseline': cpu_baseline,
             'flop_per_streamline_step': ACTOR_FLOP_PER_ROW,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

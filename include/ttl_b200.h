@@ -202,6 +202,17 @@ int ttl_streamline_offsets(const ttl_batch* b, int64_t* offsets, void* stream);
 int ttl_pack_streamlines(const ttl_batch* b, const int64_t* offsets, float* out_points,
                          void* stream);
 
+/* ---- tractogram output (tracking/tracker.py:118-125) ---------------------------------------- */
+
+/* dipy `length` of n packed streamlines (points [total][3] fp32, offsets [n+1] int64): sum of the
+ * segment norms in double -- the quantity tracker.py:120-121 compares with min/max length. */
+int ttl_streamline_lengths(const float* points, const int64_t* offsets, int32_t n, double* out_lengths,
+                           void* stream);
+/* dipy `compress_streamlines(s, tol_error, max_segment_length)` (tracker.py:123-125, --compress) as a
+ * per-point keep mask [total] and per-streamline kept-point counts [n]; the caller compacts. */
+int ttl_compress_mask(const float* points, const int64_t* offsets, int32_t n, double tol_error,
+                      double max_segment_length, uint8_t* keep, int32_t* count, void* stream);
+
 /* ---- SAC actor (algorithms/shared/offpolicy.py:61-140, shared/utils.py:41-51) -------------- */
 
 #define TTL_ACTOR_MAX_LAYERS 8

@@ -422,6 +422,54 @@ def streamline_length(s):
     return float(np.sqrt(((s[1:] - s[:-1]) ** 2).sum(-1)).sum())
 
 
+def compress_streamline(s, tol_error=0.01, max_segment_length=10.0):
+    """dipy ``compress_streamlines`` for one streamline (tracking/tracker.py:123-125, ``--compress``),
+    restated from the published algorithm of dipy/tracking/streamlinespeed.pyx
+    (``c_compress_streamline`` / ``c_dist_to_line`` / ``c_segment_length``; dipy is not installed here
+    and the reference does not pin its version, so this restatement is the definition the CUDA
+    kernel is held to -- parity with upstream unpinned):
+
+      * the first and last points are kept; streamlines of <= 2 points are copied;
+      * walking ``nxt`` = 2..N-1 with ``prev`` the last kept point: the chord (prev, nxt) replaces
+        the path if it is shorter than ``max_segment_length`` and every point strictly between them
+        lies within ``tol_error`` of the line through prev and nxt (a NaN distance counts as too
+        far); otherwise point nxt-1 is kept and becomes ``prev``;
+      * distances: |(nxt-prev) x (curr-nxt)| / |nxt-prev| with coordinate differences and their
+        products in the streamline's dtype (C float arithmetic) summed in double;
+        chord length: double sum of squared (float) differences.
+    Returns the compressed streamline (same dtype)."""
+    s = np.asarray(s)
+    N = len(s)
+    if N <= 2:
+        return s.copy()
+    dt = s.dtype.type
+    keep = [0]
+    prev = 0
+    for nxt in range(2, N):
+        dn = (s[nxt] - s[prev]).astype(np.float64)              # float difference widened to double
+        seg = np.sqrt(dn[0] * dn[0] + dn[1] * dn[1] + dn[2] * dn[2])
+        ok = False
+        if seg < max_segment_length:
+            ok = True
+            a = s[nxt] - s[prev]                                 # dtype arithmetic
+            norm2 = np.sqrt(np.float64(dt(a[0] * a[0])) + np.float64(dt(a[1] * a[1])) + np.float64(dt(a[2] * a[2])))
+            for curr in range(prev + 1, nxt):
+                b = s[curr] - s[nxt]
+                cx = np.float64(dt(dt(a[1] * b[2]) - dt(a[2] * b[1])))
+                cy = np.float64(dt(dt(a[2] * b[0]) - dt(a[0] * b[2])))
+                cz = np.float64(dt(dt(a[0] * b[1]) - dt(a[1] * b[0])))
+                with np.errstate(invalid='ignore', divide='ignore'):
+                    dist = np.sqrt(cx * cx + cy * cy + cz * cz) / norm2
+                if np.isnan(dist) or dist > tol_error:
+                    ok = False
+                    break
+        if not ok:
+            keep.append(nxt - 1)
+            prev = nxt - 1
+    keep.append(N - 1)
+    return s[np.asarray(keep)]
+
+
 def set_number_of_points(s, nb_points=128):
     """dipy ``set_number_of_points`` restated (oracles/oracle.py:52,70):
     arc-length linear resampling; differences in the input dtype, arc lengths and

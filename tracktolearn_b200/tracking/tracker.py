@@ -42,9 +42,6 @@ class Tracker(object):
         self.save_seeds = save_seeds
         self.streaming = streaming
         self.rows_per_pass = rows_per_pass
-        if compress:
-            raise NotImplementedError('--compress (dipy compress_streamlines) is a next-row item, '
-                                      'see DESIGN.md')
 
     # ----------------------------------------------------------------------------------
     def _passes(self, env):
@@ -91,8 +88,11 @@ class Tracker(object):
                 lens = streamline_lengths(batch.data, batch.offsets)
                 keep = (scaled_min_length <= lens) & (lens <= scaled_max_length)
                 seeds = batch.data_per_streamline['seeds']
+                data, offsets = batch.data, batch.offsets
+                if self.compress:     # tracker.py:123-125, on the device for the whole batch
+                    data, offsets = self._compress(env, data, offsets)
                 for i in np.nonzero(keep)[0]:
-                    s = np.array(batch.data[batch.offsets[i]:batch.offsets[i + 1]])
+                    s = np.array(data[offsets[i]:offsets[i + 1]])
                     if is_trk:
                         s += 0.5
                         s *= vox_size
@@ -102,6 +102,13 @@ class Tracker(object):
                     yield TractogramItem(s, seed_dict, {})
 
         return tracking_generator()
+
+    def _compress(self, env, data, offsets):
+        """dipy ``compress_streamlines(streamline, self.compress)`` (tracker.py:123-125) for a packed
+        batch, on the env's device; returns host arrays."""
+        from tracktolearn_b200.tracking.postprocess import compress_packed
+        d, o = compress_packed(data, offsets, tol_error=float(self.compress), device=env.device)
+        return d.cpu().numpy(), o.cpu().numpy()
 
     def track_to_file(self, env, path, dims, voxel_sizes):
         """What ``ttl_track.py`` does with ``track`` + ``nib.streamlines.save`` (runners/ttl_track.py:
@@ -121,8 +128,11 @@ class Tracker(object):
                 keep = (lo <= lens) & (lens <= hi)
                 npts = np.diff(batch.offsets)
                 sel = np.repeat(keep, npts)
-                data = batch.data[sel].astype(np.float64)
+                data = batch.data[sel]
                 offsets = np.concatenate(([0], np.cumsum(npts[keep]))).astype(np.int64)
+                if self.compress:     # after the length filter, before the space change (tracker.py:120-129)
+                    data, offsets = self._compress(env, data, offsets)
+                data = data.astype(np.float64)
                 if fmt == 'trk':
                     data = (data + 0.5) * vox_size
                 else:
