@@ -69,3 +69,42 @@ def test_ttl_track_end_to_end(tmp_path, ext):
     inner[offsets[1:-1] - 1] = False
     # step size rescaled by voxel size: 1.25 / 0.9987237 * 0.75 mm = 0.75096 voxels
     np.testing.assert_allclose(seg[inner], 0.75 / 0.9987237, rtol=2e-4)
+
+
+@pytest.mark.gpu
+def test_ttl_track_compress_flag(tmp_path):
+    """`--compress t` (ttl_track.py:223-228 -> tracker.py:123-125): same streamlines, fewer points, every
+    removed point within t (voxels, as in the reference: compression runs before the space change)
+    of the chord that replaced it; end points untouched."""
+    from tracktolearn_b200 import synthetic
+    from tracktolearn_b200.io import nifti
+    from tracktolearn_b200.io.streamlines import read_tck
+    from tracktolearn_b200.runners.ttl_track import main
+    shape = (24, 26, 22)
+    sub = synthetic.make_subject(shape, seed=5)
+    affine = np.diag([1.25, 1.25, 1.25, 1.0])
+    nifti.save(str(tmp_path / 'fodf.nii.gz'), sub['sh'].numpy(), affine)
+    nifti.save(str(tmp_path / 'mask.nii.gz'), sub['mask'].numpy(), affine)
+    nifti.save(str(tmp_path / 'seed.nii.gz'), synthetic.ellipsoid_mask(shape, frac=0.3).numpy().astype(np.uint8), affine)
+    agent = synthetic.write_agent_dir(str(tmp_path / 'agent'), kind='tracking', hidden_dims='128-128-128')
+    outs = []
+    for extra in ([], ['--compress', '0.1']):
+        out = str(tmp_path / ('out%d.tck' % len(extra)))
+        main([str(tmp_path / 'fodf.nii.gz'), str(tmp_path / 'seed.nii.gz'), str(tmp_path / 'mask.nii.gz'), out,
+              '--agent', agent, '--hyperparameters', os.path.join(agent, 'hyperparameters.json'),
+              '--n_actor', '500', '--npv', '1', '--min_length', '5', '--max_length', '60', '--rng_seed', '7'] + extra)
+        outs.append(read_tck(out))
+    (d0, o0, _), (d1, o1, _) = outs
+    assert len(o0) == len(o1) and len(o0) > 100
+    assert len(d1) < 0.8 * len(d0)
+    for i in range(len(o0) - 1):
+        a, b = d0[o0[i]:o0[i + 1]] / 1.25, d1[o1[i]:o1[i + 1]] / 1.25
+        np.testing.assert_allclose(a[0], b[0], atol=1e-5)
+        np.testing.assert_allclose(a[-1], b[-1], atol=1e-5)
+        # every original point lies within the tolerance of the compressed polyline
+        seg0, seg1 = b[:-1], b[1:]
+        u = seg1 - seg0
+        for p in a[:: max(1, len(a) // 8)]:
+            t = np.clip(((p - seg0) * u).sum(1) / np.maximum((u * u).sum(1), 1e-12), 0, 1)
+            dist = np.linalg.norm(seg0 + t[:, None] * u - p, axis=1).min()
+            assert dist <= 0.1 + 1e-3, dist

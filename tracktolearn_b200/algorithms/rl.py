@@ -3,7 +3,7 @@
 The reference crosses the host/device boundary three times per step (action D2H with a
 sync, coordinates H2D, previous directions H2D).  Here the loop only enqueues kernels: the
 actor reads the alive count from device memory, the env step consumes the action tensor in
-place, the six launches of a step are replayed from a CUDA graph, and the host learns the
+place, the launches of a step can be replayed from a CUDA graph, and the host learns the
 alive count from asynchronous copies that lag a few steps behind (the queue never drains).
 """
 import numpy as np
@@ -103,7 +103,7 @@ class RLAlgorithm(object):
         self.batch_size = batch_size
         self.rng = rng
         self.sync_every = 8
-        # CUDA-graph replay of the 6-launch step is available but off: measured on B200 the loop is
+        # CUDA-graph replay of the step is available but off: measured on B200 the loop is
         # GPU-bound even in the low-occupancy tail (800k-seed episode: 330 ms plain vs 323-331 ms
         # replayed), so the capture cost buys nothing
         self.use_cuda_graph = False
