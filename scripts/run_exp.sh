@@ -1,5 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/bench_v6.json 2> gpurun_out/bench_v6.err; tail -c 400 gpurun_out/bench_v6.err
-python -c "
-import json;d=json.load(open('gpurun_out/bench_v6.json'));print(round(d['value']/1e6,2), round(d['ms_per_step']*1e3,1), 'e2e', round(d['e2e']['value']/1e6,2), d['roofline']['frac'], {k:round(v['avg_us'],1) for k,v in d['kernels'].items()}, d['clocks'], d['cpu_baseline']['value'])"
-python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_v6_reference.json 2>/dev/null; cut -c1-200 gpurun_out/bench_v6_reference.json
+run() { tag=$1; shift; env "$@" python bench.py --no-cpu --no-e2e --steps 400 --warmup 20 > gpurun_out/exp_$tag.json 2> gpurun_out/exp_$tag.err; python -c "
+import json;d=json.load(open('gpurun_out/exp_$tag.json'));print('$tag', round(d['value']/1e6,2), round(d['ms_per_step']*1e3,1), {k:round(v['avg_us'],1) for k,v in d['kernels'].items()})" || tail -5 gpurun_out/exp_$tag.err; }
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+run scan A=1
+run scan2 A=1

@@ -344,23 +344,31 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
 }
 
 // Ordered-compaction bookkeeping shared by propagate_stop_kernel and oracle_apply_kernel: every
-// CTA (kGroup ranks, kK1Threads threads) publishes how many of its ranks stopped; the last CTA to
-// arrive scans the per-group survivor counts and updates the control block (next alive count,
-// slot refill, counters).  `stopped` must be non-zero in exactly one thread per stopped rank.
+// CTA (kGroup ranks, kK1Threads threads) publishes how many of its ranks stopped; the CTA with the
+// highest index waits for all of them, scans the per-group survivor counts and updates the control
+// block (next alive count, slot refill, counters).  `stopped` must be non-zero in exactly one thread per stopped rank.
 __device__ void compaction_bookkeeping(const ttl_batch& b, const ttl_params& prm, int cur, int n_alive,
                                        int stopped) {
-  __shared__ int s_is_last;
   __shared__ int s_part[kK1Threads / 32];
   const int grp_stops = __syncthreads_count(stopped);
+  // Every CTA publishes its count with a release-add and leaves at once (waiting for an atomic's
+  // return value to learn "am I the last one" kept every CTA on its SM for an L2 round trip: 13 % of
+  // the kernel's stall samples).  The CTA with the highest index -- dispatched after all the
+  // others -- is the scanner: it waits until the counter shows the whole grid.
   if (threadIdx.x == 0) {
     b.grp_stops[blockIdx.x] = grp_stops;
-    __threadfence();
-    const int ticket = atomicAdd(b.ctrl + 7, 1);
-    s_is_last = ticket == (int)gridDim.x - 1;
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(b.ctrl + 7) : "memory");
+  }
+  if (blockIdx.x != gridDim.x - 1) return;
+  if (threadIdx.x == 0) {
+    int seen;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(b.ctrl + 7) : "memory");
+      if (seen >= (int)gridDim.x) break;
+      __nanosleep(64);
+    }
   }
   __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
   // Thread t owns the contiguous groups [g0, g1).  Up to kScanUnroll groups per thread are loaded
   // as independent L2 reads and kept in registers (50 000 slots: 1563 groups, 13 per thread), so
   // the serial tail of the step is one load latency + one block scan.
@@ -446,6 +454,7 @@ struct ActionSrc {
   const float* partial;   // [n_alive][n_tiles][8] fp32 per-n-tile partial sums of the 6-wide head
   int n_tiles;
   const float* bias;      // head bias
+  int n_rows;             // rows the launch covers (>= the alive count): bound for speculative loads
 };
 
 template <int MINB>
@@ -457,26 +466,30 @@ __global__ void __launch_bounds__(kK1Threads, MINB) propagate_stop_kernel(
   const unsigned quad_mask = 0xFu << (lane & ~(kLanesPerRow - 1));
   const int r = blockIdx.x * kGroup + (threadIdx.x / kLanesPerRow);
   ttl_grid_dep_wait();     // the actor's last layer (head partials) / the previous step's state kernel
-  const int n_alive = b.ctrl[cur];
-  int stopped = 0;
-  if (r < n_alive) {
-  // everything this rank needs arrives with two independent loads (record + action)
-  const RankRec rec = read_rank_rec(b.rank_rec[cur], r);
-  float ax, ay, az;
+  // Everything this rank needs arrives with independent loads issued together -- alive count, rank
+  // record, action (or head partials) -- at a rank clamped into the launch so that the loads need
+  // not wait for the count they are checked against.
+  const int r_ld = min(r, src.n_rows - 1);
+  const RankRec rec = read_rank_rec(b.rank_rec[cur], r_ld);
+  float ax = 0.f, ay = 0.f, az = 0.f;
   if (src.partial) {
-    const float4* hp = reinterpret_cast<const float4*>(src.partial + (size_t)r * src.n_tiles * 8);
-    ax = 0.f; ay = 0.f; az = 0.f;
+    const float4* hp = reinterpret_cast<const float4*>(src.partial + (size_t)r_ld * src.n_tiles * 8);
     for (int t = 0; t < src.n_tiles; ++t) {
       const float4 pt = __ldg(hp + 2 * t);
       ax += pt.x; ay += pt.y; az += pt.z;
     }
+  } else {
+    ax = src.actions[(size_t)r_ld * src.lda + 0];
+    ay = src.actions[(size_t)r_ld * src.lda + 1];
+    az = src.actions[(size_t)r_ld * src.lda + 2];
+  }
+  const int n_alive = b.ctrl[cur];
+  int stopped = 0;
+  if (r < n_alive) {
+  if (src.partial) {
     ax = tanhf(ax + __ldg(src.bias + 0));
     ay = tanhf(ay + __ldg(src.bias + 1));
     az = tanhf(az + __ldg(src.bias + 2));
-  } else {
-    ax = src.actions[(size_t)r * src.lda + 0];
-    ay = src.actions[(size_t)r * src.lda + 1];
-    az = src.actions[(size_t)r * src.lda + 2];
   }
   const int i = rec.row;
   const int L = rec.L;  // points so far in this row
@@ -1298,7 +1311,7 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   if (rc) return rc;
   if (n_upper <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const ActionSrc src = {actions, lda, nullptr, 0, nullptr};
+  const ActionSrc src = {actions, lda, nullptr, 0, nullptr, n_upper};
   launch_propagate(vol, prm, b, cur, src, noise, 0, n_upper, s);
   rc = launch_build_state(vol, prm, b, cur, n_upper, s);
   if (rc) return rc;
@@ -1315,7 +1328,7 @@ int ttl_env_step_head(const ttl_volume* vol, const ttl_params* prm, const ttl_ba
   if (rc) return rc;
   if (n_upper <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const ActionSrc src = {nullptr, 0, head_partial, n_tiles, head_bias};
+  const ActionSrc src = {nullptr, 0, head_partial, n_tiles, head_bias, n_upper};
   launch_propagate(vol, prm, b, cur, src, nullptr, 0, n_upper, s);
   rc = launch_build_state(vol, prm, b, cur, n_upper, s);
   if (rc) return rc;
@@ -1331,7 +1344,7 @@ int ttl_env_step_begin(const ttl_volume* vol, const ttl_params* prm, const ttl_b
   if (rc) return rc;
   if (n_upper <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const ActionSrc src = {actions, lda, nullptr, 0, nullptr};
+  const ActionSrc src = {actions, lda, nullptr, 0, nullptr, n_upper};
   launch_propagate(vol, prm, b, cur, src, noise, 1, n_upper, s);
   TTL_CHECK_LAST();
   return 0;
