@@ -36,6 +36,7 @@ def main():
     ap.add_argument('--n-actor', type=int, default=B.N_ACTOR)
     ap.add_argument('--shape', type=int, nargs=3, default=list(SHAPE))
     ap.add_argument('--no-gather', action='store_true')
+    ap.add_argument('--graph', action='store_true', help='replay the step from CUDA graphs')
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -82,6 +83,7 @@ def main():
     env.seeds = seeds[s0:s1]
     alg = SACAuto(B.STATE_SIZE, 3, B.HIDDEN, n_actors=a.n_actor, device=dev, precision='bf16')
     alg.agent.actor.load_state_dict(synthetic.actor_state_dict(B.STATE_SIZE, B.HIDDEN, seed=1111, kind='tracking'))
+    alg.use_cuda_graph = bool(a.graph)
     tracker = Tracker(alg, a.n_actor, min_length=10.0, max_length=B.MAX_LENGTH_MM)
     stream = torch.cuda.current_stream(dev)
     setup_s = time.perf_counter() - t_setup
