@@ -331,6 +331,12 @@ void ttl_prof_enable(int32_t on);
  * (every one of them waits for its predecessor's completion before its first global access).
  * On by default; 0 switches back to plain stream-ordered launches. */
 void ttl_pdl_enable(int32_t on);
+/* A/B switches of the device-mode state kernel (default 0): bits 0-1 prefetch the row's cache lines
+ * into L1 (1) / L2 (2) before gathering, bit 3 recompute the previous-direction block from the fp32
+ * points instead of shifting the previous row's, bit 4 gather the row's <= 32 distinct voxels once
+ * (one LDG.64 per voxel per lane) instead of the 56 trilinear corners through L1 (bits 5-6: that
+ * kernel's CTAs per SM).  Results are identical in every combination. */
+void ttl_state_options(int32_t bits);
 int32_t ttl_prof_report(char* buf_host, int32_t buflen);
 
 #ifdef __cplusplus

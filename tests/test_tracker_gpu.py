@@ -165,6 +165,37 @@ def test_bf16_direction_block_is_the_rounded_point_differences():
     assert checked_long
 
 
+def test_state_kernel_variants_write_identical_rows():
+    """The 56-corner gather (default), the deduplicated 32-voxel gather (bit 4, two occupancies), the
+    shifted direction block (default) and the recomputed one (bit 3) produce bit-identical bf16
+    operands, hence bit-identical streamlines."""
+    from tracktolearn_b200 import _lib
+    lib = _lib.load()
+    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    n = len(seeds)
+    out, rows = [], []
+    try:
+        for opts in (0, 16, 16 | 32, 8):
+            lib.ttl_state_options(opts)
+            st = env.reset_streaming(0, n, 256, fp32_state=False)
+            from tracktolearn_b200.algorithms.rl import StepRunner
+            runner = StepRunner(env, alg.agent.actor, 0.0, use_graph=False)
+            for _ in range(12):
+                runner.step()
+            torch.cuda.synchronize()
+            rows.append(env._batch.state_bf16[env._cur][:256].clone())
+            st = env.reset_streaming(0, n, 256, fp32_state=False)
+            alg.validation_episode(st, env, 0.0)
+            out.append(env.get_streamlines())
+    finally:
+        lib.ttl_state_options(0)
+    for r in rows[1:]:
+        assert torch.equal(rows[0].view(torch.int16), r.view(torch.int16))
+    for b in out[1:]:
+        np.testing.assert_array_equal(out[0].lengths, b.lengths)
+        np.testing.assert_array_equal(out[0].data, b.data)
+
+
 def test_locality_order_does_not_change_any_streamline():
     """Streaming tracker with the seeds entering the slots in voxel raster order (ttl_batch.order) vs
     in row order: every row holds the same streamline, bit for bit, and the output order is the

@@ -55,6 +55,7 @@ SIGNATURES = {
     'ttl_launch_count': (c_i64, []),
     'ttl_prof_enable': (None, [c_i32]),
     'ttl_pdl_enable': (None, [c_i32]),
+    'ttl_state_options': (None, [c_i32]),
     'ttl_prof_report': (c_i32, [ctypes.c_char_p, c_i32]),
     'ttl_pad_channels': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
     'ttl_env_reset': (c_i32, [P(Volume), P(Params), P(Batch), c_vp, c_vp]),

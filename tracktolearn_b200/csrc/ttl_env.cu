@@ -840,6 +840,40 @@ __device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, 
   __syncwarp();
 }
 
+// Direction block of a device-mode row (columns 336..639 of the bf16 operand): the previous row's
+// block moved back by one direction with the newest one in front -- a 6-byte shift of 600 bytes of
+// bf16 instead of re-reading 101 fp32 points and redoing 300 subtractions (each value was rounded to
+// bf16 when it was the newest; copying it is the same as recomputing it).  A fresh streamline
+// (L == 1) has no directions.  n_dirs == 100, 304 columns.
+__device__ __forceinline__ void write_dirs_shifted(const __nv_bfloat16* __restrict__ old_dirs,
+                                                   __nv_bfloat16* __restrict__ out_dirs, int L, float3 tip,
+                                                   float3 prev_tip, int lane) {
+  const uint4* o4 = reinterpret_cast<const uint4*>(old_dirs);
+  uint4* d4 = reinterpret_cast<uint4*>(out_dirs);
+  const float dxf = __fsub_rn(tip.x, prev_tip.x), dyf = __fsub_rn(tip.y, prev_tip.y),
+              dzf = __fsub_rn(tip.z, prev_tip.z);
+  __nv_bfloat162 hxy = __floats2bfloat162_rn(dxf, dyf), hz0 = __floats2bfloat162_rn(dzf, 0.f);
+  const uint32_t w_xy = *reinterpret_cast<uint32_t*>(&hxy), w_z = *reinterpret_cast<uint32_t*>(&hz0);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int q = lane + 32 * it;
+    if (q < 38) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (L > 1) {
+        const uint4 cur4 = __ldg(o4 + q);
+        const uint4 prv4 = q > 0 ? __ldg(o4 + q - 1) : make_uint4(0u, 0u, 0u, 0u);
+        o.x = __byte_perm(prv4.z, prv4.w, 0x5432);
+        o.y = __byte_perm(prv4.w, cur4.x, 0x5432);
+        o.z = __byte_perm(cur4.x, cur4.y, 0x5432);
+        o.w = __byte_perm(cur4.y, cur4.z, 0x5432);
+        if (q == 0) { o.x = w_xy; o.y = (w_z & 0xffffu) | (cur4.x << 16); }
+        if (q == 37) { o.z = 0u; o.w = 0u; }     // columns 300..303: row padding
+      }
+      d4[q] = o;
+    }
+  }
+}
+
 // bf16-only fast path (ttl_batch.bf16_layout == 1, no fp32 row): the state is produced straight
 // as the actor's first-layer operand.  Point p owns columns [48p, 48p+48) so every (point, chunk)
 // work item converts its float4 to 4 bf16 and stores 8 aligned bytes from registers; previous
@@ -895,34 +929,7 @@ __device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& 
   // previous directions, newest first, zero padded (env.py:549-563)
   const int nd3 = prm.n_dirs * 3;
   if (old_dirs != nullptr && nd3 == 300 && n_bf16 - S == 304) {
-    // The direction block of this row is the previous row's block moved back by one direction with
-    // the newest one in front: a 6-byte shift of 600 bytes of bf16 instead of re-reading 101 fp32
-    // points and redoing 300 subtractions (each value was rounded to bf16 when it was the newest;
-    // copying it is the same as recomputing it).  A fresh streamline (L == 1) has no directions.
-    const uint4* o4 = reinterpret_cast<const uint4*>(old_dirs);
-    uint4* d4 = reinterpret_cast<uint4*>(out + S);
-    const float dxf = __fsub_rn(tip.x, prev_tip.x), dyf = __fsub_rn(tip.y, prev_tip.y),
-                dzf = __fsub_rn(tip.z, prev_tip.z);
-    __nv_bfloat162 hxy = __floats2bfloat162_rn(dxf, dyf), hz0 = __floats2bfloat162_rn(dzf, 0.f);
-    const uint32_t w_xy = *reinterpret_cast<uint32_t*>(&hxy), w_z = *reinterpret_cast<uint32_t*>(&hz0);
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int q = lane + 32 * it;
-      if (q < 38) {
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (L > 1) {
-          const uint4 cur4 = __ldg(o4 + q);
-          const uint4 prv4 = q > 0 ? __ldg(o4 + q - 1) : make_uint4(0u, 0u, 0u, 0u);
-          o.x = __byte_perm(prv4.z, prv4.w, 0x5432);
-          o.y = __byte_perm(prv4.w, cur4.x, 0x5432);
-          o.z = __byte_perm(cur4.x, cur4.y, 0x5432);
-          o.w = __byte_perm(cur4.y, cur4.z, 0x5432);
-          if (q == 0) { o.x = w_xy; o.y = (w_z & 0xffffu) | (cur4.x << 16); }
-          if (q == 37) { o.z = 0u; o.w = 0u; }     // columns 300..303: row padding
-        }
-        d4[q] = o;
-      }
-    }
+    write_dirs_shifted(old_dirs, out + S, L, tip, prev_tip, lane);
     return;
   }
   const float* last = P + (size_t)(L - 1) * 3;   // element j = last[c - 3k] - last[c - 3k - 3]
@@ -938,6 +945,151 @@ __device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& 
     __nv_bfloat162 h = __floats2bfloat162_rn(val[0], val[1]);
     *reinterpret_cast<__nv_bfloat162*>(out + S + j) = h;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Device-mode row, deduplicated gather (ttl_state_options bit 4; off by default -- measured 74-86 us
+// against 60 us for the 56-corner kernel: it executes as many instructions (selects, 32 address
+// computations) at a third of the occupancy).  The 7-point neighbourhood (tip, tip +- r along each axis,
+// 0 < r < 1 voxel) touches at most 32 distinct voxels: the 2x2x2 cell of the tip plus one 2x2 face
+// beyond it in each of the six directions -- and only the faces a shifted point actually crosses
+// into (26 voxels on average).  The 56-corner formulation above asks L1 for 56 x 192 B
+// per row and leaves the deduplication to the cache: the state kernel ran at 73 % of the L1 data
+// pipe's wavefront rate.  Here lane l < 24 owns channels (2l, 2l+1): one LDG.64 per distinct voxel
+// per lane -- a warp reads a voxel's 192 bytes once, as two full wavefronts -- all 32 issued before
+// the first is used, then 7 x 8 FMAs per channel on registers in the same corner order as the
+// 56-corner path.  Which of the tip cell's neighbours a shifted point uses is a warp-uniform choice.
+//
+// Per axis: lo0 = saturated floor of the tip coordinate (the same float clamp as tri_axis), slots
+// s = 0..3 <-> lattice index clamp(lo0 - 1 + s); the tip uses slots (1, 2), the point shifted by -r
+// slots (1 - sm, 2 - sm), by +r slots (1 + sp, 2 + sp) with sm, sp in {0, 1}.  Anything else (r >= 1,
+// which no shipped configuration has) takes the 56-corner path.
+struct AxisSlots {
+  int idx[4];   // clamped lattice index of slots 0..3
+  int sm, sp;   // does the -r / +r point start one cell lower / higher than the tip
+};
+
+__device__ __forceinline__ int sat_floor(float c, int n) {
+  return (int)fminf(fmaxf(floorf(c), -1.f), (float)n);
+}
+
+__device__ __forceinline__ AxisSlots axis_slots(float t, float rad, int n) {
+  AxisSlots a;
+  const int lo0 = sat_floor(t, n);
+  a.sm = lo0 - sat_floor(__fadd_rn(t, -rad), n);
+  a.sp = sat_floor(__fadd_rn(t, rad), n) - lo0;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) a.idx[s] = min(max(lo0 - 1 + s, 0), n - 1);
+  return a;
+}
+
+__device__ __forceinline__ float2 ldg_nc_v2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+
+// acc = sum_k w[k] * val[k], k = 0..7, as an fmaf chain from zero (the order of the 56-corner path)
+__device__ __forceinline__ float2 tri8(const float* __restrict__ w, const float2 (&val)[8]) {
+  const float4 w0 = *reinterpret_cast<const float4*>(w), w1 = *reinterpret_cast<const float4*>(w + 4);
+  const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    acc.x = fmaf(wk[k], val[k].x, acc.x);
+    acc.y = fmaf(wk[k], val[k].y, acc.y);
+  }
+  return acc;
+}
+
+// returns false (nothing written) when the neighbourhood does not fit the 32-voxel footprint
+__device__ bool build_state_row_c45_bf16_dedup(const ttl_volume& v, const ttl_params& prm, int L, float3 tip,
+                                               __nv_bfloat16* __restrict__ out, float* smem_f, int lane,
+                                               const __nv_bfloat16* __restrict__ old_dirs, float3 prev_tip) {
+  constexpr int CP = 48, S = 7 * CP;
+  const float rad = (float)prm.step_vox;
+  const AxisSlots ax = axis_slots(tip.x, rad, v.X), ay = axis_slots(tip.y, rad, v.Y), az = axis_slots(tip.z, rad, v.Z);
+  if (((ax.sm | ax.sp | ay.sm | ay.sp | az.sm | az.sp) & ~1) != 0) return false;   // warp-uniform
+
+  // the 56 trilinear weights, one per lane (and lane + 32), through shared memory as before
+  float* s_w = smem_f;
+  int* s_vox = reinterpret_cast<int*>(smem_f + 64);
+  corner_table(v, prm, tip, s_w, s_vox, lane);
+
+  // voxel offsets (in float2 units of this lane's channel pair); all warp-uniform arithmetic
+  const int l2 = min(lane, 23);
+  const float2* base = reinterpret_cast<const float2*>(v.sh) + l2;
+  auto vox = [&](int xs, int ys, int zs) -> const float2* {
+    return base + (size_t)((ax.idx[xs] * v.Y + ay.idx[ys]) * v.Z + az.idx[zs]) * (CP / 2);
+  };
+  float2 C[8], XL[4], XH[4], YL[4], YH[4], ZL[4], ZH[4];
+  const float2 zero2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) C[k] = ldg_nc_v2(vox(1 + (k >> 2), 1 + ((k >> 1) & 1), 1 + (k & 1)));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int a = 1 + (j >> 1), b = 1 + (j & 1);
+    XL[j] = ax.sm ? ldg_nc_v2(vox(0, a, b)) : zero2;
+    XH[j] = ax.sp ? ldg_nc_v2(vox(3, a, b)) : zero2;
+    YL[j] = ay.sm ? ldg_nc_v2(vox(a, 0, b)) : zero2;
+    YH[j] = ay.sp ? ldg_nc_v2(vox(a, 3, b)) : zero2;
+    ZL[j] = az.sm ? ldg_nc_v2(vox(a, b, 0)) : zero2;
+    ZH[j] = az.sp ? ldg_nc_v2(vox(a, b, 3)) : zero2;
+  }
+  // direction block while the gathers are in flight
+  write_dirs_shifted(old_dirs, out + S, L, tip, prev_tip, lane);
+  __syncwarp();   // s_w complete
+
+  float2 val[8];
+  float2 acc[7];
+  acc[0] = tri8(s_w, C);
+  // +x / -x: corner k = 4 cx + j, j = 2 cy + cz
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { val[j] = ax.sp ? C[4 + j] : C[j]; val[4 + j] = ax.sp ? XH[j] : C[4 + j]; }
+  acc[1] = tri8(s_w + 8, val);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { val[j] = ax.sm ? XL[j] : C[j]; val[4 + j] = ax.sm ? C[j] : C[4 + j]; }
+  acc[4] = tri8(s_w + 32, val);
+  // +y / -y: corner k = 4 cx + 2 cy + cz, face index j = 2 cx + cz
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k0 = 4 * (j >> 1) + (j & 1), k1 = k0 + 2;     // cy = 0 / cy = 1
+    val[k0] = ay.sp ? C[k1] : C[k0];
+    val[k1] = ay.sp ? YH[j] : C[k1];
+  }
+  acc[2] = tri8(s_w + 16, val);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k0 = 4 * (j >> 1) + (j & 1), k1 = k0 + 2;
+    val[k0] = ay.sm ? YL[j] : C[k0];
+    val[k1] = ay.sm ? C[k0] : C[k1];
+  }
+  acc[5] = tri8(s_w + 40, val);
+  // +z / -z: face index j = 2 cx + cy
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k0 = 2 * j, k1 = k0 + 1;                      // cz = 0 / cz = 1
+    val[k0] = az.sp ? C[k1] : C[k0];
+    val[k1] = az.sp ? ZH[j] : C[k1];
+  }
+  acc[3] = tri8(s_w + 24, val);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k0 = 2 * j, k1 = k0 + 1;
+    val[k0] = az.sm ? ZL[j] : C[k0];
+    val[k1] = az.sm ? C[k0] : C[k1];
+  }
+  acc[6] = tri8(s_w + 48, val);
+
+  // the volume's padding channels (45..47) are zero, so those columns come out zero
+  if (lane < 24) {
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(acc[p].x, acc[p].y);
+      *reinterpret_cast<__nv_bfloat162*>(out + p * CP + 2 * lane) = h;
+    }
+  }
+  return true;
 }
 
 // tip = P[L-1] (passed by value so a caller that already holds it skips the dependent load)
@@ -965,8 +1117,8 @@ __device__ __forceinline__ int survivors_before(const ttl_batch& b, int r, int n
 // FAST = 1: the bf16-only device mode (ttl_batch.bf16_layout == 1) compiled on its own with a register
 // budget (85) that lets one lane keep all 24 of its LDG.128 gathers in flight; in the general kernel
 // ptxas keeps 4 in flight to stay at 47 registers.
-template <int FAST>
-__global__ void __launch_bounds__(kStateWarps * 32, FAST ? 6 : 1) build_state_kernel(ttl_volume v, ttl_params prm,
+template <int FAST, int MINB>
+__global__ void __launch_bounds__(kStateWarps * 32, MINB) build_state_kernel(ttl_volume v, ttl_params prm,
                                                                                      ttl_batch b, int cur, int warp_smem,
                                                                                      int pf) {
   extern __shared__ __align__(128) uint8_t smem_dyn[];
@@ -1029,8 +1181,10 @@ __global__ void __launch_bounds__(kStateWarps * 32, FAST ? 6 : 1) build_state_ke
     // the actor has just read; a refilled slot starts from zeros (L == 1)
     const __nv_bfloat16* old_dirs =
         reinterpret_cast<const __nv_bfloat16*>(b.state_bf16[cur]) + (size_t)r * b.ld_bf16 + 7 * 48;
+    const float3 prev_tip = make_float3(rec.tx, rec.ty, rec.tz);
+    if (FAST >= 2 && build_state_row_c45_bf16_dedup(v, prm, L, tip, o16, smem_f, lane, old_dirs, prev_tip)) return;
     build_state_row_c45_bf16(v, prm, P, L, tip, o16, b.ld_bf16, smem_f, lane, pf, (pf & 8) ? nullptr : old_dirs,
-                             make_float3(rec.tx, rec.ty, rec.tz));
+                             prev_tip);
   }
   else
     build_state_row(v, prm, P, L, tip, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
@@ -1152,9 +1306,15 @@ constexpr int kStateSmem = kStateWarps * kWarpSmemBytes;
 int state_kernels_ready() {
   static bool done = false;
   if (done) return 0;
-  cudaError_t e = cudaFuncSetAttribute(build_state_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  cudaError_t e = cudaFuncSetAttribute(build_state_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(build_state_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+    e = cudaFuncSetAttribute(build_state_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(build_state_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(build_state_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(build_state_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(reset_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
@@ -1259,12 +1419,19 @@ static void launch_propagate(const ttl_volume* vol, const ttl_params* prm, const
   }
 }
 
+// A/B knobs of the state kernel (TTL_STATE_OPTIONS or ttl_state_options()): bits 0-1 prefetch the
+// row's lines into L1 (1) / L2 (2) ahead of the gathers, bit 3 recompute the direction block from the
+// fp32 points instead of shifting the previous row's, bit 4 the deduplicated 32-voxel gather instead
+// of the 56-corner one (bits 5-6: its CTAs per SM, 2/3/4).  Default 0: every alternative was
+// measured slower or equal.
+static std::atomic<int> g_state_opts{-1};
 static int state_prefetch_level() {
-  static int v = -1;
+  int v = g_state_opts.load(std::memory_order_relaxed);
   if (v < 0) {
-    const char* e = getenv("TTL_STATE_PREFETCH");
+    const char* e = getenv("TTL_STATE_OPTIONS");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 15) v = 0;
+    if (v < 0 || v > 127) v = 0;
+    g_state_opts.store(v);
   }
   return v;
 }
@@ -1276,13 +1443,28 @@ static int launch_build_state(const ttl_volume* vol, const ttl_params* prm, cons
   // the bf16-only path keeps just the corner table in shared memory: a small allocation leaves
   // the SM's 228 KB to L1, which is what dedupes the overlapping trilinear corners
   const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;
-  if (b->bf16_layout == 1)
+  const bool dedup = b->bf16_layout == 1 && prm->n_dirs == 100 && b->ld_bf16 == 640 && prm->step_vox > 0.0 &&
+                     prm->step_vox < 1.0 && (state_prefetch_level() & 16);
+  const int occ = (state_prefetch_level() >> 5) & 3;
+  if (dedup && occ == 0)
     TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<1>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
+               ttl_launch_chain(build_state_kernel<2, 2>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
+                                kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0)));
+  else if (dedup && occ == 1)
+    TTL_LAUNCH("build_state_kernel", s,
+               ttl_launch_chain(build_state_kernel<2, 3>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
+                                kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0)));
+  else if (dedup)
+    TTL_LAUNCH("build_state_kernel", s,
+               ttl_launch_chain(build_state_kernel<2, 4>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
+                                kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0)));
+  else if (b->bf16_layout == 1)
+    TTL_LAUNCH("build_state_kernel", s,
+               ttl_launch_chain(build_state_kernel<1, 6>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
                                 kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0)));
   else
     TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<0>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
+               ttl_launch_chain(build_state_kernel<0, 1>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
                                 kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, (g_ttl_pdl.load() == 1 ? 4 : 0)));
   return 0;
 }
@@ -1302,6 +1484,8 @@ static int check_step_args(const ttl_volume* vol, const ttl_params* prm, const t
     return TTL_ERR_BAD_ARG;
   return 0;
 }
+
+void ttl_state_options(int32_t bits) { g_state_opts.store(bits & 127); }
 
 int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
                  const float* actions, int32_t lda, const double* noise, int32_t n_upper,
