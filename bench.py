@@ -508,7 +508,7 @@ if __name__ == '__main__':
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--fp32-state', dest='bf16_state_only', action='store_false',
                     help='also materialise the fp32 state rows every step (the reference API tensor)')
-    ap.add_argument('--graph', action='store_true', help='replay the 6 kernels of a step from a CUDA graph')
+    ap.add_argument('--graph', action='store_true', help='replay the kernels of a step from a CUDA graph')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs)')
     ap.add_argument('--config', type=int, default=2, choices=[2, 3],
                     help='2: BASELINE.json configs[1] (default); 3: configs[2], the 290^3 0.5 mm volume')

@@ -196,6 +196,28 @@ def test_state_kernel_variants_write_identical_rows():
         np.testing.assert_array_equal(out[0].data, b.data)
 
 
+def test_cuda_graph_replay_equals_plain_launches():
+    """validation_episode with the step replayed from two captured CUDA graphs (one per ping-pong
+    parity; programmatic-dependent-launch edges inside) vs plain launches: same streamlines."""
+    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    n = len(seeds)
+    out = []
+    try:
+        for graph in (False, True):
+            alg.use_cuda_graph = graph
+            st = env.reset_streaming(0, n, 256, fp32_state=False)
+            alg.validation_episode(st, env, 0.0)
+            if graph:
+                assert alg._runner.graphs is not None and alg._runner.replays > 10
+            out.append(env.get_streamlines())
+    finally:
+        alg.use_cuda_graph = False
+    a, b = out
+    np.testing.assert_array_equal(a.lengths, b.lengths)
+    np.testing.assert_array_equal(a.data, b.data)
+    np.testing.assert_array_equal(a.data_per_streamline['flags'], b.data_per_streamline['flags'])
+
+
 def test_locality_order_does_not_change_any_streamline():
     """Streaming tracker with the seeds entering the slots in voxel raster order (ttl_batch.order) vs
     in row order: every row holds the same streamline, bit for bit, and the output order is the
