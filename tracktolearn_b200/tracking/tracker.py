@@ -112,9 +112,12 @@ class Tracker(object):
 
     def track_to_file(self, env, path, dims, voxel_sizes):
         """What ``ttl_track.py`` does with ``track`` + ``nib.streamlines.save`` (runners/ttl_track.py:
-        172-186), on packed arrays: length filter (tracker.py:118-121), voxel -> file space
-        (:127-136), streamed to a .trk / .tck writer.  Returns the number of streamlines kept."""
+        172-186), on packed arrays and on the device: dipy ``length`` and the min/max filter
+        (tracker.py:118-121), ``compress_streamlines`` (:123-125), voxel -> file space (:127-136);
+        only the kept, transformed float32 points cross PCIe, into pinned memory, and go to a
+        streaming .trk / .tck writer.  Returns the number of streamlines kept."""
         from tracktolearn_b200.io.streamlines import TckWriter, TrkWriter, detect_format
+        from tracktolearn_b200.tracking.postprocess import compress_packed, lengths_packed
         fmt = detect_format(path)
         affine = np.asarray(env.affine_vox2rasmm, dtype=np.float64)
         np.random.shuffle(env.seeds)      # tracker.py:94
@@ -122,23 +125,44 @@ class Tracker(object):
         lo, hi = self.min_length / vox_size, self.max_length / vox_size
         writer = (TrkWriter(path, dims, voxel_sizes, affine, self.save_seeds) if fmt == 'trk'
                   else TckWriter(path))
+        self.alg.agent.eval()
         try:
-            for batch in self.track_packed(env, copy=False):
-                lens = streamline_lengths(batch.data, batch.offsets)
-                keep = (lo <= lens) & (lens <= hi)
-                npts = np.diff(batch.offsets)
-                sel = np.repeat(keep, npts)
-                data = batch.data[sel]
-                offsets = np.concatenate(([0], np.cumsum(npts[keep]))).astype(np.int64)
-                if self.compress:     # after the length filter, before the space change (tracker.py:120-129)
-                    data, offsets = self._compress(env, data, offsets)
-                data = data.astype(np.float64)
-                if fmt == 'trk':
-                    data = (data + 0.5) * vox_size
+            for start, end, slots in self._passes(env):
+                if slots is None or slots >= end - start:
+                    state = env.reset(start, end)
                 else:
-                    data = data @ affine[:3, :3] + affine[:3, 3]     # tracker.py:133-136
-                writer.write(data.astype(np.float32), offsets,
-                             batch.data_per_streamline['seeds'][keep] - 0.5)
+                    bf16_actor = getattr(self.alg.agent.actor, 'precision', 'fp32') == 'bf16'
+                    state = env.reset_streaming(start, end, slots, fp32_state=not bf16_actor)
+                self.alg.validation_episode(state, env, self.prob)
+                pts, offsets = env.get_streamlines_device()
+                n = int(offsets.shape[0]) - 1
+                if n <= 0:
+                    continue
+                lens = lengths_packed(pts, offsets)
+                keep = (lens >= lo) & (lens <= hi)
+                npts = offsets[1:] - offsets[:-1]
+                data = pts[torch.repeat_interleave(keep, npts)]
+                new_off = torch.zeros((int(keep.sum().item()) + 1,), dtype=torch.int64, device=pts.device)
+                torch.cumsum(npts[keep], 0, out=new_off[1:])
+                if self.compress:     # after the length filter, before the space change (tracker.py:120-129)
+                    data, new_off = compress_packed(data, new_off, tol_error=float(self.compress))
+                d64 = data.to(torch.float64)
+                if fmt == 'trk':
+                    out = ((d64 + 0.5) * float(vox_size)).to(torch.float32)
+                else:                 # s . affine[:3,:3] + affine[:3,3] (tracker.py:133-136), term by term
+                    A = affine
+                    cols = [d64[:, 0] * A[0, c] + d64[:, 1] * A[1, c] + d64[:, 2] * A[2, c] + A[c, 3]
+                            for c in range(3)]
+                    out = torch.stack(cols, 1).to(torch.float32)
+                h_data = env._pinned('file_pts', out.numel(), torch.float32)
+                h_off = env._pinned('file_off', new_off.numel(), torch.int64)
+                h_keep = env._pinned('file_keep', n, torch.uint8)
+                h_data.copy_(out.reshape(-1), non_blocking=True)
+                h_off.copy_(new_off, non_blocking=True)
+                h_keep.copy_(keep.to(torch.uint8), non_blocking=True)
+                torch.cuda.current_stream(env.device).synchronize()
+                seeds = np.asarray(env.initial_points)[h_keep.numpy().astype(bool)] - 0.5
+                writer.write(h_data.numpy().reshape(-1, 3), h_off.numpy(), seeds)
         finally:
             writer.close()
         return writer.n
