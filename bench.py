@@ -204,9 +204,6 @@ def draw_seeds(seed_mask, rank):
     rs = np.random.RandomState(1337 + rank)
     seeds = random_seeds_from_mask(seed_mask, NPV, rs)
     rs.shuffle(seeds)
-    if os.environ.get('TTL_BENCH_SORTED_SEEDS'):     # locality experiment: seeds in voxel raster order
-        v = np.floor(seeds + 0.5).astype(np.int64)
-        seeds = seeds[np.lexsort((v[:, 2], v[:, 1], v[:, 0]))]
     return seeds
 
 
