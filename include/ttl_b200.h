@@ -130,6 +130,18 @@ typedef struct ttl_batch {
 int ttl_pad_channels(const float* src, float* dst, int64_t n_voxels, int32_t C, int32_t CP,
                      void* stream);
 
+/* Peak extraction at load time (environments/env.py:405-432, the reference's only SH-to-SF
+ * projection): per voxel with a non-zero coefficient sum, SF = sh . basis^T on n_vertices sphere
+ * directions (double), values below absolute_threshold zeroed, dipy peak_directions (local maxima over
+ * the sphere's edges given as a padded neighbour table [n_vertices][max_degree], -1 = none; relative
+ * threshold; min_separation_deg between kept peaks), the first npeaks directions scaled by
+ * value / first value -> out_peaks [n_voxels][npeaks * 3] fp32 (zeros elsewhere).
+ * sh [n_voxels][ld] fp32 with C <= 64 coefficients; basis [n_vertices][C], vertices [n_vertices][3] f64. */
+int ttl_peaks_from_sh(const float* sh, int64_t n_voxels, int32_t C, int32_t ld, const double* basis,
+                      const double* vertices, const int32_t* neighbours, int32_t n_vertices,
+                      int32_t max_degree, double relative_threshold, double absolute_threshold,
+                      double min_separation_deg, int32_t npeaks, float* out_peaks, void* stream);
+
 /* ---- TrackingEnvironment ------------------------------------------------------------------ */
 
 /* TrackingEnvironment.reset / nreset (tracking_env.py:47-133): seeds [n][3] float64 voxel

@@ -412,6 +412,92 @@ def actor_forward(sd, state, probabilistic=0.0, eps=None):
 
 
 # --------------------------------------------------------------------------------------
+# L1: load-time peak extraction (environments/env.py:405-432)
+# --------------------------------------------------------------------------------------
+def sh_basis_matrix(vertices, order=8):
+    """dipy ``sh_to_sf_matrix(sphere, order, "descoteaux07")`` (legacy basis, env.py:414) restated with
+    scipy's complex harmonics: for even l and m = -l..l, sqrt(2) Re Y_l^|m| (m < 0), Y_l^0,
+    sqrt(2) Im Y_l^m (m > 0).  -> B [V, n_coefs] float64, SF = sh . B^T."""
+    from scipy.special import sph_harm_y
+    v = np.asarray(vertices, dtype=np.float64)
+    polar = np.arccos(np.clip(v[:, 2], -1.0, 1.0))
+    azim = np.arctan2(v[:, 1], v[:, 0])
+    cols = []
+    for l in range(0, order + 1, 2):
+        for m in range(-l, l + 1):
+            y = sph_harm_y(l, abs(m), polar, azim)
+            if m < 0:
+                cols.append(np.sqrt(2.0) * y.real)
+            elif m == 0:
+                cols.append(y.real)
+            else:
+                cols.append(np.sqrt(2.0) * y.imag)
+    return np.stack(cols, axis=1)
+
+
+def local_maxima(odf, edges):
+    """dipy ``local_maxima`` (reconst/recspeed.pyx, restated): a vertex is a peak when it is greater
+    than at least one neighbour and smaller than none.  Values descending (ties: lower index first)."""
+    odf = np.asarray(odf, dtype=np.float64)
+    state = np.zeros(len(odf), dtype=np.int64)        # 0 unvisited, 1 maybe, 2 not a peak
+    for a, b in edges:
+        if odf[a] < odf[b]:
+            state[a] = 2
+            state[b] = max(state[b], 1)
+        elif odf[a] > odf[b]:
+            state[a] = max(state[a], 1)
+            state[b] = 2
+    idx = np.nonzero(state == 1)[0]
+    order = np.lexsort((idx, -odf[idx]))
+    idx = idx[order]
+    return odf[idx], idx
+
+
+def peak_directions(odf, vertices, edges, relative_peak_threshold=0.5, min_separation_angle=25.0):
+    """dipy ``peak_directions`` restated: local maxima, drop those below the relative threshold
+    (measured from max(min(odf), 0)), then greedily drop directions within the separation angle
+    (|cos|, antipodal symmetry) of an already kept one."""
+    values, indices = local_maxima(odf, edges)
+    n = len(values)
+    if n == 0 or values[0] < 0.0:
+        return np.zeros((0, 3)), np.zeros(0), np.zeros(0, dtype=np.int64)
+    if n == 1:
+        return vertices[indices], values, indices
+    odf_min = max(float(np.min(odf)), 0.0)
+    norm = values - odf_min
+    n = int(np.sum(np.cumprod(norm >= relative_peak_threshold * norm[0])))
+    indices = indices[:n]
+    dirs = vertices[indices]
+    cos_sim = np.cos(np.deg2rad(min_separation_angle))
+    kept = []
+    for i in range(n):
+        if all(abs(float(np.dot(dirs[i], dirs[j]))) <= cos_sim for j in kept):
+            kept.append(i)
+    kept = np.asarray(kept, dtype=np.int64)
+    return dirs[kept], values[kept], indices[kept]
+
+
+def peaks_from_sh(data, vertices, edges, B, npeaks=5, relative_threshold=0.1, absolute_threshold=0.0):
+    """environments/env.py:405-432: per voxel with a non-zero coefficient sum, scilpy
+    ``get_maximas(sh, sphere, B, 0.1, 0)`` (SF = sh . B^T, values below the absolute threshold zeroed,
+    ``peak_directions`` with the default 25 degree separation), the first ``npeaks`` directions scaled by
+    value / first value -> [..., npeaks * 3] float32 (``reshape_peaks_for_visualization``)."""
+    data = np.asarray(data)
+    shape = data.shape[:-1]
+    flat = data.reshape(-1, data.shape[-1])
+    out = np.zeros((flat.shape[0], npeaks, 3), dtype=np.float64)
+    for i in np.nonzero(np.sum(flat, axis=-1))[0]:
+        sf = np.dot(flat[i], B.T)
+        sf[sf < absolute_threshold] = 0.0
+        d, val, _ = peak_directions(sf, vertices, edges, relative_threshold, 25.0)
+        if len(val):
+            n = min(npeaks, len(val))
+            w = val[:n] / val[0] if val[0] != 0 else np.zeros(n)
+            out[i, :n] = d[:n] * w[:, None]
+    return out.reshape(shape + (npeaks * 3,)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
 # O1-O2: TractOracle-Net
 # --------------------------------------------------------------------------------------
 def streamline_length(s):

@@ -58,6 +58,8 @@ SIGNATURES = {
     'ttl_state_options': (None, [c_i32]),
     'ttl_prof_report': (c_i32, [ctypes.c_char_p, c_i32]),
     'ttl_pad_channels': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
+    'ttl_peaks_from_sh': (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_f64, c_f64, c_f64,
+                                  c_i32, c_vp, c_vp]),
     'ttl_env_reset': (c_i32, [P(Volume), P(Params), P(Batch), c_vp, c_vp]),
     'ttl_env_step': (c_i32, [P(Volume), P(Params), P(Batch), c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]),
     'ttl_env_step_head': (c_i32, [P(Volume), P(Params), P(Batch), c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]),

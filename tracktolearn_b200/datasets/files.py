@@ -56,22 +56,26 @@ def set_sh_order_basis(sh, sh_basis, target_basis='descoteaux07', target_order=6
     return np.ascontiguousarray(sh, dtype=np.float32)
 
 
-def load_files(signal_file, in_seed, in_mask, sh_basis, target_sh_order=6, compute_peaks=False):
+def load_files(signal_file, in_seed, in_mask, sh_basis, target_sh_order=6, compute_peaks=False,
+               device='cuda:0'):
     """Reference: environments/env.py:350-449.  Peaks are only needed for the alignment reward,
-    which ``ttl_track`` never computes (compute_reward=False, ttl_track.py:80); the reference still
-    spends minutes extracting them voxel by voxel (env.py:417-425) -- we do not."""
+    which ``ttl_track`` never computes (compute_reward=False, ttl_track.py:80); the reference extracts
+    them for every voxel in a Python loop regardless (env.py:417-425, minutes on a whole brain).  Here
+    they are computed only when asked for, by one kernel launch (datasets/peaks.py), on this package's
+    own 321-direction hemisphere instead of dipy's repulsion724 (absent offline)."""
     signal = nifti.load(signal_file)
     if not np.allclose(np.mean(signal.zooms[:3]), signal.zooms[0], atol=1e-03):
         print('WARNING: ODF SH file is not isotropic. Tracking cannot be ran robustly. You are '
               'entering undefined behavior territory.')
     data = set_sh_order_basis(signal.get_fdata(dtype=np.float32), sh_basis,
                               target_order=target_sh_order, target_basis='descoteaux07')
+    peaks_volume = None
     if compute_peaks:
-        raise NotImplementedError('peak extraction from files (env.py:405-432) is a next-row item; '
-                                  'pass peaks explicitly when rewards are needed')
+        from tracktolearn_b200.datasets.peaks import compute_peaks as _compute_peaks
+        peaks_volume = MRIDataVolume(_compute_peaks(data, device=device).cpu().numpy(), signal.affine)
     seeding = nifti.load(in_seed)
     tracking = nifti.load(in_mask)
     signal_volume = MRIDataVolume(data, signal.affine)
     seeding_volume = MRIDataVolume(seeding.get_fdata(), seeding.affine)
     tracking_volume = MRIDataVolume(tracking.get_fdata(), tracking.affine)
-    return (signal_volume, None, tracking_volume, seeding_volume)
+    return (signal_volume, peaks_volume, tracking_volume, seeding_volume)

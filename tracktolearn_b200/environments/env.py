@@ -168,7 +168,8 @@ class BaseEnv(object):
         from tracktolearn_b200.datasets.files import load_files
         (input_volume, peaks_volume, tracking_mask, seeding_mask) = load_files(
             env_dto['in_odf'], env_dto['in_seed'], env_dto['in_mask'], env_dto['sh_basis'],
-            env_dto['target_sh_order'], compute_peaks=bool(env_dto.get('compute_reward')))
+            env_dto['target_sh_order'], compute_peaks=bool(env_dto.get('compute_reward')),
+            device=env_dto.get('device', 'cuda:0'))
         subj_files = (input_volume, tracking_mask, seeding_mask, peaks_volume, env_dto['reference'])
         return cls(subj_files, 'testing', env_dto)
 
