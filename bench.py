@@ -66,7 +66,7 @@ def ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the step's kernels from
     the committed `ncu --set full` capture of this same command (profiles/README.md); None when the
     summary file is absent."""
-    path = os.path.join(ROOT, 'profiles', 'r1_step_v6_ncu_summary.json')
+    path = os.path.join(ROOT, 'profiles', 'r1_step_v7_ncu_summary.json')
     if not os.path.exists(path):
         return {}
 
@@ -117,19 +117,39 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
+
+    def wait_first(self, timeout_s):
+        """Block until nvidia-smi has produced its first sample (it starts slowly)."""
+        t0 = time.monotonic()
+        while self.proc is not None and not self.rows and time.monotonic() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t_begin = time.monotonic()
+
+    def mark_end(self):
+        self.t_end = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0, t1 = getattr(self, 't_begin', 0.0), getattr(self, 't_end', float('inf'))
+        # a sample is read ~one period after it was taken: accept rows up to 40 ms past the end mark;
+        # a timed region shorter than the sampling period falls back to the nearest samples around it
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.04]
+        window = 'timed region'
+        if len(rows) < 2:
+            rows = [r for (t, r) in self.rows if t0 - 0.1 <= t <= t1 + 0.1]
+            window = 'timed region +-100 ms (region shorter than the sampling period)'
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(',')]
             if len(f) < 9:
                 continue
@@ -144,7 +164,7 @@ class ClockSampler(object):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': float(max(smax)) if smax else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 # ------------------------------------------------------------------------------------------
@@ -319,6 +339,10 @@ def main_gpu(args):
     # two mean lifetimes to reach its steady-state mix of streamline ages and positions; right after
     # reset every streamline still sits on the seed shell and the gather enjoys unrepresentative L2
     # locality
+    # the clock sampler starts before the untimed steps: nvidia-smi needs 0.1-0.3 s before its first
+    # sample, longer than a short timed region; only the samples taken between the two marks count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(BURN_IN):
         one_step(action_buf)
     for _ in range(args.warmup):
@@ -327,15 +351,16 @@ def main_gpu(args):
     steps_before = env.streamline_steps()
     launches_before = lib.ttl_launch_count()
     replays_before = runner_box['r'].replays
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.wait_first(2.0)
+    sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
         one_step(action_buf)
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     # kernels launched one by one + kernels replayed from the captured step graphs
@@ -406,7 +431,7 @@ def main_gpu(args):
     dense_launches = sum(n for n, _ in dn)
     dense_total_ms = sum(ms for _, ms in dn)
     traffic = ncu_traffic()
-    traffic_src = 'profiles/r1_step_v6_ncu_summary.json (ncu --set full of this command, bytes per launch)'
+    traffic_src = 'profiles/r1_step_v7_ncu_summary.json (ncu --set full of this command, bytes per launch)'
     roofline = None
     if dense_launches:
         steps_prof = dense_launches / 3.0
