@@ -127,16 +127,23 @@ def main():
     gather_ms = None
     n_total = len(local)
     if world > 1 and not a.no_gather:
+        # the final exchange from the device (the env still holds the last pass): every rank's packed
+        # streamlines go to rank 0 over NVLink, one pinned D2H there.  The first call also sets up
+        # NCCL's point-to-point channels.
         gather_ms = []
-        for _ in range(2):      # the first call also sets up NCCL's point-to-point channels
+        for _ in range(3):
             barrier()
             t0 = time.perf_counter()
-            merged = parallel.gather_tractogram(local)
+            merged = parallel.gather_env_streamlines(env, copy=False)
             barrier()
             gather_ms.append(1000.0 * (time.perf_counter() - t0))
         if rank == 0:
             n_total = len(merged)
             ok['gathered_all'] = bool(n_total == a.seeds)
+            s0, s1 = parallel.shard_bounds(len(seeds), 0, world)
+            ok['gathered_rank0_slice_identical'] = bool(
+                np.array_equal(merged.data[:merged.offsets[s1 - s0]], local.data)
+                and np.array_equal(merged.data_per_streamline['seeds'], seeds))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     u = torch.tensor([units, steps, float(all(ok.values()))], dtype=torch.float64, device=dev)
     if world > 1:

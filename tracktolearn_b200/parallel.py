@@ -50,25 +50,39 @@ def _pinned(nbytes):
     return cur
 
 
-def gather_tractogram(local, dst=0):
-    """Gather packed tractograms on rank `dst` in rank order.  Returns the merged Tractogram on
-    `dst` and None elsewhere.  One all_gather of the sizes, then every rank sends exactly its rows
-    straight into its slice of rank `dst`'s buffer (batched point-to-point: NVLink device-to-device
-    under NCCL, one pinned D2H on `dst`; plain CPU tensors under gloo)."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
-        return local
+def _pinned_named(name, nbytes):
+    cur = _PINNED.get(name)
+    if cur is None or cur.numel() < nbytes:
+        cur = torch.empty((int(nbytes * 1.25) + 4096,), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        _PINNED[name] = cur
+    return cur
+
+
+def gather_packed(points, lengths, seeds, flags, dst=0, copy=True):
+    """Gather packed streamlines on rank `dst` in rank order.
+
+    ``points`` [n_pts, 3] float32, ``lengths`` [n] int64, ``seeds`` [n, 3] float64, ``flags`` [n] int64:
+    tensors on this rank's device for the backend (CUDA under NCCL -- e.g. straight from
+    ``env.get_streamlines_device()``, no host round trip -- CPU under gloo).  One all_gather of the
+    sizes, then every rank sends exactly its rows into its slice of `dst`'s buffers (batched
+    point-to-point: device-to-device over NVLink under NCCL) and `dst` makes one D2H copy per array
+    into grow-only pinned memory.  With ``copy=False`` the returned arrays are views of that pinned
+    memory, valid until the next gather.  Returns a Tractogram on `dst`, None elsewhere."""
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = _device_for_backend()
-    n_sl = len(local)
-    n_pts = int(local.offsets[-1]) if n_sl else 0
+    parts = [(points.to(dev, dtype=torch.float32).reshape(-1, 3).contiguous(), 3, torch.float32, 'pts'),
+             (lengths.to(dev, dtype=torch.int64).reshape(-1, 1).contiguous(), 1, torch.int64, 'len'),
+             (seeds.to(dev, dtype=torch.float64).reshape(-1, 3).contiguous(), 3, torch.float64, 'seeds'),
+             (flags.to(dev, dtype=torch.int64).reshape(-1, 1).contiguous(), 1, torch.int64, 'flags')]
+    n_sl, n_pts = int(parts[1][0].shape[0]), int(parts[0][0].shape[0])
     sizes = torch.tensor([n_sl, n_pts], dtype=torch.int64, device=dev)
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes)
     all_sizes = torch.stack(all_sizes).cpu().numpy()
-
-    def gather_rows(arr, counts, width, dtype):
-        mine = torch.as_tensor(np.ascontiguousarray(arr).reshape(-1, width)).to(dev, dtype=dtype).contiguous()
-        ops, buf = [], None
+    n_per, p_per = all_sizes[:, 0], all_sizes[:, 1]
+    ops, bufs = [], []
+    for mine, width, dtype, name in parts:
+        counts = p_per if name == 'pts' else n_per
         if rank == dst:
             buf = torch.empty((int(counts.sum()), width), dtype=dtype, device=dev)
             o = 0
@@ -79,29 +93,55 @@ def gather_tractogram(local, dst=0):
                 elif c > 0:
                     ops.append(dist.P2POp(dist.irecv, buf[o:o + c], r))
                 o += c
+            bufs.append(buf)
         elif int(counts[rank]) > 0:
             ops.append(dist.P2POp(dist.isend, mine, dst))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        if rank != dst:
-            return None
-        if buf.is_cuda:
-            host = _pinned(buf.numel() * buf.element_size())[:buf.numel() * buf.element_size()].view(dtype)
-            host = host.view(buf.shape)
-            host.copy_(buf)
-            return host.numpy().copy()
-        return buf.numpy()
-
-    n_per, p_per = all_sizes[:, 0], all_sizes[:, 1]
-    data = gather_rows(local.data, p_per, 3, torch.float32)
-    lens = gather_rows(np.diff(local.offsets).astype(np.int64), n_per, 1, torch.int64)
-    seeds = gather_rows(np.asarray(local.data_per_streamline.get('seeds', np.zeros((n_sl, 3)))), n_per, 3,
-                        torch.float64)
-    flags = gather_rows(np.asarray(local.data_per_streamline.get('flags', np.zeros(n_sl))).astype(np.int64),
-                        n_per, 1, torch.int64)
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     if rank != dst:
         return None
+    host = []
+    for buf, (_, _, dtype, name) in zip(bufs, parts):
+        if buf.is_cuda:
+            nbytes = buf.numel() * buf.element_size()
+            h = _pinned_named(name, nbytes)[:nbytes].view(dtype).view(buf.shape)
+            h.copy_(buf, non_blocking=True)
+            host.append(h)
+        else:
+            host.append(buf)
+    if bufs and bufs[0].is_cuda:
+        torch.cuda.current_stream(bufs[0].device).synchronize()
+    arrs = [h.numpy().copy() if copy else h.numpy() for h in host]
+    data, lens, gseeds, gflags = arrs
     offsets = np.concatenate(([0], np.cumsum(lens[:, 0]))).astype(np.int64)
-    return Tractogram(data=data, offsets=offsets,
-                      data_per_streamline={'seeds': seeds, 'flags': flags[:, 0]})
+    return Tractogram(data=data, offsets=offsets, data_per_streamline={'seeds': gseeds, 'flags': gflags[:, 0]})
+
+
+def gather_tractogram(local, dst=0, copy=True):
+    """Gather host-side packed tractograms (``Tractogram``) on rank `dst` in rank order; returns the
+    merged Tractogram on `dst` and None elsewhere.  Prefer ``gather_env_streamlines`` when the
+    streamlines are still on the device."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    n_sl = len(local)
+    return gather_packed(
+        torch.as_tensor(np.ascontiguousarray(local.data, dtype=np.float32)).reshape(-1, 3),
+        torch.as_tensor(np.diff(local.offsets).astype(np.int64)),
+        torch.as_tensor(np.ascontiguousarray(local.data_per_streamline.get('seeds', np.zeros((n_sl, 3))),
+                                             dtype=np.float64)).reshape(-1, 3),
+        torch.as_tensor(np.asarray(local.data_per_streamline.get('flags', np.zeros(n_sl))).astype(np.int64)),
+        dst=dst, copy=copy)
+
+
+def gather_env_streamlines(env, dst=0, copy=True):
+    """The final exchange of a multi-GPU tracking run, from the device: this rank's packed streamlines
+    (``env.get_streamlines_device()``), seeds and flags go to rank `dst` without touching the host on
+    the sending side.  Single process: the env's own tractogram."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return env.get_streamlines(copy=copy)
+    pts, offsets = env.get_streamlines_device()
+    n = int(offsets.shape[0]) - 1
+    seeds = torch.as_tensor(np.ascontiguousarray(env.initial_points, dtype=np.float64)).reshape(-1, 3)
+    return gather_packed(pts, offsets[1:] - offsets[:-1], seeds, env._batch.flags[:n].to(torch.int64),
+                         dst=dst, copy=copy)
