@@ -47,7 +47,17 @@ class TrackToLearnTrack(object):
         self.compute_reward = False
         if not torch.cuda.is_available():
             raise SystemExit('ttl_track (tracktolearn_b200) needs a CUDA device; there is no CPU path')
-        self.device = torch.device('cuda')
+        # one process per GPU under torchrun: NCCL for the final tractogram gather only
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        if self.world > 1:
+            import torch.distributed as dist
+            local = int(os.environ.get('LOCAL_RANK', '0'))
+            torch.cuda.set_device(local)
+            if not dist.is_initialized():
+                dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            self.device = torch.device('cuda', local)
+        else:
+            self.device = torch.device('cuda')
         self.fa_map = None      # the reference looks up the wrong key here: never set
         self.agent = track_dto['agent']
         self.hyperparameters = track_dto['hyperparameters']
@@ -104,7 +114,8 @@ class TrackToLearnTrack(object):
         tracker = Tracker(alg, self.n_actor, compress=self.compress, min_length=self.min_length,
                           max_length=self.max_length, save_seeds=self.save_seeds)
         n = tracker.track_to_file(env, self.out_tractogram, ref_img.shape[:3], ref_img.zooms[:3])
-        print('Wrote {} streamlines to {}.'.format(n, self.out_tractogram))
+        if int(os.environ.get('RANK', '0')) == 0:
+            print('Wrote {} streamlines to {}.'.format(n, self.out_tractogram))
         return n
 
 

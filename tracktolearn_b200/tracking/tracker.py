@@ -118,54 +118,87 @@ class Tracker(object):
         streaming .trk / .tck writer.  Returns the number of streamlines kept."""
         from tracktolearn_b200.io.streamlines import TckWriter, TrkWriter, detect_format
         from tracktolearn_b200.tracking.postprocess import compress_packed, lengths_packed
+        import torch.distributed as dist
+        from tracktolearn_b200 import parallel
         fmt = detect_format(path)
         affine = np.asarray(env.affine_vox2rasmm, dtype=np.float64)
         np.random.shuffle(env.seeds)      # tracker.py:94
+        # One process per GPU (torchrun): every rank shuffled the same seed list with the same RNG state;
+        # it keeps its contiguous slice, tracks and post-processes it on its own device, and rank 0
+        # receives the packed results over NCCL and writes them in rank order -- the order one GPU
+        # produces (SURVEY 8(e)).
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        if world > 1:
+            env.seeds = parallel.shard_seeds(env.seeds, rank, world)
         vox_size = np.mean(np.abs(affine)[np.diag_indices(4)][:3])
         lo, hi = self.min_length / vox_size, self.max_length / vox_size
-        writer = (TrkWriter(path, dims, voxel_sizes, affine, self.save_seeds) if fmt == 'trk'
-                  else TckWriter(path))
+        writer = None
+        if rank == 0:
+            writer = (TrkWriter(path, dims, voxel_sizes, affine, self.save_seeds) if fmt == 'trk'
+                      else TckWriter(path))
         self.alg.agent.eval()
+        n_passes = len(list(self._passes(env)))
+        if world > 1:       # ranks may differ by one seed: agree on the number of passes
+            t = torch.tensor([n_passes], device=env.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_passes = int(t.item())
+        passes = list(self._passes(env))
         try:
-            for start, end, slots in self._passes(env):
-                if slots is None or slots >= end - start:
-                    state = env.reset(start, end)
-                else:
-                    bf16_actor = getattr(self.alg.agent.actor, 'precision', 'fp32') == 'bf16'
-                    state = env.reset_streaming(start, end, slots, fp32_state=not bf16_actor)
-                self.alg.validation_episode(state, env, self.prob)
-                pts, offsets = env.get_streamlines_device()
-                n = int(offsets.shape[0]) - 1
-                if n <= 0:
+            for ip in range(n_passes):
+                out = torch.zeros((0, 3), dtype=torch.float32, device=env.device)
+                new_off = torch.zeros((1,), dtype=torch.int64, device=env.device)
+                seeds_kept = np.zeros((0, 3))
+                if ip < len(passes) and passes[ip][1] > passes[ip][0]:
+                    start, end, slots = passes[ip]
+                    if slots is None or slots >= end - start:
+                        state = env.reset(start, end)
+                    else:
+                        bf16_actor = getattr(self.alg.agent.actor, 'precision', 'fp32') == 'bf16'
+                        state = env.reset_streaming(start, end, slots, fp32_state=not bf16_actor)
+                    self.alg.validation_episode(state, env, self.prob)
+                    pts, offsets = env.get_streamlines_device()
+                    lens = lengths_packed(pts, offsets)
+                    keep = (lens >= lo) & (lens <= hi)
+                    npts = offsets[1:] - offsets[:-1]
+                    data = pts[torch.repeat_interleave(keep, npts)]
+                    new_off = torch.zeros((int(keep.sum().item()) + 1,), dtype=torch.int64, device=pts.device)
+                    torch.cumsum(npts[keep], 0, out=new_off[1:])
+                    if self.compress:     # after the length filter, before the space change (tracker.py:120-129)
+                        data, new_off = compress_packed(data, new_off, tol_error=float(self.compress))
+                    d64 = data.to(torch.float64)
+                    if fmt == 'trk':
+                        out = ((d64 + 0.5) * float(vox_size)).to(torch.float32)
+                    else:                 # s . affine[:3,:3] + affine[:3,3] (tracker.py:133-136), term by term
+                        A = affine
+                        cols = [d64[:, 0] * A[0, c] + d64[:, 1] * A[1, c] + d64[:, 2] * A[2, c] + A[c, 3]
+                                for c in range(3)]
+                        out = torch.stack(cols, 1).to(torch.float32)
+                    seeds_kept = np.asarray(env.initial_points)[keep.cpu().numpy()] - 0.5
+                if world > 1:
+                    n_kept = int(new_off.shape[0]) - 1
+                    merged = parallel.gather_packed(out, new_off[1:] - new_off[:-1], torch.as_tensor(seeds_kept),
+                                                    torch.zeros((n_kept,), dtype=torch.int64), copy=False)
+                    if rank == 0 and len(merged) > 0:
+                        writer.write(merged.data, merged.offsets, merged.data_per_streamline['seeds'])
                     continue
-                lens = lengths_packed(pts, offsets)
-                keep = (lens >= lo) & (lens <= hi)
-                npts = offsets[1:] - offsets[:-1]
-                data = pts[torch.repeat_interleave(keep, npts)]
-                new_off = torch.zeros((int(keep.sum().item()) + 1,), dtype=torch.int64, device=pts.device)
-                torch.cumsum(npts[keep], 0, out=new_off[1:])
-                if self.compress:     # after the length filter, before the space change (tracker.py:120-129)
-                    data, new_off = compress_packed(data, new_off, tol_error=float(self.compress))
-                d64 = data.to(torch.float64)
-                if fmt == 'trk':
-                    out = ((d64 + 0.5) * float(vox_size)).to(torch.float32)
-                else:                 # s . affine[:3,:3] + affine[:3,3] (tracker.py:133-136), term by term
-                    A = affine
-                    cols = [d64[:, 0] * A[0, c] + d64[:, 1] * A[1, c] + d64[:, 2] * A[2, c] + A[c, 3]
-                            for c in range(3)]
-                    out = torch.stack(cols, 1).to(torch.float32)
+                if int(new_off.shape[0]) <= 1:
+                    continue
                 h_data = env._pinned('file_pts', out.numel(), torch.float32)
                 h_off = env._pinned('file_off', new_off.numel(), torch.int64)
-                h_keep = env._pinned('file_keep', n, torch.uint8)
                 h_data.copy_(out.reshape(-1), non_blocking=True)
                 h_off.copy_(new_off, non_blocking=True)
-                h_keep.copy_(keep.to(torch.uint8), non_blocking=True)
                 torch.cuda.current_stream(env.device).synchronize()
-                seeds = np.asarray(env.initial_points)[h_keep.numpy().astype(bool)] - 0.5
-                writer.write(h_data.numpy().reshape(-1, 3), h_off.numpy(), seeds)
+                writer.write(h_data.numpy().reshape(-1, 3), h_off.numpy(), seeds_kept)
         finally:
-            writer.close()
-        return writer.n
+            if writer is not None:
+                writer.close()
+        n = writer.n if writer is not None else 0
+        if world > 1:
+            t = torch.tensor([n], device=env.device)
+            dist.broadcast(t, 0)
+            n = int(t.item())
+        return n
 
     def track_and_validate(self, env):
         """Reference: tracking/tracker.py:204-259 (batch by batch, with rewards)."""
