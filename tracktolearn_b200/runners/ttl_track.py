@@ -216,7 +216,12 @@ def parse_args(argv=None):
 def main(argv=None):
     """ Main tracking script """
     args = parse_args(argv)
-    TrackToLearnTrack(vars(args)).run()
+    try:
+        TrackToLearnTrack(vars(args)).run()
+    finally:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+            dist.destroy_process_group()
 
 
 if __name__ == '__main__':
