@@ -223,3 +223,46 @@ def test_episode_with_oracle_criterion_and_bonus_matches_reference_fixture():
     tr = env.get_streamlines()
     np.testing.assert_array_equal(tr.lengths, g['sl_lengths'])
     OracleSingleton.clear()
+
+
+def test_empty_and_single_streamline_batches():
+    """Edge sizes of the reference protocol: an empty batch (reset(k, k)), a single streamline, and a
+    batch that empties while stepping -- no launch with zero rows, shapes as in the reference."""
+    from tests.gpu_helpers import make_gpu_env
+    g = load_golden('env_noisy')
+    env, sub = make_gpu_env(g, True, False, seeds=g['seeds'])
+    # empty
+    s = env.reset(3, 3)
+    assert tuple(s.shape) == (0, env.get_state_size())
+    st, r, d, info = env.step(np.zeros((0, 3), dtype=np.float32))
+    assert tuple(st.shape) == (0, env.get_state_size()) and len(d) == 0 and len(info['continue_idx']) == 0
+    st, ns = env.harvest()
+    assert tuple(st.shape) == (0, env.get_state_size()) and len(ns) == 0
+    assert len(env.get_streamlines()) == 0
+    # one streamline, tracked by hand until it stops; matches the oracle on the same actions
+    seeds = np.asarray(env.seeds[5:6])
+    ref = O.OracleEnv(sub['sh'], sub['mask'], seeds, meta(g)['vox'], meta(g)['step_mm'], theta=meta(g)['theta'],
+                      max_length_mm=meta(g)['max_length'], threshold=meta(g)['threshold'], noisy=True)
+    s = env.reset(5, 6)
+    s_ref = ref.reset(0, 1)
+    np.testing.assert_allclose(s.cpu().numpy(), s_ref, atol=1e-5)
+    rs = np.random.RandomState(0)
+    a = rs.normal(size=(1, 3)).astype(np.float32)
+    steps = 0
+    while len(env.continue_idx):
+        st, _, d, _ = env.step(a)
+        st_r, _, d_r, _ = ref.step(a)
+        assert (d == d_r).all()
+        np.testing.assert_allclose(st.cpu().numpy(), st_r, atol=1e-5)
+        env.harvest()
+        ref.harvest()
+        steps += 1
+        assert steps <= env.max_nb_steps
+    assert len(ref.continue_idx) == 0
+    t = env.get_streamlines()
+    sl, _, fl = ref.get_streamlines()
+    assert len(t) == 1 and t.lengths[0] == len(sl[0]) and t.data_per_streamline['flags'][0] == fl[0]
+    np.testing.assert_allclose(t.streamlines[0], sl[0], atol=1e-5)
+    # stepping an already empty env is a no-op
+    st, r, d, info = env.step(np.zeros((0, 3), dtype=np.float32))
+    assert tuple(st.shape) == (0, env.get_state_size())

@@ -1368,13 +1368,17 @@ int ttl_env_reset(const ttl_volume* vol, const ttl_params* prm, const ttl_batch*
                   const double* seeds, void* stream) {
   int rc = check_common(vol, prm);
   if (rc) return rc;
-  if (!b || !seeds || b->n > b->capacity || b->ld_state > kMaxStateLd || (b->ld_state & 3) ||
-      b->ld_state < 7 * vol->C + 3 * prm->n_dirs || b->n_slots <= 0)
+  if (!b || (!seeds && b->n > 0) || b->n < 0 || b->n > b->capacity || b->ld_state > kMaxStateLd ||
+      (b->ld_state & 3) || b->ld_state < 7 * vol->C + 3 * prm->n_dirs || b->n_slots <= 0)
     return TTL_ERR_BAD_ARG;
   rc = check_layout(vol, prm, b);
   if (rc) return rc;
-  if (b->n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (b->n == 0) {   // an empty batch (reset(k, k)) still has to clear the control block
+    TTL_LAUNCH("reset_kernel", s, reset_kernel<<<1, 32, 0, s>>>(*b, seeds));
+    TTL_CHECK_LAST();
+    return 0;
+  }
   const int n_init = b->n > b->n_slots ? b->n : b->n_slots;
   TTL_LAUNCH("reset_kernel", s, reset_kernel<<<ttl_div_up(n_init, 256), 256, 0, s>>>(*b, seeds));
   const int n0 = b->n < b->n_slots ? b->n : b->n_slots;
@@ -1490,10 +1494,10 @@ void ttl_state_options(int32_t bits) { g_state_opts.store(bits & 127); }
 int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
                  const float* actions, int32_t lda, const double* noise, int32_t n_upper,
                  void* stream) {
+  if (n_upper <= 0) return 0;   // nothing alive: no launch (and no action buffer to look at)
   if (!actions || lda < 3) return TTL_ERR_BAD_ARG;
   int rc = check_step_args(vol, prm, b, cur, &n_upper);
   if (rc) return rc;
-  if (n_upper <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const ActionSrc src = {actions, lda, nullptr, 0, nullptr, n_upper};
   launch_propagate(vol, prm, b, cur, src, noise, 0, n_upper, s);
@@ -1506,11 +1510,11 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
 int ttl_env_step_head(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
                       const float* head_partial, int32_t n_tiles, const float* head_bias,
                       int32_t n_upper, void* stream) {
+  if (n_upper <= 0) return 0;
   if (!head_partial || !head_bias || n_tiles < 1 || (reinterpret_cast<uintptr_t>(head_partial) & 15))
     return TTL_ERR_BAD_ARG;
   int rc = check_step_args(vol, prm, b, cur, &n_upper);
   if (rc) return rc;
-  if (n_upper <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const ActionSrc src = {nullptr, 0, head_partial, n_tiles, head_bias, n_upper};
   launch_propagate(vol, prm, b, cur, src, nullptr, 0, n_upper, s);
@@ -1523,10 +1527,10 @@ int ttl_env_step_head(const ttl_volume* vol, const ttl_params* prm, const ttl_ba
 int ttl_env_step_begin(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
                        const float* actions, int32_t lda, const double* noise, int32_t n_upper,
                        void* stream) {
+  if (n_upper <= 0) return 0;
   if (!actions || lda < 3) return TTL_ERR_BAD_ARG;
   int rc = check_step_args(vol, prm, b, cur, &n_upper);
   if (rc) return rc;
-  if (n_upper <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const ActionSrc src = {actions, lda, nullptr, 0, nullptr, n_upper};
   launch_propagate(vol, prm, b, cur, src, noise, 1, n_upper, s);
@@ -1539,8 +1543,8 @@ int ttl_env_step_finish(const ttl_volume* vol, const ttl_params* prm, const ttl_
                         float bonus, int32_t n_upper, void* stream) {
   int rc = check_common(vol, prm);
   if (rc) return rc;
-  if (!b || !scores || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
   if (n_upper <= 0) return 0;
+  if (!b || !scores || (cur != 0 && cur != 1)) return TTL_ERR_BAD_ARG;
   if (n_upper > b->n_slots) n_upper = b->n_slots;
   cudaStream_t s = (cudaStream_t)stream;
   TTL_LAUNCH("oracle_apply_kernel", s,
@@ -1554,8 +1558,8 @@ int ttl_env_step_finish(const ttl_volume* vol, const ttl_params* prm, const ttl_
 
 int ttl_env_gather_step_state(const ttl_batch* b, int32_t cur, int32_t n_rows, float* out,
                               int32_t ld_out, void* stream) {
-  if (!b || !out) return TTL_ERR_BAD_ARG;
   if (n_rows <= 0) return 0;
+  if (!b || !out) return TTL_ERR_BAD_ARG;
   TTL_LAUNCH("gather_rows_kernel", (cudaStream_t)stream, gather_rows_kernel<<<ttl_div_up((long long)n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       b->state[cur ^ 1], b->dest, n_rows, b->ld_state, out, ld_out, b->state_size));
   TTL_CHECK_LAST();
@@ -1566,8 +1570,8 @@ int ttl_format_state(const ttl_volume* vol, const ttl_params* prm, const float* 
                      int32_t L, float* out, int32_t ld_out, void* stream) {
   int rc = check_common(vol, prm);
   if (rc) return rc;
-  if (!points || !out || L < 1) return TTL_ERR_BAD_ARG;
   if (n <= 0) return 0;
+  if (!points || !out || L < 1) return TTL_ERR_BAD_ARG;
   rc = state_kernels_ready();
   if (rc) return rc;
   TTL_LAUNCH("format_state_kernel", (cudaStream_t)stream,
@@ -1582,8 +1586,8 @@ int ttl_stopping_flags(const ttl_volume* vol, const ttl_params* prm, const float
                        void* stream) {
   int rc = check_common(vol, prm);
   if (rc) return rc;
-  if (!points || !out_flags || L < 1) return TTL_ERR_BAD_ARG;
   if (n <= 0) return 0;
+  if (!points || !out_flags || L < 1) return TTL_ERR_BAD_ARG;
   TTL_LAUNCH("stopping_flags_kernel", (cudaStream_t)stream, stopping_flags_kernel<<<ttl_div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(
       *vol, *prm, points, n, L, out_flags, out_mask_value, out_reward));
   TTL_CHECK_LAST();
@@ -1598,8 +1602,8 @@ int ttl_streamline_offsets(const ttl_batch* b, int64_t* offsets, void* stream) {
 }
 
 int ttl_pack_streamlines(const ttl_batch* b, const int64_t* offsets, float* out_points, void* stream) {
+  if (b && b->n == 0) return 0;
   if (!b || !offsets || !out_points) return TTL_ERR_BAD_ARG;
-  if (b->n == 0) return 0;
   TTL_LAUNCH("pack_kernel", (cudaStream_t)stream, pack_kernel<<<ttl_div_up((long long)b->n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       *b, (const long long*)offsets, out_points));
   TTL_CHECK_LAST();

@@ -100,8 +100,8 @@ extern "C" {
 
 int ttl_streamline_lengths(const float* points, const int64_t* offsets, int32_t n, double* out_lengths,
                            void* stream) {
-  if (!points || !offsets || !out_lengths) return TTL_ERR_BAD_ARG;
   if (n <= 0) return 0;
+  if (!points || !offsets || !out_lengths) return TTL_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   TTL_LAUNCH("streamline_length_kernel", s,
              streamline_length_kernel<<<ttl_div_up(n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
@@ -112,8 +112,8 @@ int ttl_streamline_lengths(const float* points, const int64_t* offsets, int32_t 
 
 int ttl_compress_mask(const float* points, const int64_t* offsets, int32_t n, double tol_error,
                       double max_segment_length, uint8_t* keep, int32_t* count, void* stream) {
-  if (!points || !offsets || !keep || !count || !(tol_error >= 0.0)) return TTL_ERR_BAD_ARG;
   if (n <= 0) return 0;
+  if (!points || !offsets || !keep || !count || !(tol_error >= 0.0)) return TTL_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   TTL_LAUNCH("compress_mask_kernel", s,
              compress_mask_kernel<<<ttl_div_up(n, kWarpsPerBlock), kWarpsPerBlock * 32, 0, s>>>(
