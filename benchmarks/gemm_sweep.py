@@ -17,7 +17,7 @@ def main():
     lib = _lib.load()
     dev = torch.device('cuda:0')
     sp = _lib.stream_ptr(dev)
-    m, n = 50000, 1024
+    m, n = int(os.environ.get('GEMM_M', '50000')), 1024
     out = {}
     mode = 1
     for k in (128, 256, 512, 640, 768, 1024, 1536, 2048):
