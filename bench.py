@@ -108,7 +108,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '20'],
+                 '--format=csv,noheader,nounits', '-lms', '10'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
