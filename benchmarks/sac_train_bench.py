@@ -28,6 +28,8 @@ def main():
     ap.add_argument('--n-actor', type=int, default=4096)
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--shape', type=int, nargs=3, default=[64, 64, 64])
+    ap.add_argument('--tf32', action='store_true', help='let the learner\'s torch matmuls use TF32 tensor cores '
+                    '(the reference and the default run them in fp32)')
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -61,6 +63,8 @@ def main():
     alg = SACAuto(615, 3, '1024-1024-1024', n_actors=a.n_actor, batch_size=a.batch, device=dev, precision='bf16')
     alg.agent.actor.load_state_dict(synthetic.actor_state_dict(615, '1024-1024-1024', seed=1111, kind='tracking'))
     learner = alg.enable_training(replay_size=1000000, batch_size=a.batch, start_timesteps=a.n_actor)
+    if a.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
     np.random.seed(rank)
     torch.manual_seed(rank)
     stream = torch.cuda.current_stream(dev)
@@ -107,7 +111,7 @@ def main():
         sec = float(t[0]) * 1e-3
         grad_bytes = sum(p.numel() for p in learner.actor.parameters()) * 4 + \
             sum(p.numel() for p in learner.critic.parameters()) * 4 + 4
-        print(json.dumps({
+        print(json.dumps({'learner_matmul': 'tf32' if a.tf32 else 'fp32',
             'metric': 'training streamline-steps/sec (rollout + one SAC update per env step)',
             'value': float(usum[0]) / sec, 'unit': 'streamline-steps/s', 'n_gpus': world, 'scaling': 'weak',
             'updates_per_s_per_replica': float(u[1]) / sec, 'env_steps_rank0': int(sum(lengths)),
