@@ -372,13 +372,17 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   const int n_m = (m + 2 * BM - 1) / (2 * BM), n_n = (n_pad + BN - 1) / BN;
   const int total = n_m * n_n, kblocks = k_pad / BK;
 
+  // relu: bit 0 = apply ReLU; bits 8.. = how many of the fused head's outputs are wanted (0 = all):
+  // the deterministic policy reads mu only, half of the 6-wide head
+  const int head_n = (relu >> 8) ? min(relu >> 8, HEAD_OUT > 0 ? HEAD_OUT : 1) : (HEAD_OUT > 0 ? HEAD_OUT : 1);
+  relu &= 1;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bar0 + 256u - raw));
   float* s_head = s_bias + EXTRA_SMEM_BIAS / 4;
   const bool bias_in_smem = n_pad <= EXTRA_SMEM_BIAS / 4;
   if (bias_in_smem)
     for (int t = threadIdx.x; t < n_pad; t += GEMM_THREADS) s_bias[t] = bias[t];
   if (HEAD_OUT > 0) {
-    for (int t = threadIdx.x; t < HEAD_OUT * n_pad; t += GEMM_THREADS) {
+    for (int t = threadIdx.x; t < head_n * n_pad; t += GEMM_THREADS) {
       const int o = t / n_pad, c = t - o * n_pad;
       s_head[t] = c < head_k ? head_w[(size_t)o * head_k + c] : 0.f;
     }
@@ -484,6 +488,7 @@ dense_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         if (HEAD_OUT > 0) {
 #pragma unroll
           for (int o = 0; o < HEAD_OUT; ++o) {
+            if (o >= head_n) break;   // warp-uniform
             const float* wrow = s_head + o * n_pad + col0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -957,9 +962,11 @@ int run_bf16_layers(ttl_actor_plan* p, const CUtensorMap& map_a0, const int32_t*
     // layer i: act[i&1] (pitch k_pad[i]) -> act[(i+1)&1] (pitch k_pad[i+1] = n_pad[i])
     const bool fused = p->fuse_head && i == nl - 2;
     const bool alt = alt_w0 && i == 0;
+    // only mu is needed when nothing reads log_std: deterministic policy, no log-prob, no raw output
+    const int head_n = (fused && probabilistic == 0.f && !logp && !pre) ? n_out / 2 : 0;
     int rc = launch_dense_bf16(i == 0 ? map_a0 : p->map_a[i], alt ? p->map_w0_alt : p->map_w[i],
                                alt ? p->map_w0_alt2 : p->map_w2[i], p->bq[i], p->act[(i + 1) & 1],
-                               p->n_pad[i], n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1, s,
+                               p->n_pad[i], n_rows_dev, n_rows_max, p->n_pad[i], p->k_pad[i], 1 | (head_n << 8), s,
                                fused ? w.w[nl - 1] : nullptr, k_last, fused ? p->head_partial : nullptr);
     if (rc) return rc;
   }
