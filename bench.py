@@ -66,7 +66,7 @@ def ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the step's kernels from
     the committed `ncu --set full` capture of this same command (profiles/README.md); None when the
     summary file is absent."""
-    path = os.path.join(ROOT, 'profiles', 'r1_step_v7_ncu_summary.json')
+    path = os.path.join(ROOT, 'profiles', 'r1_step_v9_ncu_summary.json')
     if not os.path.exists(path):
         return {}
 
@@ -431,7 +431,7 @@ def main_gpu(args):
     dense_launches = sum(n for n, _ in dn)
     dense_total_ms = sum(ms for _, ms in dn)
     traffic = ncu_traffic()
-    traffic_src = 'profiles/r1_step_v7_ncu_summary.json (ncu --set full of this command, bytes per launch)'
+    traffic_src = 'profiles/r1_step_v9_ncu_summary.json (ncu --set full of this command, bytes per launch)'
     roofline = None
     if dense_launches:
         steps_prof = dense_launches / 3.0
