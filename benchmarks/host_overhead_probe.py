@@ -18,9 +18,15 @@ def main():
     from tests.test_tracker_gpu import _setup
     from tracktolearn_b200.algorithms.rl import StepRunner
     env, alg, sub, seeds, sd = _setup(shape=(48, 52, 44), n_seeds=60000, precision='bf16')
+    hidden = os.environ.get('PROBE_HIDDEN', '1024-1024-1024')
+    rows = int(os.environ.get('PROBE_ROWS', '256'))
+    from tracktolearn_b200 import synthetic
+    from tracktolearn_b200.algorithms.sac_auto import SACAuto
+    alg = SACAuto(615, 3, hidden, n_actors=rows, device=torch.device('cuda:0'), precision='bf16')
+    alg.agent.actor.load_state_dict(synthetic.actor_state_dict(615, hidden, seed=5, kind='tracking'))
     out = {}
     for graph in (False, True):
-        env.reset_streaming(0, len(seeds), 256, fp32_state=False)
+        env.reset_streaming(0, len(seeds), rows, fp32_state=False)
         r = StepRunner(env, alg.agent.actor, 0.0, use_graph=graph)
         for _ in range(50):
             r.step()
