@@ -57,6 +57,8 @@ class TrkWriter(object):
 
     def write(self, data, offsets, seeds=None):
         n = len(offsets) - 1
+        if n <= 0:
+            return
         lens = np.diff(offsets).astype(np.int64)
         n_prop = 3 if self.save_seeds else 0
         total = int(lens.sum()) * 3 + n * (1 + n_prop)
@@ -97,6 +99,8 @@ class TckWriter(object):
 
     def write(self, data, offsets, seeds=None):
         n = len(offsets) - 1
+        if n <= 0:
+            return
         lens = np.diff(offsets).astype(np.int64)
         total = int(lens.sum()) + n
         out = np.full((total, 3), np.nan, dtype='<f4')
