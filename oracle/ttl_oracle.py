@@ -13,8 +13,13 @@ container -- ``tests/golden/make_golden.py``, checked by ``tests/test_oracle_gol
 Two third-party pieces are restated from their published algorithms because their sources
 are absent: dwi_ml's trilinear neighbourhood interpolation (pinned by the reference only to
 the branch ``for_beluga_scilpy2``, requirements.txt:1) and dipy's ``set_number_of_points`` /
-``random_seeds_from_mask`` (unpinned).  For those two functions parity is UNPINNED against
-upstream: the fixtures pin this restatement.
+``random_seeds_from_mask`` (unpinned).  For those functions parity is UNPINNED against
+upstream: the fixtures pin this restatement.  The same holds for the two
+"next-row" pieces added later, both dipy / scilpy algorithms that the reference only calls:
+``compress_streamline`` (dipy ``compress_streamlines``, tracker.py:123-125) and
+``local_maxima`` / ``peak_directions`` / ``peaks_from_sh`` (scilpy ``get_maximas`` -> dipy
+``peak_directions``, env.py:405-432; evaluated on this repository's own sphere because dipy's
+``repulsion724`` data file is absent).  They have no reference-recorded fixtures: PARITY UNPINNED.
 
 Each function cites the reference lines it follows (paths relative to
 ``/root/reference/TrackToLearn``).
