@@ -24,13 +24,17 @@
 extern "C" {
 #endif
 
-#define TTL_ABI_VERSION 2
+#define TTL_ABI_VERSION 3
 
 /* StoppingFlags, environments/stopping_criteria.py:10-20 */
 #define TTL_STOPPING_MASK 1
 #define TTL_STOPPING_LENGTH 2
 #define TTL_STOPPING_CURVATURE 4
 #define TTL_STOPPING_ORACLE 64
+
+#define TTL_OPERAND_BF16 0
+#define TTL_OPERAND_FP16 1
+#define TTL_OPERAND_TF32 2
 
 #define TTL_ERR_BAD_ARG (-1)
 #define TTL_ERR_UNSUPPORTED (-2)
@@ -81,24 +85,29 @@ typedef struct ttl_batch {
   int32_t* npts;           /* [capacity] running point count of every row (1 after reset) */
   uint8_t* dones;          /* [capacity] */
   int32_t* alive[2];       /* ping-pong lists of alive global rows, ascending */
-  int32_t* ctrl;           /* [8] device ints: [0],[1] alive count of alive[0],alive[1];
+  int32_t* ctrl;           /* [16] device ints: [0],[1] alive count of alive[0],alive[1];
                               [2] steps taken; [3] alive count before the last step;
                               [4],[5] int64 streamline-steps so far; [6] next unseeded row;
-                              [7] block ticket; [8] survivors of the last step; [9] rows refilled in
-                              the last step; [10] first row refilled in the last step  (16 ints) */
+                              [8] survivors of the last step; [9] rows refilled in the last step;
+                              [10] first row refilled in the last step; [12],[13] ping-pong copies of
+                              [6] used by the step kernels; [14] set when an fp16 operand row
+                              saturated (|value| > 65504); others reserved */
   uint8_t* stop;           /* [n_slots+16] per rank (position in the alive list): stopped this step */
   int32_t* dest;           /* [n_slots] per rank: row of state[next] that holds its new state */
   int32_t* step_flags;     /* [n_slots] per rank: flags raised this step */
   float* reward;           /* [n_slots] per rank */
   float* state[2];         /* ping-pong [n_slots][ld_state] fp32 state rows.  state[cur] rows
                               [0, n_alive) are the states of alive[cur] in order. */
-  void* state_bf16[2];     /* ping-pong [n_slots][ld_bf16] bf16 copies of the state rows, zero padded
-                              to ld_bf16 = round_up(state_size, 64): the actor's first-layer TMA
-                              operand, written by the same kernel that writes state[] */
+  void* state_bf16[2];     /* ping-pong [n_slots][ld_bf16] operand rows: the state rows in the actor's
+                              operand type (operand_fmt below; "bf16" in the names is historical),
+                              zero padded to ld_bf16 = round_up(state_size, 64) elements, 16-byte
+                              aligned: the actor's first-layer TMA operand, written by the same kernel
+                              that writes state[] */
   int32_t ld_bf16;
-  int32_t max_groups;      /* entries in grp_stops / grp_prefix: ceil(n_slots / 32) + 1 */
+  int32_t max_groups;      /* entries in grp_stops: ceil(n_slots / 32) + 1 */
   int32_t* grp_stops;      /* [max_groups] streamlines stopped this step per group of 32 ranks */
-  int32_t* grp_prefix;     /* [max_groups] exclusive prefix of survivors per group */
+  int32_t* sg_stops;       /* [2][ceil(max_groups / 64)] ping-pong: stops per super-group of 64 groups,
+                              accumulated by the stop kernels, consumed and cleared by the state kernel */
   int32_t bf16_layout;     /* column order of state_bf16 rows: 0 = the reference's
                               [7*C | 3*n_dirs | 0..]; 1 = channel-padded [7*CP | 3*n_dirs | 0..]
                               (every neighbourhood point starts on a 16-byte boundary; the actor's
@@ -112,6 +121,8 @@ typedef struct ttl_batch {
                               chasing alive[] -> npts[] -> points[] (tracking_env.py:181-188 re-slices
                               the streamline buffer for the same purpose) */
   float* step_tip;         /* [n_slots+16][4] per rank of alive[cur]: the point added this step */
+  int32_t operand_fmt;     /* element type of state_bf16 rows: TTL_OPERAND_BF16 / _FP16 (2 bytes) or
+                              TTL_OPERAND_TF32 (fp32 words rounded to tf32; bf16_layout 1 only) */
   const int32_t* order;    /* NULL, or a permutation [n] of the rows: the order in which seeds take slots
                               (slot k of reset gets row order[k]; refills continue from there).  Rows
                               keep their identity -- results, flags and the output order are per row --
@@ -168,13 +179,14 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
  * ttl_actor_head_partial returns after a forward with action == NULL): action = tanh(mu), the
  * deterministic policy that tracking uses (prob = 0: tracker.py:28, ttl_track.py:172-175;
  * offpolicy.py:126-128 with std * 0).  head_partial [n_alive][n_tiles][8] fp32 per-column-tile
- * partial sums of the 6-wide output layer, head_bias [6].  The sums are taken in tile order like the
- * actor's own finishing pass, so this entry point and ttl_actor_forward* + ttl_env_step give the
- * same bits; it saves one launch and the action round trip per step.  No noise input: the noisy
+ * partial sums of the 6-wide output layer (tiles_per_256 = 256 / tile width of the launch that wrote
+ * them), head_bias [6].  The sums follow the same fixed tree as the actor's own finishing pass, so this
+ * entry point and ttl_actor_forward* + ttl_env_step give the same bits whatever the tile width; it
+ * saves one launch and the action round trip per step.  No noise input: the noisy
  * environment with sigma > 0 goes through ttl_env_step. */
 int ttl_env_step_head(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
-                      const float* head_partial, int32_t n_tiles, const float* head_bias,
-                      int32_t n_upper, void* stream);
+                      const float* head_partial, int32_t n_tiles, int32_t tiles_per_256,
+                      const float* head_bias, int32_t n_upper, void* stream);
 
 /* The same step split in two so that TractOracle-Net can be consulted in between
  * (OracleStoppingCriterion, stopping_criteria.py:113-154: stop where the score < 0.5 once the
@@ -228,8 +240,15 @@ int ttl_compress_mask(const float* points, const int64_t* offsets, int32_t n, do
 /* ---- SAC actor (algorithms/shared/offpolicy.py:61-140, shared/utils.py:41-51) -------------- */
 
 #define TTL_ACTOR_MAX_LAYERS 8
-#define TTL_PRECISION_BF16 0   /* tcgen05 bf16 operands, fp32 TMEM accumulators */
+/* Arithmetic of the hidden layers.  The reference runs them as fp32 GEMMs (offpolicy.py:94-140, no
+ * autocast).  Relative half-ulp of the operands: bf16 2^-9, fp16 and tf32 2^-12 (11 significant bits);
+ * measured output error against the fp32 reference on the 615-1024^3-6 network: bf16 ~4e-3 of the
+ * output scale, fp16 / tf32 ~5e-4 (tests/test_actor_gpu.py). */
+#define TTL_PRECISION_BF16 0   /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulators */
 #define TTL_PRECISION_FP32 1   /* CUDA-core fp32 reference-precision path */
+#define TTL_PRECISION_FP16 2   /* tcgen05 kind::f16, fp16 operands: bf16's rate, tf32's precision, range
+                                  +-65504 (stores saturate and raise ttl_actor_overflow) */
+#define TTL_PRECISION_TF32 3   /* tcgen05 kind::tf32, fp32 words rounded to tf32: half the rate, fp32 range */
 
 typedef struct ttl_actor_weights {
   int32_t n_layers;                         /* linear layers (4 for 1024-1024-1024) */
@@ -239,47 +258,63 @@ typedef struct ttl_actor_weights {
   const float* b[TTL_ACTOR_MAX_LAYERS];     /* [out] fp32 */
 } ttl_actor_weights;
 
-typedef struct ttl_actor_plan ttl_actor_plan; /* opaque: packed bf16 weights, TMA maps, scratch */
+typedef struct ttl_actor_plan ttl_actor_plan; /* opaque: packed operand weights, TMA maps, scratch */
 
-/* Host-side: packs weights (bf16, K padded to 64, N padded to the tile) into `workspace`
- * (device, ttl_actor_workspace_bytes() bytes) and encodes the TMA descriptors for batches of
- * up to max_rows states.  Enqueues the packing kernels on `stream`. */
-int64_t ttl_actor_workspace_bytes(const ttl_actor_weights* w, int32_t max_rows);
+/* Host-side: packs weights (operand type of `precision`, K padded to 64, N padded to 64) into
+ * `workspace` (device, 1024-byte aligned, ttl_actor_workspace_bytes() bytes) and encodes the TMA
+ * descriptors for batches of up to max_rows states.  Enqueues the packing kernels on `stream`. */
+int64_t ttl_actor_workspace_bytes(const ttl_actor_weights* w, int32_t max_rows, int32_t precision);
 int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int32_t max_rows,
-                          void* workspace, int64_t workspace_bytes, void* stream);
+                          int32_t precision, void* workspace, int64_t workspace_bytes, void* stream);
 void ttl_actor_plan_destroy(ttl_actor_plan* plan);
+int ttl_actor_precision(const ttl_actor_plan* plan);
+/* A/B switches of the tensor-core layers (default 0): bit 0 = one launch per layer instead of one
+ * persistent launch for the whole network; bits 8.. = pin the N tile to 256 / 128 / 64 (default: chosen
+ * per launch from the row count).  Outputs are identical bit for bit in every combination. */
+void ttl_actor_options(int32_t bits);
 /* The fp32 weights the plan was created from changed in place (an optimiser step,
- * algorithms/sac_auto.py:220-232): repack the bf16 copies.  Three small launches. */
+ * algorithms/sac_auto.py:220-232): repack the operand copies.  A few small launches. */
 int ttl_actor_plan_refresh(ttl_actor_plan* plan, void* stream);
 
 /* MaxEntropyActor.forward (offpolicy.py:94-140): state [n][ld_state] fp32 ->
  * action [n][3] = tanh(mu + exp(clamp(log_std,-20,2)) * probabilistic * eps), logp [n]
- * (may be NULL), pre [n][2*action] raw network output (may be NULL).
+ * (may be NULL), pre [n][2*action] raw network output (may be NULL), in the plan's precision.
  * n is read from *n_rows_dev when that is non-NULL (no host sync), else n_rows_max.
- * eps [n][3] fp32 may be NULL when probabilistic == 0. */
+ * eps [n][3] fp32 may be NULL when probabilistic == 0.  action == NULL (tensor-core tiers with the
+ * output layer fused): stop after the last hidden layer, see ttl_actor_head_partial. */
 int ttl_actor_forward(ttl_actor_plan* plan, const float* state, int32_t ld_state,
                       const int32_t* n_rows_dev, int32_t n_rows_max, float probabilistic,
-                      const float* eps, float* action, float* logp, float* pre,
-                      int32_t precision, void* stream);
-/* Same (bf16 tier only) when the caller already holds the bf16, zero-padded copy of the states
- * that ttl_env_step / ttl_env_reset write (ttl_batch.state_bf16): state_bf16 [rows_alloc][ld]
- * with ld == round_up(in_dim, 64).  Skips the packing pass. */
-int ttl_actor_forward_packed(ttl_actor_plan* plan, const void* state_bf16, int32_t ld,
+                      const float* eps, float* action, float* logp, float* pre, void* stream);
+/* Same (tensor-core tiers only) when the caller already holds the zero-padded operand rows that
+ * ttl_env_step / ttl_env_reset write (ttl_batch.state_bf16, element type = ttl_batch.operand_fmt,
+ * which must be the plan's): state_op [rows_alloc][ld] with ld == round_up(in_dim, 64).  Skips the
+ * packing pass. */
+int ttl_actor_forward_packed(ttl_actor_plan* plan, const void* state_op, int32_t ld,
                              int32_t rows_alloc, const int32_t* n_rows_dev, int32_t n_rows_max,
                              float probabilistic, const float* eps, float* action, float* logp,
                              float* pre, int32_t layout, void* stream);
 /* With action == NULL (and logp == pre == NULL) ttl_actor_forward_packed stops after the last
  * tensor-core layer when the 6-wide output layer is fused into it: the per-tile partial sums of
- * mu / log_std stay in the plan's scratch and this call returns where (see ttl_env_step_head).
+ * mu / log_std stay in the plan's scratch and this call -- made AFTER the forward, the tile width is
+ * chosen per launch -- returns where and in which geometry (see ttl_env_step_head):
+ * partial [rows][n_tiles][8] fp32, tiles_per_256 = 256 / tile width.
  * TTL_ERR_UNSUPPORTED when the plan's output layer is not fused. */
 int ttl_actor_head_partial(const ttl_actor_plan* plan, const float** partial, int32_t* n_tiles,
-                           const float** bias);
+                           int32_t* tiles_per_256, const float** bias);
+/* fp16 tier: 1 when a state or activation value was outside +-65504 and was saturated since the last
+ * clearing call (synchronises `stream`).  The caller should then re-run in tf32. */
+int ttl_actor_overflow(ttl_actor_plan* plan, int32_t* out_host, int32_t clear, void* stream);
 /* Prepares the plan for ttl_batch.bf16_layout == 1: packs a copy of the first layer's weights
  * whose columns follow [n_points*CP | rest] (zero columns for the CP - C padding channels). */
 int ttl_actor_plan_set_layout(ttl_actor_plan* plan, int32_t C, int32_t CP, int32_t n_points, void* stream);
 
 /* Stand-alone dense layer used by the actor and exposed for tests:
- * C[m][ldc] (bf16) = act(A[m][k] (bf16) . W[n][k]^T (bf16) + bias[n]), tcgen05/TMEM/TMA. */
+ * C[m][ldc] = act(A[m][k] . W[n][k]^T + bias[n]) with A, W, C in the operand type of `precision`
+ * (bf16 / fp16 / tf32-rounded fp32), tcgen05/TMEM/TMA; bn = 0 (auto) or the N tile 256 / 128 / 64.
+ * k and n multiples of 64, ldc a multiple of 16, C 32-byte aligned. */
+int ttl_gemm_tc(const void* A, const void* W, const float* bias, void* C, int32_t m, int32_t n,
+                int32_t k, int32_t ldc, int32_t relu, const int32_t* m_dev, int32_t precision,
+                int32_t bn, void* stream);
 int ttl_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t m,
                   int32_t n, int32_t k, int32_t ldc, int32_t relu, const int32_t* m_dev,
                   void* stream);
@@ -345,9 +380,7 @@ void ttl_prof_enable(int32_t on);
 void ttl_pdl_enable(int32_t on);
 /* A/B switches of the device-mode state kernel (default 0): bits 0-1 prefetch the row's cache lines
  * into L1 (1) / L2 (2) before gathering, bit 3 recompute the previous-direction block from the fp32
- * points instead of shifting the previous row's, bit 4 gather the row's <= 32 distinct voxels once
- * (one LDG.64 per voxel per lane) instead of the 56 trilinear corners through L1 (bits 5-6: that
- * kernel's CTAs per SM).  Results are identical in every combination. */
+ * points instead of shifting the previous row's.  Results are identical in every combination. */
 void ttl_state_options(int32_t bits);
 int32_t ttl_prof_report(char* buf_host, int32_t buflen);
 

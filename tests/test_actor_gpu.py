@@ -1,7 +1,10 @@
-"""tcgen05 dense layer and the SAC actor forward against torch fp32 / the oracle / the
-reference-recorded fixture."""
-import ctypes
+"""tcgen05 dense layers and the SAC actor forward against torch fp32 / the oracle / the
+reference-recorded fixture, in every precision tier.
 
+Tolerances (north_star: actor outputs within 1e-3 relative, 1e-5 in fp32).  Half-ulp of the operand
+types: bf16 2^-9 = 1.95e-3, fp16 and tf32 2^-12 = 2.4e-4.  On the 615-1024^3-6 network the measured
+max-abs error over the output scale is ~4e-3 for bf16 (so bf16 CANNOT meet 1e-3 and is asserted at
+6e-3) and ~5e-4 for fp16 / tf32 (asserted at 1e-3, together with the action error after tanh)."""
 import numpy as np
 import pytest
 import torch
@@ -12,28 +15,47 @@ from tracktolearn_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 
+TC_TOL = {'bf16': 6e-3, 'fp16': 1e-3, 'tf32': 1e-3}
+OP_DTYPE = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'tf32': torch.float32}
+OUT_ULP = {'bf16': 2.0 ** -8, 'fp16': 2.0 ** -11, 'tf32': 2.0 ** -11}
 
-@pytest.mark.parametrize('m,n,k', [(128, 256, 64), (300, 512, 640), (1000, 1024, 1024), (77, 64, 128)])
-def test_gemm_bf16_tcgen05(m, n, k):
+
+def _round_operand(x, prec):
+    """fp32 tensor -> the values the tensor core sees (and, as a second result, the device operand)."""
+    if prec == 'tf32':
+        # round to nearest, ties away from zero, on the 13 low mantissa bits (cvt.rna.tf32.f32)
+        bits = x.contiguous().view(torch.int32)
+        r = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+        return r.double(), r
+    op = x.to(OP_DTYPE[prec])
+    return op.double(), op
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp16', 'tf32'])
+@pytest.mark.parametrize('m,n,k,bn', [(128, 256, 64, 0), (300, 512, 640, 0), (1000, 1024, 1024, 256), (77, 64, 128, 64),
+                                      (513, 320, 192, 128), (2048, 1024, 1024, 64)])
+def test_gemm_tcgen05(prec, m, n, k, bn):
     from tracktolearn_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(m + n + k)
-    A = (torch.randn((m, k), generator=g) * 0.5).cuda().to(torch.bfloat16)
-    W = (torch.randn((n, k), generator=g) * 0.1).cuda().to(torch.bfloat16)
-    bias = torch.zeros(((n + 255) // 256 * 256,), device='cuda')
-    bias[:n] = torch.randn((n,), generator=g).cuda()
-    C = torch.zeros((m, n), device='cuda', dtype=torch.bfloat16)
+    A64, A = _round_operand((torch.randn((m, k), generator=g) * 0.5).cuda(), prec)
+    W64, W = _round_operand((torch.randn((n, k), generator=g) * 0.1).cuda(), prec)
+    bias = torch.randn((n,), generator=g).cuda()
+    C = torch.zeros((m, n), device='cuda', dtype=OP_DTYPE[prec])
     m_dev = torch.tensor([m], dtype=torch.int32, device='cuda')
     for relu in (0, 1):
-        _lib.check(lib.ttl_gemm_bf16(_lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(C), m, n, k, n, relu,
-                                     _lib.ptr(m_dev), _lib.stream_ptr(torch.device('cuda:0'))), 'gemm')
+        _lib.check(lib.ttl_gemm_tc(_lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(C), m, n, k, n, relu,
+                                   _lib.ptr(m_dev), _lib.PRECISIONS[prec], bn,
+                                   _lib.stream_ptr(torch.device('cuda:0'))), 'gemm')
         torch.cuda.synchronize()
-        ref = A.float() @ W.float().t() + bias[:n]
+        ref = A64 @ W64.t() + bias.double()
         if relu:
             ref = torch.relu(ref)
-        err = (C.float() - ref).abs().max().item()
+        err = (C.double() - ref).abs().max().item()
         scale = ref.abs().max().item()
-        assert err <= 1e-2 * scale, (err, scale)   # bf16 output rounding (2^-8 relative)
+        # exact products of exactly representable operands: what is left is fp32 accumulation and the
+        # rounding of the stored output
+        assert err <= OUT_ULP[prec] * scale, (err, scale)
 
 
 def test_gemm_respects_device_row_count():
@@ -75,53 +97,114 @@ def test_actor_fp32_tier_matches_reference_fixture():
     assert torch.equal(ac.select_action(state, 0.0), a)
 
 
-def test_actor_bf16_tier_small_net():
+@pytest.mark.parametrize('prec', ['bf16', 'fp16', 'tf32'])
+def test_actor_tensor_core_tiers_small_net_vs_reference_fixture(prec):
+    """The reference's own MaxEntropyActor outputs (tests/golden/actor.npz), deterministic and
+    probabilistic, against every tensor-core tier."""
     g = load_golden('actor')
     hidden = '-'.join(str(int(h)) for h in g['hidden'])
-    ac, _ = _actor(hidden, int(g['seed']), 'bf16')
-    a, _, pre = ac.actor.forward_device(torch.from_numpy(g['state']).cuda(), 0.0, want_pre=True)
+    ac, _ = _actor(hidden, int(g['seed']), prec)
+    st = torch.from_numpy(g['state']).cuda()
+    a, _, pre = ac.actor.forward_device(st, 0.0, want_pre=True)
     scale = np.abs(g['pre']).max()
-    assert np.abs(pre.cpu().numpy() - g['pre']).max() <= 1e-2 * scale
-    assert np.abs(a.cpu().numpy() - g['action_det']).max() <= 1e-2
+    assert np.abs(pre.cpu().numpy() - g['pre']).max() <= TC_TOL[prec] * scale
+    assert np.abs(a.cpu().numpy() - g['action_det']).max() <= TC_TOL[prec]
+    a1, lp1, _ = ac.actor.forward_device(st, 1.0, eps=torch.from_numpy(g['eps']).cuda())
+    assert np.abs(a1.cpu().numpy() - g['action_prob1']).max() <= 2 * TC_TOL[prec]
+    assert np.abs(lp1.cpu().numpy() - g['logp_prob1']).max() <= 40 * TC_TOL[prec] * max(1.0, np.abs(g['logp_prob1']).max())
 
 
 @pytest.mark.parametrize('kind', ['random', 'tracking'])
-def test_actor_full_size_both_tiers(kind):
-    """615-1024-1024-1024-6 (the bundled agent's shape) on 5000 states: fp32 tier within 1e-5,
-    bf16 tensor-core tier within 1e-3 of the output scale... of the fp32 oracle."""
+def test_actor_full_size_all_tiers(kind):
+    """615-1024-1024-1024-6 (the bundled agent's shape) on 50 000 states (BASELINE configs[1]'s batch),
+    both synthetic checkpoints, against the fp32 oracle: fp32 tier 1e-5; fp16 and tf32 tiers within
+    1e-3 (max-abs over the output scale AND action error after tanh); bf16 within 6e-3 -- its half-ulp
+    is 2^-9 = 1.95e-3, so no bf16-operand path can meet 1e-3 (measured ~4e-3)."""
     hidden = '1024-1024-1024'
+    n = 50000
     rs = np.random.RandomState(0)
-    state = rs.normal(size=(5000, 615)).astype(np.float32)
+    state = rs.normal(size=(n, 615)).astype(np.float32)
     state[:, 315:] *= 0.3
+    a_ref = np.empty((n, 3), np.float32)
+    pre_ref = np.empty((n, 6), np.float32)
     ac32, sd = _actor(hidden, 1111, 'fp32', kind)
-    ac16, _ = _actor(hidden, 1111, 'bf16', kind)
-    a_ref, _, pre_ref = O.actor_forward(sd, state, 0.0)
+    for s0 in range(0, n, 10000):
+        a_ref[s0:s0 + 10000], _, pre_ref[s0:s0 + 10000] = O.actor_forward(sd, state[s0:s0 + 10000], 0.0)
     st = torch.from_numpy(state).cuda()
-    a32, _, pre32 = ac32.actor.forward_device(st, 0.0, want_pre=True)
-    a16, _, pre16 = ac16.actor.forward_device(st, 0.0, want_pre=True)
     scale = np.abs(pre_ref).max()
+    a32, _, pre32 = ac32.actor.forward_device(st, 0.0, want_pre=True)
     e32 = np.abs(pre32.cpu().numpy() - pre_ref).max() / scale
-    e16 = np.abs(pre16.cpu().numpy() - pre_ref).max() / scale
-    print('actor %s: fp32 tier rel err %.2e, bf16 tier rel err %.2e (scale %.3g)' % (kind, e32, e16, scale))
     assert e32 <= 1e-5
-    assert e16 <= 1e-2
     assert np.abs(a32.cpu().numpy() - a_ref).max() <= 1e-5
-    # row count taken from device memory, strided state rows (the env's 616-float pitch)
-    buf = torch.zeros((5000, 616), device='cuda')
-    buf[:, :615] = st
-    n_dev = torch.tensor([1234], dtype=torch.int32, device='cuda')
-    out = torch.full((5000, 3), 9.0, device='cuda')
-    ac16.actor.forward_device(buf[:, :615], 0.0, n_rows_dev=n_dev, out_action=out, want_logp=False)
-    assert torch.equal(out[:1234], a16[:1234]) and (out[1234:] == 9.0).all()
+    del ac32
+    for prec in ('fp16', 'tf32', 'bf16'):
+        ac, _ = _actor(hidden, 1111, prec, kind)
+        a, _, pre = ac.actor.forward_device(st, 0.0, want_pre=True)
+        e_pre = np.abs(pre.cpu().numpy() - pre_ref).max() / scale
+        e_act = np.abs(a.cpu().numpy() - a_ref).max()
+        print('actor %s %s: pre err / scale %.2e, action err %.2e (scale %.3g)' % (kind, prec, e_pre, e_act, scale))
+        assert e_pre <= TC_TOL[prec], (prec, e_pre)
+        assert e_act <= TC_TOL[prec], (prec, e_act)
+        assert not ac.actor.overflowed()
+        if prec == 'fp16':
+            # row count taken from device memory, strided state rows (the env's 616-float pitch)
+            buf = torch.zeros((5000, 616), device='cuda')
+            buf[:, :615] = st[:5000]
+            n_dev = torch.tensor([1234], dtype=torch.int32, device='cuda')
+            out = torch.full((5000, 3), 9.0, device='cuda')
+            ac.actor.forward_device(buf[:, :615], 0.0, n_rows_dev=n_dev, out_action=out, want_logp=False)
+            assert torch.equal(out[:1234], a[:1234]) and (out[1234:] == 9.0).all()
+        del ac
 
 
-def test_actor_packed_bf16_state_matches_packing_path():
-    """ttl_actor_forward_packed (bf16 rows supplied by the env) == ttl_actor_forward (packs fp32)."""
-    ac16, _ = _actor('1024-1024-1024', 1111, 'bf16', 'tracking')
+@pytest.mark.parametrize('prec', ['bf16', 'fp16', 'tf32'])
+def test_actor_packed_operand_rows_match_packing_path(prec):
+    """ttl_actor_forward_packed (operand rows supplied by the env) == ttl_actor_forward (packs fp32)."""
+    ac, _ = _actor('1024-1024-1024', 1111, prec, 'tracking')
     rs = np.random.RandomState(1)
     st = torch.from_numpy(rs.normal(size=(3000, 615)).astype(np.float32)).cuda()
-    sb = torch.zeros((3000, 640), dtype=torch.bfloat16, device='cuda')
-    sb[:, :615] = st.to(torch.bfloat16)
-    a1, _, p1 = ac16.actor.forward_device(st, 0.0, want_pre=True)
-    a2, _, p2 = ac16.actor.forward_device(st, 0.0, want_pre=True, state_bf16=sb)
+    sb = torch.zeros((3000, 640), dtype=OP_DTYPE[prec], device='cuda')
+    sb[:, :615] = _round_operand(st, prec)[1]
+    a1, _, p1 = ac.actor.forward_device(st, 0.0, want_pre=True)
+    a2, _, p2 = ac.actor.forward_device(st, 0.0, want_pre=True, state_bf16=sb)
     assert torch.equal(p1, p2) and torch.equal(a1, a2)
+
+
+@pytest.mark.parametrize('prec', ['fp16', 'tf32'])
+def test_tile_width_and_launch_mode_do_not_change_a_bit(prec):
+    """One persistent launch for the three layers vs one launch per layer, and N tiles of 256 / 128 / 64
+    (chosen from the row count in production): the fused head's partial sums follow a fixed tree, so
+    every combination must give identical bits -- at row counts from 1 to a few thousand, which also
+    exercises the dependency flags between layers when the whole network fits one wave of clusters."""
+    from tracktolearn_b200 import _lib
+    lib = _lib.load()
+    ac, sd = _actor('1024-1024-1024', 1111, prec, 'tracking')
+    rs = np.random.RandomState(2)
+    try:
+        for rows in (1, 100, 257, 2049, 5000):
+            state = rs.normal(size=(rows, 615)).astype(np.float32)
+            st = torch.from_numpy(state).cuda()
+            ref = None
+            for opts in (0, 1, 256 << 8, 128 << 8, 64 << 8, (64 << 8) | 1, (128 << 8) | 1):
+                lib.ttl_actor_options(opts)
+                for _ in range(2):      # twice: the second launch starts from the flags the first one reset
+                    a, lp, pre = ac.actor.forward_device(st, 0.0, want_pre=True)
+                if ref is None:
+                    ref = (a.clone(), pre.clone())
+                    _, _, pre_ref = O.actor_forward(sd, state, 0.0)
+                    assert np.abs(pre.cpu().numpy() - pre_ref).max() <= 1e-3 * max(np.abs(pre_ref).max(), 1e-6)
+                else:
+                    assert torch.equal(pre, ref[1]) and torch.equal(a, ref[0]), (rows, opts)
+    finally:
+        lib.ttl_actor_options(0)
+
+
+def test_fp16_tier_reports_saturation():
+    ac, _ = _actor('1024-1024-1024', 1111, 'fp16', 'tracking')
+    st = torch.zeros((300, 615), device='cuda')
+    ac.actor.forward_device(st, 0.0)
+    assert not ac.actor.overflowed()
+    st[7, 3] = 1e6
+    ac.actor.forward_device(st, 0.0)
+    assert ac.actor.overflowed()
+    assert not ac.actor.overflowed()      # cleared by the read

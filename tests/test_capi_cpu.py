@@ -24,7 +24,7 @@ def test_library_builds_and_exports_declared_symbols():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.ttl_abi_version() == 2
+    assert lib.ttl_abi_version() == _lib.ABI_VERSION == 3
     assert lib.ttl_launch_count() >= 0
 
 
@@ -37,6 +37,7 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ttl_volume), sizeof(ttl_params), sizeof(ttl_batch),
          sizeof(ttl_actor_weights), sizeof(ttl_oracle_weights), offsetof(ttl_batch, alive),
          offsetof(ttl_batch, state), offsetof(ttl_params, theta_rad));
+  printf("%zu %zu %zu\n", offsetof(ttl_batch, sg_stops), offsetof(ttl_batch, operand_fmt), offsetof(ttl_batch, order));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -47,7 +48,8 @@ int main(void) {
         got = [int(x) for x in subprocess.check_output([exe]).split()]
     want = [ctypes.sizeof(_lib.Volume), ctypes.sizeof(_lib.Params), ctypes.sizeof(_lib.Batch),
             ctypes.sizeof(_lib.ActorWeights), ctypes.sizeof(_lib.OracleWeights),
-            _lib.Batch.alive.offset, _lib.Batch.state.offset, _lib.Params.theta_rad.offset]
+            _lib.Batch.alive.offset, _lib.Batch.state.offset, _lib.Params.theta_rad.offset,
+            _lib.Batch.sg_stops.offset, _lib.Batch.operand_fmt.offset, _lib.Batch.order.offset]
     assert got == want
 
 
@@ -72,7 +74,7 @@ def test_tensor_core_kernels_keep_their_registers():
         pytest.skip('cuobjdump not available')
     out = subprocess.run([tool, '-res-usage', _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          check=True).stdout.decode()
-    found = re.findall(r'Function (\S*dense_bf16_2cta_kernel\S*):\s*\n\s*REG:(\d+) STACK:(\d+)', out)
-    assert len(found) == 2, found
+    found = re.findall(r'Function (\S*mlp_pair_kernel\S*):\s*\n\s*REG:(\d+) STACK:(\d+)', out)
+    assert len(found) == 6, found          # {bf16, fp16, tf32} x {plain, fused head}
     for name, reg, stack in found:
         assert int(stack) == 0, (name, reg, stack)

@@ -8,6 +8,17 @@ from tracktolearn_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 
+TC = ['bf16', 'fp16', 'tf32']        # tensor-core tiers of the actor = element types of the env's operand rows
+OP_DTYPE = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'tf32': torch.float32}
+
+
+def _round_like_operand(x, prec):
+    """numpy fp32 -> the values an operand row of type `prec` holds (as fp32)."""
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if prec == 'tf32':          # cvt.rna.tf32.f32: nearest, ties away from zero, 13 low mantissa bits dropped
+        return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).numpy()
+    return t.to(OP_DTYPE[prec]).float().numpy()
+
 
 def _setup(shape=(32, 36, 30), n_seeds=900, precision='fp32'):
     from tests.gpu_helpers import make_gpu_env
@@ -22,6 +33,7 @@ def _setup(shape=(32, 36, 30), n_seeds=900, precision='fp32'):
     sd = synthetic.actor_state_dict(615, '128-128-128', seed=5, kind='tracking')
     alg = SACAuto(615, 3, '128-128-128', n_actors=256, device=torch.device('cuda:0'), precision=precision)
     alg.agent.actor.load_state_dict(sd)
+    env.operand = precision if precision in TC else 'bf16'      # default element type of reset_streaming's rows
     return env, alg, sub, seeds, {k: v.numpy() for k, v in sd.items()}
 
 
@@ -47,7 +59,8 @@ def test_validation_episode_matches_oracle_closed_loop():
     assert same_len.mean() < 1.0 or env.streamline_steps() == int(sum(ref.lengths - 1))
 
 
-def test_streaming_refill_equals_batch_tracking():
+@pytest.mark.parametrize('prec', TC)
+def test_streaming_refill_equals_batch_tracking(prec):
     """Streaming tracker (256 slots over 900 seeds) gives, seed for seed, bit-identical
     streamlines to tracking the seeds in consecutive batches (same kernels, same order of
     arithmetic per streamline)."""
@@ -89,8 +102,9 @@ def test_tracker_track_filters_and_transforms():
     np.testing.assert_allclose(lens, ref, rtol=1e-12, atol=1e-9)
 
 
-def test_bf16_only_state_mode_tracks_the_same_streamlines():
-    """Streaming with the fp32 state tensor materialised vs the bf16-only mode (channel-padded
+@pytest.mark.parametrize('prec', TC)
+def test_bf16_only_state_mode_tracks_the_same_streamlines(prec):
+    """Streaming with the fp32 state tensor materialised vs the operand-only mode (channel-padded
     operand layout, permuted first-layer weights): same operand values, only the K order of the
     first GEMM differs, so trajectories agree to float rounding."""
     env, alg, sub, seeds, sd = _setup(precision='bf16')
@@ -111,7 +125,8 @@ def test_bf16_only_state_mode_tracks_the_same_streamlines():
     assert (a.data_per_streamline['flags'] == b.data_per_streamline['flags'])[same].all()
 
 
-def test_fused_head_step_is_bit_identical_to_action_round_trip():
+@pytest.mark.parametrize('prec', TC)
+def test_fused_head_step_is_bit_identical_to_action_round_trip(prec):
     """Device loop with the env step reading tanh(mu) from the actor's fused output layer
     (ttl_env_step_head) vs actor -> action buffer -> ttl_env_step: same streamlines, bit for bit,
     in both state modes."""
@@ -132,7 +147,8 @@ def test_fused_head_step_is_bit_identical_to_action_round_trip():
     alg.fuse_head = True
 
 
-def test_bf16_direction_block_is_the_rounded_point_differences():
+@pytest.mark.parametrize('prec', TC)
+def test_bf16_direction_block_is_the_rounded_point_differences(prec):
     """Device mode builds the previous-direction block of a state row by shifting the previous row's
     block (bf16) and putting the newest direction in front.  After a number of steps with refills it
     must equal, bit for bit, bf16(points[L-1-k] - points[L-2-k]) recomputed from the fp32 streamline
@@ -153,29 +169,30 @@ def test_bf16_direction_block_is_the_rounded_point_differences():
         rows = bb.alive[env._cur][:n_alive].cpu().numpy()
         npts = bb.npts.cpu().numpy()[rows]
         pts = bb.points.cpu().numpy()[rows]
+        assert bb.state_bf16[env._cur].dtype == OP_DTYPE[prec]
         got = bb.state_bf16[env._cur][:n_alive].float().cpu().numpy()
         want = np.zeros((n_alive, 304), dtype=np.float32)
         for a in range(n_alive):
             L = int(npts[a])
             d = np.diff(pts[a, :L], axis=0)[::-1][:100]          # newest first
             want[a, :d.size] = d.reshape(-1)
-        want = torch.from_numpy(want).to(torch.bfloat16).float().numpy()
+        want = _round_like_operand(want, prec)
         np.testing.assert_array_equal(got[:, 336:640], want)
         checked_long = checked_long or int(npts.max()) > 10
     assert checked_long
 
 
-def test_state_kernel_variants_write_identical_rows():
-    """The 56-corner gather (default), the deduplicated 32-voxel gather (bit 4, two occupancies), the
-    shifted direction block (default) and the recomputed one (bit 3) produce bit-identical bf16
-    operands, hence bit-identical streamlines."""
+@pytest.mark.parametrize('prec', TC)
+def test_state_kernel_variants_write_identical_rows(prec):
+    """The shifted direction block (default) and the recomputed one (bit 3), with and without the L2
+    prefetch (bit 1), produce bit-identical operand rows, hence bit-identical streamlines."""
     from tracktolearn_b200 import _lib
     lib = _lib.load()
     env, alg, sub, seeds, sd = _setup(precision='bf16')
     n = len(seeds)
     out, rows = [], []
     try:
-        for opts in (0, 16, 16 | 32, 8):
+        for opts in (0, 8, 2, 8 | 1):
             lib.ttl_state_options(opts)
             st = env.reset_streaming(0, n, 256, fp32_state=False)
             from tracktolearn_b200.algorithms.rl import StepRunner
@@ -189,14 +206,16 @@ def test_state_kernel_variants_write_identical_rows():
             out.append(env.get_streamlines())
     finally:
         lib.ttl_state_options(0)
+    bits = torch.int32 if prec == 'tf32' else torch.int16
     for r in rows[1:]:
-        assert torch.equal(rows[0].view(torch.int16), r.view(torch.int16))
+        assert torch.equal(rows[0].view(bits), r.view(bits))
     for b in out[1:]:
         np.testing.assert_array_equal(out[0].lengths, b.lengths)
         np.testing.assert_array_equal(out[0].data, b.data)
 
 
-def test_cuda_graph_replay_equals_plain_launches():
+@pytest.mark.parametrize('prec', TC)
+def test_cuda_graph_replay_equals_plain_launches(prec):
     """validation_episode with the step replayed from two captured CUDA graphs (one per ping-pong
     parity; programmatic-dependent-launch edges inside) vs plain launches: same streamlines."""
     env, alg, sub, seeds, sd = _setup(precision='bf16')
@@ -218,7 +237,8 @@ def test_cuda_graph_replay_equals_plain_launches():
     np.testing.assert_array_equal(a.data_per_streamline['flags'], b.data_per_streamline['flags'])
 
 
-def test_locality_order_does_not_change_any_streamline():
+@pytest.mark.parametrize('prec', TC)
+def test_locality_order_does_not_change_any_streamline(prec):
     """Streaming tracker with the seeds entering the slots in voxel raster order (ttl_batch.order) vs
     in row order: every row holds the same streamline, bit for bit, and the output order is the
     rows' (shuffled) order in both."""

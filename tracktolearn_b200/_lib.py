@@ -11,7 +11,11 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libttl_b200.so')
 c_i32, c_i64, c_f32, c_f64, c_vp = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
                                     ctypes.c_void_p)
 MAX_LAYERS = 8
-PRECISION_BF16, PRECISION_FP32 = 0, 1
+PRECISION_BF16, PRECISION_FP32, PRECISION_FP16, PRECISION_TF32 = 0, 1, 2, 3
+PRECISIONS = {'bf16': PRECISION_BF16, 'fp32': PRECISION_FP32, 'fp16': PRECISION_FP16, 'tf32': PRECISION_TF32}
+OPERAND_BF16, OPERAND_FP16, OPERAND_TF32 = 0, 1, 2
+OPERAND_OF_PRECISION = {'bf16': OPERAND_BF16, 'fp16': OPERAND_FP16, 'tf32': OPERAND_TF32}
+ABI_VERSION = 3
 
 
 class Volume(ctypes.Structure):
@@ -32,7 +36,8 @@ class Batch(ctypes.Structure):
                 ('npts', c_vp), ('dones', c_vp), ('alive', c_vp * 2), ('ctrl', c_vp), ('stop', c_vp), ('dest', c_vp),
                 ('step_flags', c_vp), ('reward', c_vp), ('state', c_vp * 2),
                 ('state_bf16', c_vp * 2), ('ld_bf16', c_i32), ('max_groups', c_i32), ('grp_stops', c_vp),
-                ('grp_prefix', c_vp), ('bf16_layout', c_i32), ('rank_rec', c_vp * 2), ('step_tip', c_vp), ('order', c_vp)]
+                ('sg_stops', c_vp), ('bf16_layout', c_i32), ('rank_rec', c_vp * 2), ('step_tip', c_vp),
+                ('operand_fmt', c_i32), ('order', c_vp)]
 
 
 class ActorWeights(ctypes.Structure):
@@ -62,7 +67,7 @@ SIGNATURES = {
                                   c_i32, c_vp, c_vp]),
     'ttl_env_reset': (c_i32, [P(Volume), P(Params), P(Batch), c_vp, c_vp]),
     'ttl_env_step': (c_i32, [P(Volume), P(Params), P(Batch), c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]),
-    'ttl_env_step_head': (c_i32, [P(Volume), P(Params), P(Batch), c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]),
+    'ttl_env_step_head': (c_i32, [P(Volume), P(Params), P(Batch), c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_vp]),
     'ttl_env_step_begin': (c_i32, [P(Volume), P(Params), P(Batch), c_i32, c_vp, c_i32, c_vp, c_i32, c_vp]),
     'ttl_env_step_finish': (c_i32, [P(Volume), P(Params), P(Batch), c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp]),
     'ttl_oracle_features_rows': (c_i32, [P(Batch), c_i32, c_i32, c_vp, c_vp]),
@@ -73,14 +78,18 @@ SIGNATURES = {
     'ttl_streamline_lengths': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
     'ttl_compress_mask': (c_i32, [c_vp, c_vp, c_i32, c_f64, c_f64, c_vp, c_vp, c_vp]),
     'ttl_pack_streamlines': (c_i32, [P(Batch), c_vp, c_vp, c_vp]),
-    'ttl_actor_workspace_bytes': (c_i64, [P(ActorWeights), c_i32]),
-    'ttl_actor_plan_create': (c_i32, [P(c_vp), P(ActorWeights), c_i32, c_vp, c_i64, c_vp]),
+    'ttl_actor_workspace_bytes': (c_i64, [P(ActorWeights), c_i32, c_i32]),
+    'ttl_actor_plan_create': (c_i32, [P(c_vp), P(ActorWeights), c_i32, c_i32, c_vp, c_i64, c_vp]),
     'ttl_actor_plan_destroy': (None, [c_vp]),
+    'ttl_actor_precision': (c_i32, [c_vp]),
+    'ttl_actor_options': (None, [c_i32]),
     'ttl_actor_plan_refresh': (c_i32, [c_vp, c_vp]),
-    'ttl_actor_forward': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
+    'ttl_actor_forward': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'ttl_actor_forward_packed': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
-    'ttl_actor_head_partial': (c_i32, [c_vp, P(c_vp), P(c_i32), P(c_vp)]),
+    'ttl_actor_head_partial': (c_i32, [c_vp, P(c_vp), P(c_i32), P(c_i32), P(c_vp)]),
+    'ttl_actor_overflow': (c_i32, [c_vp, P(c_i32), c_i32, c_vp]),
     'ttl_actor_plan_set_layout': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'ttl_gemm_tc': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
     'ttl_gemm_bf16': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'ttl_oracle_features': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
     'ttl_oracle_forward': (c_i32, [P(OracleWeights), c_vp, c_i32, c_vp, c_vp]),
@@ -105,11 +114,22 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise TTLError('%s not found: build it with `python -m tracktolearn_b200.build` '
                        '(there is no CPU fallback)' % LIB_PATH)
+    # a library built from other sources than the ones next to it must not be used silently
+    from tracktolearn_b200 import build as _build
+    stamp = os.path.join(os.path.dirname(LIB_PATH), 'libttl_b200.sha256')
+    if os.path.isdir(_build.CSRC) and os.environ.get('TTL_SKIP_DIGEST', '0') != '1':
+        have = open(stamp).read().strip() if os.path.exists(stamp) else None
+        if have != _build._digest():
+            raise TTLError('%s is stale (its stamp does not match csrc/ + include/ttl_b200.h): rebuild it with '
+                           '`python -m tracktolearn_b200.build`' % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.ttl_abi_version() != ABI_VERSION:
+        raise TTLError('%s has ABI version %d, this package binds version %d: rebuild it'
+                       % (LIB_PATH, lib.ttl_abi_version(), ABI_VERSION))
     if os.environ.get('TTL_PDL', '1') == '0':      # A/B measurements: plain stream-ordered launches
         lib.ttl_pdl_enable(0)
     _lib = lib

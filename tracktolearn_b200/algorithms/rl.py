@@ -40,7 +40,8 @@ class StepRunner(object):
         env = self.env
         if self.fuse_head:
             head = self.actor.forward_head_partial(env.current_state_bf16(), rows,
-                                                   n_rows_dev=env.alive_count_tensor(), layout=env.bf16_layout)
+                                                   n_rows_dev=env.alive_count_tensor(), layout=env.bf16_layout,
+                                                   state=env.current_state())
             if head is not None:
                 env.step_device_head(head)
                 env.harvest_device()

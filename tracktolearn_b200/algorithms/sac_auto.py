@@ -16,7 +16,7 @@ class SACAuto(RLAlgorithm):
 
     def __init__(self, input_size, action_size, hidden_dims, lr=3e-4, gamma=0.99, alpha=0.2,
                  n_actors=4096, batch_size=2 ** 12, replay_size=1e6, rng=None, device=None,
-                 precision='bf16'):
+                 precision='fp16'):
         super().__init__(input_size, action_size, hidden_dims, lr, gamma, batch_size, rng, device)
         self.n_actors = n_actors
         self.agent = SACActorCritic(input_size, action_size, hidden_dims, device, precision=precision)

@@ -2,10 +2,19 @@
 (reference: algorithms/shared/offpolicy.py:234-482).
 
 The actor forward -- the only dense contraction on the tracking path -- runs through
-``ttl_actor_forward`` (csrc/ttl_actor.cu): tcgen05 tensor cores in bf16 with fp32 TMEM
-accumulators by default, or the CUDA-core fp32 tier with ``precision='fp32'``.
-The critic is only carried for checkpoint compatibility (``load`` reads both files like the
-reference does, offpolicy.py:342-357); training updates are out of this package's hot path.
+``ttl_actor_forward`` (csrc/ttl_actor.cu, csrc/ttl_mlp.cuh) on tcgen05 tensor cores with fp32 TMEM
+accumulators.  ``precision`` picks the operand type:
+
+  'fp16'  (default) 11 significant bits at the full 16-bit tensor rate; outputs within 1e-3 of the
+          reference's fp32 arithmetic (measured ~5e-4 of the output scale).  Range +-65504: values
+          outside saturate and raise a flag (``MaxEntropyActor.overflowed()``); re-run in 'tf32' then.
+  'tf32'  the same 11 bits with fp32's range at half the tensor rate.
+  'bf16'  8 significant bits: ~4e-3 of the output scale, outside the 1e-3 tolerance; kept for
+          throughput comparisons.
+  'fp32'  the reference's arithmetic on the CUDA cores (1e-5), used by the parity tests.
+
+The critic is carried for checkpoint compatibility (``load`` reads both files like the reference does,
+offpolicy.py:342-357) and handed to the learner when training is enabled.
 """
 import ctypes
 import os
@@ -27,7 +36,9 @@ class MaxEntropyActor(object):
 
     ``state_dict`` keys: ``layers.{0,2,4,..}.{weight,bias}`` (shared/utils.py:41-51)."""
 
-    def __init__(self, state_dim, action_dim, hidden_dims, device, precision='bf16'):
+    def __init__(self, state_dim, action_dim, hidden_dims, device, precision='fp16'):
+        if precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s, not %r" % (sorted(_lib.PRECISIONS), precision))
         self.state_dim = int(state_dim)
         self.action_dim = int(action_dim)
         self.hidden_layers = format_widths(hidden_dims)
@@ -120,13 +131,14 @@ class MaxEntropyActor(object):
         self._drop_plan()
         rows = max(int(rows), 128)
         w = self._weights_struct()
-        nbytes = self._lib.ttl_actor_workspace_bytes(ctypes.byref(w), rows)
+        prec = _lib.PRECISIONS[self.precision]
+        nbytes = self._lib.ttl_actor_workspace_bytes(ctypes.byref(w), rows, prec)
         if nbytes < 0:
             raise _lib.TTLError('unsupported actor architecture %s' % (self._dims,))
         self._workspace = torch.zeros((nbytes + 1024,), dtype=torch.uint8, device=self.device)
         base = (self._workspace.data_ptr() + 1023) // 1024 * 1024
         plan = ctypes.c_void_p()
-        _lib.check(self._lib.ttl_actor_plan_create(ctypes.byref(plan), ctypes.byref(w), rows,
+        _lib.check(self._lib.ttl_actor_plan_create(ctypes.byref(plan), ctypes.byref(w), rows, prec,
                                                    ctypes.c_void_p(base), nbytes,
                                                    _lib.stream_ptr(self.device)), 'ttl_actor_plan_create')
         self._plan = plan
@@ -137,8 +149,8 @@ class MaxEntropyActor(object):
                        want_logp=True, want_pre=False, out_action=None, state_bf16=None, layout=None):
         """state: CUDA fp32 [rows, >= state_dim] (row stride free).  ``n_rows_dev``: optional
         device int32 tensor with the live row count (no host sync).  ``state_bf16``: the env's
-        bf16 zero-padded copy of the same rows ([rows_alloc, round_up(state_dim, 64)]); with it
-        the bf16 tier skips its packing pass.  Returns
+        zero-padded copy of the same rows in this actor's operand type ([rows_alloc,
+        round_up(state_dim, 64)], ``env.current_state_bf16()``); with it the packing pass is skipped.  Returns
         (action [rows,3], logp [rows] or None, pre [rows,6] or None)."""
         if state is not None:
             if state.dim() < 2:
@@ -158,8 +170,7 @@ class MaxEntropyActor(object):
         if probabilistic != 0.0 and eps is None:
             eps = torch.randn((rows, A), dtype=torch.float32, device=self.device)
         self._ensure_plan(rows)
-        prec = _lib.PRECISION_BF16 if self.precision == 'bf16' else _lib.PRECISION_FP32
-        if prec == _lib.PRECISION_BF16 and state_bf16 is not None:
+        if self._operand_matches(state_bf16):
             lay = 0
             if layout is not None and layout[0] == 1:
                 lay = 1
@@ -174,43 +185,74 @@ class MaxEntropyActor(object):
                 _lib.ptr(logp), _lib.ptr(pre), lay, _lib.stream_ptr(self.device)), 'ttl_actor_forward_packed')
             self._keep = (state_bf16, eps)
             return action, logp, pre
+        if state is None:
+            raise _lib.TTLError('the env produced %s operand rows only; a %s actor needs matching operand rows or the '
+                                'fp32 state tensor' % (state_bf16.dtype, self.precision))
         ld = state.stride(0) if state.shape[0] > 1 else state.shape[1]
         _lib.check(self._lib.ttl_actor_forward(
             self._plan, _lib.ptr(state), int(ld), _lib.ptr(n_rows_dev), rows, float(probabilistic),
-            _lib.ptr(eps), _lib.ptr(action), _lib.ptr(logp), _lib.ptr(pre), prec,
+            _lib.ptr(eps), _lib.ptr(action), _lib.ptr(logp), _lib.ptr(pre),
             _lib.stream_ptr(self.device)), 'ttl_actor_forward')
         self._keep = (state, eps)
         return action, logp, pre
 
-    def forward_head_partial(self, state_bf16, n_rows, n_rows_dev=None, layout=None):
+    def forward_head_partial(self, state_bf16, n_rows, n_rows_dev=None, layout=None, state=None):
         """Deterministic policy (prob = 0) for the device loop: runs the tensor-core layers over the
-        env's bf16 state rows and leaves the 6-wide output layer as per-tile partial sums in the
-        plan's scratch.  Returns (partial_ptr, n_tiles, bias_ptr) for ``env.step_device_head``, or
-        None when this actor cannot do it (fp32 tier, output layer not fused)."""
-        if self.precision != 'bf16' or state_bf16 is None:
+        env's operand rows (or, when their element type is not this actor's, over ``state``: the fp32 rows,
+        packed first) and leaves the 6-wide output layer as per-tile partial sums in the plan's scratch.
+        Returns (partial_ptr, n_tiles, tiles_per_256, bias_ptr) for ``env.step_device_head``, or None when
+        this actor cannot do it (fp32 tier, output layer not fused, no usable rows)."""
+        packed = self._operand_matches(state_bf16)
+        if self.precision not in self._OPERAND_DTYPES or (not packed and state is None):
             return None
         rows = int(n_rows)
         self._ensure_plan(rows)
-        partial, n_tiles, bias = ctypes.c_void_p(), ctypes.c_int32(), ctypes.c_void_p()
-        rc = self._lib.ttl_actor_head_partial(self._plan, ctypes.byref(partial), ctypes.byref(n_tiles),
-                                              ctypes.byref(bias))
-        if rc != 0:
+        partial, n_tiles, per256, bias = ctypes.c_void_p(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_void_p()
+
+        def query():
+            return self._lib.ttl_actor_head_partial(self._plan, ctypes.byref(partial), ctypes.byref(n_tiles),
+                                                    ctypes.byref(per256), ctypes.byref(bias))
+        if query() != 0:          # the output layer is not fused into the last hidden layer
             return None
-        lay = 0
-        if layout is not None and layout[0] == 1:
-            lay = 1
-            if self._plan_layout != tuple(layout):
-                _lib.check(self._lib.ttl_actor_plan_set_layout(
-                    self._plan, int(layout[1]), int(layout[2]), int(layout[3]),
-                    _lib.stream_ptr(self.device)), 'ttl_actor_plan_set_layout')
-                self._plan_layout = tuple(layout)
-        if rows > 0:
+        if rows > 0 and packed:
+            lay = 0
+            if layout is not None and layout[0] == 1:
+                lay = 1
+                if self._plan_layout != tuple(layout):
+                    _lib.check(self._lib.ttl_actor_plan_set_layout(
+                        self._plan, int(layout[1]), int(layout[2]), int(layout[3]),
+                        _lib.stream_ptr(self.device)), 'ttl_actor_plan_set_layout')
+                    self._plan_layout = tuple(layout)
             _lib.check(self._lib.ttl_actor_forward_packed(
                 self._plan, _lib.ptr(state_bf16), int(state_bf16.stride(0)), int(state_bf16.shape[0]),
                 _lib.ptr(n_rows_dev), rows, 0.0, None, None, None, None, lay,
                 _lib.stream_ptr(self.device)), 'ttl_actor_forward_packed')
-        self._keep = (state_bf16, None)
-        return partial.value, int(n_tiles.value), bias.value
+            self._keep = (state_bf16, None)
+        elif rows > 0:
+            ld = state.stride(0) if state.shape[0] > 1 else state.shape[1]
+            _lib.check(self._lib.ttl_actor_forward(
+                self._plan, _lib.ptr(state), int(ld), _lib.ptr(n_rows_dev), rows, 0.0, None, None, None, None,
+                _lib.stream_ptr(self.device)), 'ttl_actor_forward')
+            self._keep = (state, None)
+        query()                   # the geometry of the partials depends on the launch just made
+        return partial.value, int(n_tiles.value), int(per256.value), bias.value
+
+    _OPERAND_DTYPES = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'tf32': torch.float32}
+
+    def _operand_matches(self, rows):
+        """Can ``rows`` (the env's operand rows) feed the first layer as they are?"""
+        return (rows is not None and self.precision in self._OPERAND_DTYPES
+                and rows.dtype == self._OPERAND_DTYPES[self.precision])
+
+    def overflowed(self, clear=True):
+        """fp16 tier: True when a state or activation value had to be saturated to +-65504 since the
+        last clearing call (one 4-byte D2H copy + stream sync).  Always False for the other tiers."""
+        if self.precision != 'fp16' or self._plan is None:
+            return False
+        out = ctypes.c_int32(0)
+        _lib.check(self._lib.ttl_actor_overflow(self._plan, ctypes.byref(out), int(bool(clear)),
+                                                _lib.stream_ptr(self.device)), 'ttl_actor_overflow')
+        return bool(out.value)
 
     def __call__(self, state, probabilistic):
         """Reference: MaxEntropyActor.forward (offpolicy.py:94-140) -> (pi_action, logp_pi)."""
@@ -230,7 +272,7 @@ class MaxEntropyActor(object):
 class SACActorCritic(object):
     """Reference: algorithms/shared/offpolicy.py:407-482 (+ ActorCritic base :234-372)."""
 
-    def __init__(self, state_dim, action_dim, hidden_dims, device, precision='bf16'):
+    def __init__(self, state_dim, action_dim, hidden_dims, device, precision='fp16'):
         self.device = torch.device(device)
         self.actor = MaxEntropyActor(state_dim, action_dim, hidden_dims, self.device, precision)
         self.critic_state_dict = None   # carried for save/load symmetry; not evaluated here

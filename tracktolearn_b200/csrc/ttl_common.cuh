@@ -69,6 +69,57 @@ static inline cudaError_t ttl_launch_chain(void (*kernel)(KArgs...), dim3 grid, 
 }
 #endif
 
+// ---- operand conversions shared by the actor kernels and the env's state kernel --------------------
+// fp32 -> tf32 (10-bit mantissa) with round-to-nearest, returned as the fp32 bit pattern
+__device__ __forceinline__ uint32_t ttl_round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// two fp32 -> packed fp16 pair (lo = a, hi = b), saturating to +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t ttl_pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// two fp32 -> packed bf16 pair (lo = a, hi = b)
+__device__ __forceinline__ uint32_t ttl_pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// fmt: TTL_OPERAND_BF16 or TTL_OPERAND_FP16 (run-time)
+__device__ __forceinline__ uint32_t ttl_pack16(float a, float b, int fmt) {
+  return fmt == TTL_OPERAND_FP16 ? ttl_pack_f16x2_sat(a, b) : ttl_pack_bf16x2(a, b);
+}
+
+// Sum of the actor's fused-head partials for one output.  The producing kernel (ttl_mlp.cuh) forms
+// a tile's partial as a fixed tree over 64-column groups -- p_g = fma chain over group g, tile =
+// (p0 + p1) + (p2 + p3) over the groups it covers -- so that the total does not depend on the tile
+// width of the launch: the consumer rebuilds the tree per 256-column super-tile and adds the
+// super-tiles left to right.  p: this row's partials [n_tiles][8]; tiles_per_256 = 256 / tile width.
+__device__ __forceinline__ float ttl_head_tree_sum(const float* __restrict__ p, int n_tiles, int tiles_per_256,
+                                                  int o) {
+  float acc = 0.f;
+  for (int t = 0; t < n_tiles; t += tiles_per_256) {
+    float s;
+    if (tiles_per_256 == 1) {
+      s = __ldg(p + (size_t)t * 8 + o);
+    } else if (tiles_per_256 == 2) {
+      const float a = __ldg(p + (size_t)t * 8 + o);
+      const float b = t + 1 < n_tiles ? __ldg(p + (size_t)(t + 1) * 8 + o) : 0.f;
+      s = a + b;
+    } else {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = t + j < n_tiles ? __ldg(p + (size_t)(t + j) * 8 + o) : 0.f;
+      s = (v[0] + v[1]) + (v[2] + v[3]);
+    }
+    acc += s;
+  }
+  return acc;
+}
+
 __device__ __forceinline__ uint32_t ttl_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -17,17 +17,19 @@
 // [rank][ld_state=616] fp32 so rows start 16-byte aligned.
 //
 // Two launches per step, none of which needs the host:
-//   propagate_stop  one thread per alive streamline (byte/flag work, 64 fp64 spline taps); each
-//                   CTA publishes how many of its 128 ranks stopped and the last CTA to finish
-//                   scans those counts (ordered compaction bookkeeping, slot refill, counters)
-//   build_state     one warp per rank: derives its position in the compacted alive list from
-//                   the group prefix + a ballot over its group's stop flags (keeps the
-//                   reference's ascending continue_idx order), stages the 7x8 trilinear corner
-//                   voxels (192 B each) into shared memory with cp.async (all ~10 KB in flight
-//                   at once, duplicates of the ~26-voxel footprint hit L1), then every lane
-//                   produces consecutive state elements so fp32 and bf16 rows are written with
-//                   fully coalesced stores.
+//   propagate_stop  4 lanes per alive streamline (byte/flag work, 64 fp64 spline taps split over the
+//                   lanes); each CTA (32 ranks) publishes how many of its ranks stopped, per group and
+//                   added into a counter per super-group of 64 groups -- no scan, no waiting
+//   build_state     one warp per rank: derives its position in the compacted alive list from the
+//                   super-group counters + the group counts of its super-group + a ballot over its
+//                   group's stop flags (keeps the reference's ascending continue_idx order), gathers
+//                   the 7x8 trilinear corner voxels as LDG.128 straight into registers (duplicates of
+//                   the ~26-voxel footprint hit L1) and writes the fp32 row and / or the actor's
+//                   operand row (bf16, fp16 or tf32-rounded fp32); one thread of the grid advances the
+//                   control block (next alive count, slot refill, counters).
+// The kernel boundary is the only synchronisation between the two.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "ttl_common.cuh"
 
@@ -38,6 +40,8 @@ namespace {
 constexpr int kGroup = 32;          // ranks per compaction group == rows per propagate_stop CTA
 constexpr int kLanesPerRow = 4;     // lanes that share one streamline's 64 spline taps
 constexpr int kK1Threads = kGroup * kLanesPerRow;
+constexpr int kSuper = 64;          // groups per super-group counter (ttl_batch.sg_stops)
+__host__ __device__ __forceinline__ int super_count(int max_groups) { return (max_groups + kSuper - 1) / kSuper; }
 
 // ------------------------------------------------------------------------------------------
 // float helpers that refuse FMA contraction, so sums of products round like numpy's
@@ -319,7 +323,11 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
     b.ctrl[8] = 0;
     b.ctrl[9] = 0;
     b.ctrl[10] = 0;
+    b.ctrl[12] = n0;  // ping-pong copies of the cursor that the step kernels read / write
+    b.ctrl[13] = n0;
+    b.ctrl[14] = 0;   // fp16 operand rows: a state value saturated
   }
+  for (int j = i; j < 2 * super_count(b.max_groups); j += gridDim.x * blockDim.x) b.sg_stops[j] = 0;
   if (i < b.n_slots) {
     b.dest[i] = i;
     b.stop[i] = 0;
@@ -343,101 +351,18 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
   b.dones[i] = 0;
 }
 
-// Ordered-compaction bookkeeping shared by propagate_stop_kernel and oracle_apply_kernel: every
-// CTA (kGroup ranks, kK1Threads threads) publishes how many of its ranks stopped; the CTA with the
-// highest index waits for all of them, scans the per-group survivor counts and updates the control
-// block (next alive count, slot refill, counters).  `stopped` must be non-zero in exactly one thread per stopped rank.
-__device__ void compaction_bookkeeping(const ttl_batch& b, const ttl_params& prm, int cur, int n_alive,
-                                       int stopped) {
-  __shared__ int s_part[kK1Threads / 32];
+// Ordered-compaction bookkeeping shared by propagate_stop_kernel and oracle_apply_kernel: every CTA
+// (kGroup ranks, kK1Threads threads) publishes how many of its ranks stopped -- per group, and added
+// into the counter of its super-group (kSuper groups).  Nothing waits: the state kernel that follows
+// turns the counts into positions (survivors_before) and advances the control block, with the kernel
+// boundary as the only synchronisation.  `stopped` must be non-zero in exactly one thread per stopped
+// rank.  sg_stops holds two sets of counters; set `cur` is used by the step that reads alive[cur] and
+// is cleared again by the state kernel of the following step.
+__device__ __forceinline__ void publish_stops(const ttl_batch& b, int cur, int stopped) {
   const int grp_stops = __syncthreads_count(stopped);
-  // Every CTA publishes its count with a release-add and leaves at once (waiting for an atomic's
-  // return value to learn "am I the last one" kept every CTA on its SM for an L2 round trip: 13 % of
-  // the kernel's stall samples).  The CTA with the highest index -- dispatched after all the
-  // others -- is the scanner: it waits until the counter shows the whole grid.
   if (threadIdx.x == 0) {
     b.grp_stops[blockIdx.x] = grp_stops;
-    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(b.ctrl + 7) : "memory");
-  }
-  if (blockIdx.x != gridDim.x - 1) return;
-  if (threadIdx.x == 0) {
-    int seen;
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(b.ctrl + 7) : "memory");
-      if (seen >= (int)gridDim.x) break;
-      __nanosleep(64);
-    }
-  }
-  __syncthreads();
-  // Thread t owns the contiguous groups [g0, g1).  Up to kScanUnroll groups per thread are loaded
-  // as independent L2 reads and kept in registers (50 000 slots: 1563 groups, 13 per thread), so
-  // the serial tail of the step is one load latency + one block scan.
-  constexpr int kScanUnroll = 16;
-  const int ngrp = gridDim.x;
-  const int per = (ngrp + kK1Threads - 1) / kK1Threads;
-  const int g0 = min(ngrp, (int)threadIdx.x * per), g1 = min(ngrp, g0 + per);
-  int surv[kScanUnroll];
-  int keep = 0;
-  if (per <= kScanUnroll) {
-#pragma unroll
-    for (int u = 0; u < kScanUnroll; ++u) {
-      const int g = g0 + u;
-      surv[u] = g < g1 ? __ldcg(b.grp_stops + g) : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < kScanUnroll; ++u) {
-      const int g = g0 + u;
-      surv[u] = g < g1 ? max(0, min(kGroup, n_alive - g * kGroup)) - surv[u] : 0;
-      keep += surv[u];
-    }
-  } else {
-    for (int g = g0; g < g1; ++g) keep += max(0, min(kGroup, n_alive - g * kGroup)) - __ldcg(b.grp_stops + g);
-  }
-  // block-wide inclusive scan of `keep`: shuffles inside the warp, warp totals through shared memory
-  int incl = keep;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int a = __shfl_up_sync(0xffffffffu, incl, off);
-    if ((int)(threadIdx.x & 31) >= off) incl += a;
-  }
-  if ((threadIdx.x & 31) == 31) s_part[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  int warp_off = 0, total_keep_all = 0;
-#pragma unroll
-  for (int w = 0; w < kK1Threads / 32; ++w) {
-    const int tw = s_part[w];
-    if (w < (int)(threadIdx.x >> 5)) warp_off += tw;
-    total_keep_all += tw;
-  }
-  int pos = warp_off + incl - keep;
-  if (per <= kScanUnroll) {
-#pragma unroll
-    for (int u = 0; u < kScanUnroll; ++u) {
-      const int g = g0 + u;
-      if (g < g1) b.grp_prefix[g] = pos;
-      pos += surv[u];
-    }
-  } else {
-    for (int g = g0; g < g1; ++g) {
-      b.grp_prefix[g] = pos;
-      pos += max(0, min(kGroup, n_alive - g * kGroup)) - __ldcg(b.grp_stops + g);
-    }
-  }
-  if (threadIdx.x == kK1Threads - 1) {
-    const int total_keep = total_keep_all;
-    const int cursor = b.ctrl[6];
-    int n_new = 0;
-    if (prm.refill) n_new = max(0, min(b.n_slots - total_keep, b.n - cursor));
-    b.ctrl[cur ^ 1] = total_keep + n_new;   // alive count of the next list
-    b.ctrl[2] = b.ctrl[2] + 1;
-    b.ctrl[3] = n_alive;
-    b.ctrl[6] = cursor + n_new;
-    b.ctrl[7] = 0;
-    b.ctrl[8] = total_keep;
-    b.ctrl[9] = n_new;
-    b.ctrl[10] = cursor;
-    long long* total = reinterpret_cast<long long*>(b.ctrl + 4);
-    *total += n_alive;
+    if (grp_stops) atomicAdd(b.sg_stops + cur * super_count(b.max_groups) + (blockIdx.x / kSuper), grp_stops);
   }
 }
 
@@ -453,6 +378,7 @@ struct ActionSrc {
   int lda;
   const float* partial;   // [n_alive][n_tiles][8] fp32 per-n-tile partial sums of the 6-wide head
   int n_tiles;
+  int tiles_per_256;      // 256 / (tile width of the launch that wrote the partials)
   const float* bias;      // head bias
   int n_rows;             // rows the launch covers (>= the alive count): bound for speculative loads
 };
@@ -473,11 +399,10 @@ __global__ void __launch_bounds__(kK1Threads, MINB) propagate_stop_kernel(
   const RankRec rec = read_rank_rec(b.rank_rec[cur], r_ld);
   float ax = 0.f, ay = 0.f, az = 0.f;
   if (src.partial) {
-    const float4* hp = reinterpret_cast<const float4*>(src.partial + (size_t)r_ld * src.n_tiles * 8);
-    for (int t = 0; t < src.n_tiles; ++t) {
-      const float4 pt = __ldg(hp + 2 * t);
-      ax += pt.x; ay += pt.y; az += pt.z;
-    }
+    const float* hp = src.partial + (size_t)r_ld * src.n_tiles * 8;
+    ax = ttl_head_tree_sum(hp, src.n_tiles, src.tiles_per_256, 0);
+    ay = ttl_head_tree_sum(hp, src.n_tiles, src.tiles_per_256, 1);
+    az = ttl_head_tree_sum(hp, src.n_tiles, src.tiles_per_256, 2);
   } else {
     ax = src.actions[(size_t)r_ld * src.lda + 0];
     ay = src.actions[(size_t)r_ld * src.lda + 1];
@@ -570,7 +495,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB) propagate_stop_kernel(
   }
   }  // r < n_alive
 
-  if (!(defer & 1)) compaction_bookkeeping(b, prm, cur, n_alive, stopped);
+  if (!(defer & 1)) publish_stops(b, cur, stopped);
 }
 
 // OracleStoppingCriterion (stopping_criteria.py:113-154) and OracleReward (oracle_reward.py:45-93)
@@ -603,7 +528,7 @@ __global__ void __launch_bounds__(kK1Threads) oracle_apply_kernel(ttl_params prm
     if (prm.compute_reward && bonus > 0.f && stopped && L > min_pts_reward && sc > 0.5f)
       b.reward[r] = (float)((double)b.reward[r] + (double)bonus);
   }
-  compaction_bookkeeping(b, prm, cur, n_alive, stopped);
+  publish_stops(b, cur, stopped);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -715,8 +640,8 @@ __device__ __forceinline__ void prefetch_corners(const ttl_volume& v, const int*
 // Generic channel count: lane l produces elements l, l+32, ... with scalar gathers.
 __device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& prm, const float* P, int L, float3 tip,
                                         float* __restrict__ out_f32, int n_f32,
-                                        __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f,
-                                        int lane) {
+                                        uint16_t* __restrict__ out_bf16, int n_bf16, float* smem_f,
+                                        int lane, int fmt) {
   float* s_w = smem_f;
   int* s_vox = reinterpret_cast<int*>(smem_f + 64);
   float* s_pts = smem_f + 128;
@@ -745,10 +670,7 @@ __device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& p
     if (out_f32 && o < n_f32) out_f32[o] = val;
     if (out_bf16) {
       const float nxt = __shfl_down_sync(0xffffffffu, val, 1);
-      if (!(lane & 1) && o < n_bf16) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(val, nxt);
-        *reinterpret_cast<__nv_bfloat162*>(out_bf16 + o) = h;
-      }
+      if (!(lane & 1) && o < n_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + o) = ttl_pack16(val, nxt, fmt);
     }
   }
   __syncwarp();
@@ -764,7 +686,7 @@ __device__ void build_state_row_generic(const ttl_volume& v, const ttl_params& p
 // measured at 172 us/step at 50 000 rows: 12.5 KB/warp capped the SM at 16 warps.)
 __device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, const float* P, int L, float3 tip,
                                     float* __restrict__ out_f32, int n_f32,
-                                    __nv_bfloat16* __restrict__ out_bf16, int n_bf16, float* smem_f, int lane) {
+                                    uint16_t* __restrict__ out_bf16, int n_bf16, float* smem_f, int lane, int fmt) {
   constexpr int C = 45, CP4 = 12, S = 7 * C;
   float* s_w = smem_f;                                  // [56] trilinear weights
   int* s_vox = reinterpret_cast<int*>(smem_f + 64);     // [56] voxel index
@@ -831,29 +753,48 @@ __device__ void build_state_row_c45(const ttl_volume& v, const ttl_params& prm, 
     for (int q = lane; q < (n_bf16 >> 3); q += 32) {
       const float4 a = *reinterpret_cast<const float4*>(s_row + 8 * q);
       const float4 c = *reinterpret_cast<const float4*>(s_row + 8 * q + 4);
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(c.x, c.y), h3 = __floats2bfloat162_rn(c.z, c.w);
-      d8[q] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                         *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+      d8[q] = make_uint4(ttl_pack16(a.x, a.y, fmt), ttl_pack16(a.z, a.w, fmt), ttl_pack16(c.x, c.y, fmt),
+                         ttl_pack16(c.z, c.w, fmt));
     }
   }
   __syncwarp();
 }
 
-// Direction block of a device-mode row (columns 336..639 of the bf16 operand): the previous row's
-// block moved back by one direction with the newest one in front -- a 6-byte shift of 600 bytes of
-// bf16 instead of re-reading 101 fp32 points and redoing 300 subtractions (each value was rounded to
-// bf16 when it was the newest; copying it is the same as recomputing it).  A fresh streamline
-// (L == 1) has no directions.  n_dirs == 100, 304 columns.
-__device__ __forceinline__ void write_dirs_shifted(const __nv_bfloat16* __restrict__ old_dirs,
-                                                   __nv_bfloat16* __restrict__ out_dirs, int L, float3 tip,
-                                                   float3 prev_tip, int lane) {
+// Direction block of a device-mode row (columns 336..639 of the operand row): the previous row's
+// block moved back by one direction with the newest one in front -- for the 16-bit formats a 6-byte
+// shift of 600 bytes instead of re-reading 101 fp32 points and redoing 300 subtractions (each value
+// was rounded when it was the newest; copying it is the same as recomputing it).  A fresh streamline
+// (L == 1) has no directions.  n_dirs == 100, 304 columns.  FMT: TTL_OPERAND_*.
+template <int FMT>
+__device__ __forceinline__ void write_dirs_shifted(const uint8_t* __restrict__ old_dirs, uint8_t* __restrict__ out_dirs,
+                                                   int L, float3 tip, float3 prev_tip, int lane) {
   const uint4* o4 = reinterpret_cast<const uint4*>(old_dirs);
   uint4* d4 = reinterpret_cast<uint4*>(out_dirs);
   const float dxf = __fsub_rn(tip.x, prev_tip.x), dyf = __fsub_rn(tip.y, prev_tip.y),
               dzf = __fsub_rn(tip.z, prev_tip.z);
-  __nv_bfloat162 hxy = __floats2bfloat162_rn(dxf, dyf), hz0 = __floats2bfloat162_rn(dzf, 0.f);
-  const uint32_t w_xy = *reinterpret_cast<uint32_t*>(&hxy), w_z = *reinterpret_cast<uint32_t*>(&hz0);
+  if (FMT == TTL_OPERAND_TF32) {
+    // 304 fp32 words = 76 quads; out[j] = old[j - 3]
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+      const int q = lane + 32 * it;
+      if (q < 76) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (L > 1 && q < 75) {
+          const uint4 cur4 = __ldg(o4 + q);
+          if (q > 0) {
+            const uint4 prv4 = __ldg(o4 + q - 1);
+            o.x = prv4.y; o.y = prv4.z; o.z = prv4.w;
+          } else {
+            o.x = ttl_round_tf32(dxf); o.y = ttl_round_tf32(dyf); o.z = ttl_round_tf32(dzf);
+          }
+          o.w = cur4.x;
+        }
+        d4[q] = o;
+      }
+    }
+    return;
+  }
+  const uint32_t w_xy = ttl_pack16(dxf, dyf, FMT), w_z = ttl_pack16(dzf, 0.f, FMT);
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
     const int q = lane + 32 * it;
@@ -874,15 +815,19 @@ __device__ __forceinline__ void write_dirs_shifted(const __nv_bfloat16* __restri
   }
 }
 
-// bf16-only fast path (ttl_batch.bf16_layout == 1, no fp32 row): the state is produced straight
-// as the actor's first-layer operand.  Point p owns columns [48p, 48p+48) so every (point, chunk)
-// work item converts its float4 to 4 bf16 and stores 8 aligned bytes from registers; previous
-// directions follow at column 336.  No row staging: 512 B of shared memory per warp.
-__device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& prm, const float* P, int L, float3 tip,
-                                         __nv_bfloat16* __restrict__ out, int n_bf16, float* smem_f, int lane,
-                                         int pf = 0, const __nv_bfloat16* __restrict__ old_dirs = nullptr,
-                                         float3 prev_tip = make_float3(0.f, 0.f, 0.f)) {
+// Operand-only fast path (ttl_batch.bf16_layout == 1, no fp32 row): the state is produced straight
+// as the actor's first-layer operand in the element type FMT (bf16 / fp16: 2 bytes; tf32: fp32 words
+// rounded to tf32).  Point p owns columns [48p, 48p+48) so every (point, chunk) work item converts its
+// float4 and stores 8 (16) aligned bytes from registers; previous directions follow at column 336.
+// No row staging: 512 B of shared memory per warp.  `sat`: set when an fp16 value saturated.
+template <int FMT>
+__device__ void build_state_row_c45_op(const ttl_volume& v, const ttl_params& prm, const float* P, int L, float3 tip,
+                                       void* __restrict__ out_v, int n_op, float* smem_f, int lane, int pf = 0,
+                                       const uint8_t* __restrict__ old_dirs = nullptr,
+                                       float3 prev_tip = make_float3(0.f, 0.f, 0.f), int* sat = nullptr) {
   constexpr int CP = 48, CP4 = 12, S = 7 * CP;
+  constexpr int ES = FMT == TTL_OPERAND_TF32 ? 4 : 2;
+  uint8_t* out = static_cast<uint8_t*>(out_v);
   float* s_w = smem_f;
   int* s_vox = reinterpret_cast<int*>(smem_f + 64);
   corner_table(v, prm, tip, s_w, s_vox, lane);
@@ -921,19 +866,26 @@ __device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& 
     // the volume's padding channels are zero, so columns 45..47 of every point come out zero
     // (NaN weights excepted, and those columns meet zero weights in the actor anyway)
     if (lane + 32 * t < 7 * CP4) {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
-      *reinterpret_cast<uint2*>(out + p * CP + ck * 4) =
-          make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      uint8_t* d = out + (size_t)(p * CP + ck * 4) * ES;
+      if (FMT == TTL_OPERAND_TF32) {
+        *reinterpret_cast<uint4*>(d) = make_uint4(ttl_round_tf32(acc.x), ttl_round_tf32(acc.y),
+                                                  ttl_round_tf32(acc.z), ttl_round_tf32(acc.w));
+      } else {
+        if (FMT == TTL_OPERAND_FP16 && sat &&
+            fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w))) > 65504.f)
+          *sat = 1;
+        *reinterpret_cast<uint2*>(d) = make_uint2(ttl_pack16(acc.x, acc.y, FMT), ttl_pack16(acc.z, acc.w, FMT));
+      }
     }
   }
   // previous directions, newest first, zero padded (env.py:549-563)
   const int nd3 = prm.n_dirs * 3;
-  if (old_dirs != nullptr && nd3 == 300 && n_bf16 - S == 304) {
-    write_dirs_shifted(old_dirs, out + S, L, tip, prev_tip, lane);
+  if (old_dirs != nullptr && nd3 == 300 && n_op - S == 304) {
+    write_dirs_shifted<FMT>(old_dirs, out + (size_t)S * ES, L, tip, prev_tip, lane);
     return;
   }
   const float* last = P + (size_t)(L - 1) * 3;   // element j = last[c - 3k] - last[c - 3k - 3]
-  for (int j = 2 * lane; j < n_bf16 - S; j += 64) {
+  for (int j = 2 * lane; j < n_op - S; j += 64) {
     float val[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -942,182 +894,74 @@ __device__ void build_state_row_c45_bf16(const ttl_volume& v, const ttl_params& 
       val[e] = 0.f;
       if (jj < nd3 && k < L - 1) val[e] = __fsub_rn(__ldg(last + c - 3 * k), __ldg(last + c - 3 * k - 3));
     }
-    __nv_bfloat162 h = __floats2bfloat162_rn(val[0], val[1]);
-    *reinterpret_cast<__nv_bfloat162*>(out + S + j) = h;
+    if (FMT == TTL_OPERAND_TF32)
+      *reinterpret_cast<uint2*>(out + (size_t)(S + j) * 4) = make_uint2(ttl_round_tf32(val[0]), ttl_round_tf32(val[1]));
+    else
+      *reinterpret_cast<uint32_t*>(out + (size_t)(S + j) * 2) = ttl_pack16(val[0], val[1], FMT);
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// Device-mode row, deduplicated gather (ttl_state_options bit 4; off by default -- measured 74-86 us
-// against 60 us for the 56-corner kernel: it executes as many instructions (selects, 32 address
-// computations) at a third of the occupancy).  The 7-point neighbourhood (tip, tip +- r along each axis,
-// 0 < r < 1 voxel) touches at most 32 distinct voxels: the 2x2x2 cell of the tip plus one 2x2 face
-// beyond it in each of the six directions -- and only the faces a shifted point actually crosses
-// into (26 voxels on average).  The 56-corner formulation above asks L1 for 56 x 192 B
-// per row and leaves the deduplication to the cache: the state kernel ran at 73 % of the L1 data
-// pipe's wavefront rate.  Here lane l < 24 owns channels (2l, 2l+1): one LDG.64 per distinct voxel
-// per lane -- a warp reads a voxel's 192 bytes once, as two full wavefronts -- all 32 issued before
-// the first is used, then 7 x 8 FMAs per channel on registers in the same corner order as the
-// 56-corner path.  Which of the tip cell's neighbours a shifted point uses is a warp-uniform choice.
-//
-// Per axis: lo0 = saturated floor of the tip coordinate (the same float clamp as tri_axis), slots
-// s = 0..3 <-> lattice index clamp(lo0 - 1 + s); the tip uses slots (1, 2), the point shifted by -r
-// slots (1 - sm, 2 - sm), by +r slots (1 + sp, 2 + sp) with sm, sp in {0, 1}.  Anything else (r >= 1,
-// which no shipped configuration has) takes the 56-corner path.
-struct AxisSlots {
-  int idx[4];   // clamped lattice index of slots 0..3
-  int sm, sp;   // does the -r / +r point start one cell lower / higher than the tip
-};
-
-__device__ __forceinline__ int sat_floor(float c, int n) {
-  return (int)fminf(fmaxf(floorf(c), -1.f), (float)n);
-}
-
-__device__ __forceinline__ AxisSlots axis_slots(float t, float rad, int n) {
-  AxisSlots a;
-  const int lo0 = sat_floor(t, n);
-  a.sm = lo0 - sat_floor(__fadd_rn(t, -rad), n);
-  a.sp = sat_floor(__fadd_rn(t, rad), n) - lo0;
-#pragma unroll
-  for (int s = 0; s < 4; ++s) a.idx[s] = min(max(lo0 - 1 + s, 0), n - 1);
-  return a;
-}
-
-__device__ __forceinline__ float2 ldg_nc_v2(const float2* p) {
-  float2 r;
-  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  return r;
-}
-
-// acc = sum_k w[k] * val[k], k = 0..7, as an fmaf chain from zero (the order of the 56-corner path)
-__device__ __forceinline__ float2 tri8(const float* __restrict__ w, const float2 (&val)[8]) {
-  const float4 w0 = *reinterpret_cast<const float4*>(w), w1 = *reinterpret_cast<const float4*>(w + 4);
-  const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    acc.x = fmaf(wk[k], val[k].x, acc.x);
-    acc.y = fmaf(wk[k], val[k].y, acc.y);
-  }
-  return acc;
-}
-
-// returns false (nothing written) when the neighbourhood does not fit the 32-voxel footprint
-__device__ bool build_state_row_c45_bf16_dedup(const ttl_volume& v, const ttl_params& prm, int L, float3 tip,
-                                               __nv_bfloat16* __restrict__ out, float* smem_f, int lane,
-                                               const __nv_bfloat16* __restrict__ old_dirs, float3 prev_tip) {
-  constexpr int CP = 48, S = 7 * CP;
-  const float rad = (float)prm.step_vox;
-  const AxisSlots ax = axis_slots(tip.x, rad, v.X), ay = axis_slots(tip.y, rad, v.Y), az = axis_slots(tip.z, rad, v.Z);
-  if (((ax.sm | ax.sp | ay.sm | ay.sp | az.sm | az.sp) & ~1) != 0) return false;   // warp-uniform
-
-  // the 56 trilinear weights, one per lane (and lane + 32), through shared memory as before
-  float* s_w = smem_f;
-  int* s_vox = reinterpret_cast<int*>(smem_f + 64);
-  corner_table(v, prm, tip, s_w, s_vox, lane);
-
-  // voxel offsets (in float2 units of this lane's channel pair); all warp-uniform arithmetic
-  const int l2 = min(lane, 23);
-  const float2* base = reinterpret_cast<const float2*>(v.sh) + l2;
-  auto vox = [&](int xs, int ys, int zs) -> const float2* {
-    return base + (size_t)((ax.idx[xs] * v.Y + ay.idx[ys]) * v.Z + az.idx[zs]) * (CP / 2);
-  };
-  float2 C[8], XL[4], XH[4], YL[4], YH[4], ZL[4], ZH[4];
-  const float2 zero2 = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) C[k] = ldg_nc_v2(vox(1 + (k >> 2), 1 + ((k >> 1) & 1), 1 + (k & 1)));
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int a = 1 + (j >> 1), b = 1 + (j & 1);
-    XL[j] = ax.sm ? ldg_nc_v2(vox(0, a, b)) : zero2;
-    XH[j] = ax.sp ? ldg_nc_v2(vox(3, a, b)) : zero2;
-    YL[j] = ay.sm ? ldg_nc_v2(vox(a, 0, b)) : zero2;
-    YH[j] = ay.sp ? ldg_nc_v2(vox(a, 3, b)) : zero2;
-    ZL[j] = az.sm ? ldg_nc_v2(vox(a, b, 0)) : zero2;
-    ZH[j] = az.sp ? ldg_nc_v2(vox(a, b, 3)) : zero2;
-  }
-  // direction block while the gathers are in flight
-  write_dirs_shifted(old_dirs, out + S, L, tip, prev_tip, lane);
-  __syncwarp();   // s_w complete
-
-  float2 val[8];
-  float2 acc[7];
-  acc[0] = tri8(s_w, C);
-  // +x / -x: corner k = 4 cx + j, j = 2 cy + cz
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { val[j] = ax.sp ? C[4 + j] : C[j]; val[4 + j] = ax.sp ? XH[j] : C[4 + j]; }
-  acc[1] = tri8(s_w + 8, val);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { val[j] = ax.sm ? XL[j] : C[j]; val[4 + j] = ax.sm ? C[j] : C[4 + j]; }
-  acc[4] = tri8(s_w + 32, val);
-  // +y / -y: corner k = 4 cx + 2 cy + cz, face index j = 2 cx + cz
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k0 = 4 * (j >> 1) + (j & 1), k1 = k0 + 2;     // cy = 0 / cy = 1
-    val[k0] = ay.sp ? C[k1] : C[k0];
-    val[k1] = ay.sp ? YH[j] : C[k1];
-  }
-  acc[2] = tri8(s_w + 16, val);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k0 = 4 * (j >> 1) + (j & 1), k1 = k0 + 2;
-    val[k0] = ay.sm ? YL[j] : C[k0];
-    val[k1] = ay.sm ? C[k0] : C[k1];
-  }
-  acc[5] = tri8(s_w + 40, val);
-  // +z / -z: face index j = 2 cx + cy
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k0 = 2 * j, k1 = k0 + 1;                      // cz = 0 / cz = 1
-    val[k0] = az.sp ? C[k1] : C[k0];
-    val[k1] = az.sp ? ZH[j] : C[k1];
-  }
-  acc[3] = tri8(s_w + 24, val);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k0 = 2 * j, k1 = k0 + 1;
-    val[k0] = az.sm ? ZL[j] : C[k0];
-    val[k1] = az.sm ? C[k0] : C[k1];
-  }
-  acc[6] = tri8(s_w + 48, val);
-
-  // the volume's padding channels (45..47) are zero, so those columns come out zero
-  if (lane < 24) {
-#pragma unroll
-    for (int p = 0; p < 7; ++p) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(acc[p].x, acc[p].y);
-      *reinterpret_cast<__nv_bfloat162*>(out + p * CP + 2 * lane) = h;
-    }
-  }
-  return true;
 }
 
 // tip = P[L-1] (passed by value so a caller that already holds it skips the dependent load)
 __device__ __forceinline__ void build_state_row(const ttl_volume& v, const ttl_params& prm, const float* P,
                                                 int L, float3 tip, float* __restrict__ out_f32, int n_f32,
-                                                __nv_bfloat16* __restrict__ out_bf16, int n_bf16,
-                                                float* smem_f, int lane, int layout = 0) {
+                                                void* __restrict__ out_op, int n_op,
+                                                float* smem_f, int lane, int layout = 0, int fmt = 0) {
   if (layout == 1) {   // host guarantees C == 45, CP == 48, no fp32 row
-    build_state_row_c45_bf16(v, prm, P, L, tip, out_bf16, n_bf16, smem_f, lane);
+    if (fmt == TTL_OPERAND_TF32) build_state_row_c45_op<TTL_OPERAND_TF32>(v, prm, P, L, tip, out_op, n_op, smem_f, lane);
+    else if (fmt == TTL_OPERAND_FP16) build_state_row_c45_op<TTL_OPERAND_FP16>(v, prm, P, L, tip, out_op, n_op, smem_f, lane);
+    else build_state_row_c45_op<TTL_OPERAND_BF16>(v, prm, P, L, tip, out_op, n_op, smem_f, lane);
     return;
   }
-  if (v.C == 45 && v.CP == 48 && max(n_f32, n_bf16) <= kMaxStateLd)
-    build_state_row_c45(v, prm, P, L, tip, out_f32, n_f32, out_bf16, n_bf16, smem_f, lane);
+  uint16_t* o16 = static_cast<uint16_t*>(out_op);   // layout 0 carries a 16-bit copy only (check_layout)
+  if (v.C == 45 && v.CP == 48 && max(n_f32, n_op) <= kMaxStateLd)
+    build_state_row_c45(v, prm, P, L, tip, out_f32, n_f32, o16, n_op, smem_f, lane, fmt);
   else
-    build_state_row_generic(v, prm, P, L, tip, out_f32, n_f32, out_bf16, n_bf16, smem_f, lane);
+    build_state_row_generic(v, prm, P, L, tip, out_f32, n_f32, o16, n_op, smem_f, lane, fmt);
 }
 
-// rank r of the old alive list -> (number of survivors before r); all lanes return the value.
-__device__ __forceinline__ int survivors_before(const ttl_batch& b, int r, int n_old, int lane) {
+// Position bookkeeping of the state kernel, per warp, from what the stop kernels published:
+//   stops before rank r = sum of the super-group counters before r's super-group
+//                       + sum of the group counts of r's super-group before r's group
+//                       + stopped ranks of r's own group before r (ballot over the stop flags);
+//   total stops         = sum of all super-group counters.
+// A handful of independent loads per lane and two warp reductions; all lanes return the values.
+struct Compaction {
+  int keep_before;   // survivors among the ranks before r
+  int total_keep;    // survivors of the whole list
+};
+__device__ __forceinline__ Compaction survivors_before(const ttl_batch& b, int cur, int r, int n_old, int lane) {
   const int g = r / kGroup, base = g * kGroup, pos = r - base;      // kGroup == 32: one flag per lane
-  const bool counts = lane < pos && base + lane < n_old && b.stop[base + lane] == 0;
-  return b.grp_prefix[g] + __popc(__ballot_sync(0xffffffffu, counts));
+  const int sgr = g / kSuper;
+  const int n_groups = (n_old + kGroup - 1) / kGroup, n_super = (n_groups + kSuper - 1) / kSuper;
+  const int* sg = b.sg_stops + cur * super_count(b.max_groups);
+  int before = 0, total = 0;
+  for (int j = lane; j < n_super; j += 32) {
+    const int v = __ldcg(sg + j);
+    total += v;
+    before += j < sgr ? v : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < kSuper / 32; ++j) {
+    const int gg = sgr * kSuper + lane + 32 * j;
+    before += gg < g ? __ldcg(b.grp_stops + gg) : 0;
+  }
+  const bool stopped_before = lane < pos && base + lane < n_old && b.stop[base + lane] != 0;
+  before += stopped_before ? 1 : 0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    before += __shfl_xor_sync(0xffffffffu, before, off);
+    total += __shfl_xor_sync(0xffffffffu, total, off);
+  }
+  Compaction c;
+  c.keep_before = r - before;
+  c.total_keep = n_old - total;
+  return c;
 }
 
-// FAST = 1: the bf16-only device mode (ttl_batch.bf16_layout == 1) compiled on its own with a register
+// FAST = 1: the operand-only device mode (ttl_batch.bf16_layout == 1) compiled on its own with a register
 // budget (85) that lets one lane keep all 24 of its LDG.128 gathers in flight; in the general kernel
-// ptxas keeps 4 in flight to stay at 47 registers.
-template <int FAST, int MINB>
+// ptxas keeps 4 in flight to stay at 47 registers.  FMT: element type of the operand rows in that mode.
+template <int FAST, int MINB, int FMT>
 __global__ void __launch_bounds__(kStateWarps * 32, MINB) build_state_kernel(ttl_volume v, ttl_params prm,
                                                                                      ttl_batch b, int cur, int warp_smem,
                                                                                      int pf) {
@@ -1125,19 +969,41 @@ __global__ void __launch_bounds__(kStateWarps * 32, MINB) build_state_kernel(ttl
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* smem_f = reinterpret_cast<float*>(smem_dyn + (size_t)warp * warp_smem);
   const int r = blockIdx.x * kStateWarps + warp;
-  ttl_grid_dep_wait();     // propagate_stop / oracle_apply: flags, new points, compaction totals
+  ttl_grid_dep_wait();     // propagate_stop / oracle_apply: flags, new points, stop counts
   // Release the dependent (the actor's first layer) now: once the last wave of this grid is running,
   // its CTAs take over SMs as they drain and set up barriers / tensor memory / descriptors there.
   // Measured on B200 (50 000 rows): 316 -> 312 us per step.  The same early release in the dense
   // kernels and in propagate_stop was measured slower (up to +38 us with all of them on), so those
   // release at exit.
   if (pf & 4) ttl_grid_dep_launch();
-  const int n_old = b.ctrl[3];
+  const int n_old = b.ctrl[cur];
+  const int cursor = b.ctrl[12 + cur];
+  // independent loads first: stop counts / flags (rank), this rank's record and new point
+  const int r_ld = min(r, max(n_old - 1, 0));
+  const RankRec rec = read_rank_rec(b.rank_rec[cur], r_ld);
+  const float4 q = __ldg(reinterpret_cast<const float4*>(b.step_tip) + r_ld);
+  const Compaction cp = survivors_before(b, cur, r_ld, n_old, lane);
+  const int total_keep = cp.total_keep;
+  const int n_new = prm.refill ? max(0, min(b.n_slots - total_keep, b.n - cursor)) : 0;
+  if (r == 0 && lane == 0) {
+    // one thread of the grid advances the control block (what the reference's harvest() does on the
+    // host, tracking_env.py:223-245).  Every value it overwrites is either unused by this kernel or
+    // read by it from the other ping-pong slot.
+    b.ctrl[cur ^ 1] = total_keep + n_new;   // alive count of the next list
+    b.ctrl[2] = b.ctrl[2] + 1;
+    b.ctrl[3] = n_old;
+    b.ctrl[6] = cursor + n_new;
+    b.ctrl[12 + (cur ^ 1)] = cursor + n_new;
+    b.ctrl[8] = total_keep;
+    b.ctrl[9] = n_new;
+    b.ctrl[10] = cursor;
+    long long* total = reinterpret_cast<long long*>(b.ctrl + 4);
+    *total += n_old;
+    int* sg_next = b.sg_stops + (cur ^ 1) * super_count(b.max_groups);
+    for (int j = 0; j < super_count(b.max_groups); ++j) sg_next[j] = 0;
+  }
   if (r >= n_old) return;
-  // independent loads first: stop flags / group prefix (rank), this rank's record and new point
-  const RankRec rec = read_rank_rec(b.rank_rec[cur], r);
-  const float4 q = __ldg(reinterpret_cast<const float4*>(b.step_tip) + r);
-  const int keep_before = survivors_before(b, r, n_old, lane);
+  const int keep_before = cp.keep_before;
   const bool stopped = b.stop[r] != 0;
   int row, dst, L;
   float3 tip = make_float3(q.x, q.y, q.z);
@@ -1151,12 +1017,11 @@ __global__ void __launch_bounds__(kStateWarps * 32, MINB) build_state_kernel(ttl
       write_rank_rec(b.rank_rec[cur ^ 1], dst, row, L, q.x, q.y, q.z, rec.tx, rec.ty, rec.tz);
     }
   } else {
-    const int total_keep = b.ctrl[8];
     const int j = r - keep_before;        // how many stopped before this rank
     dst = total_keep + j;
     if (lane == 0) b.dest[r] = dst;
-    if (j < b.ctrl[9]) {                  // streaming refill: this freed slot takes a fresh seed
-      row = b.order ? b.order[b.ctrl[10] + j] : b.ctrl[10] + j;
+    if (j < n_new) {                      // streaming refill: this freed slot takes a fresh seed
+      row = b.order ? b.order[cursor + j] : cursor + j;
       L = 1;
       const float* S = b.points + (size_t)row * b.max_pts * 3;
       tip = make_float3(S[0], S[1], S[2]);
@@ -1172,22 +1037,21 @@ __global__ void __launch_bounds__(kStateWarps * 32, MINB) build_state_kernel(ttl
     }
   }
   const float* P = b.points + (size_t)row * b.max_pts * 3;
-  __nv_bfloat16* o16 = b.state_bf16[cur ^ 1]
-                           ? reinterpret_cast<__nv_bfloat16*>(b.state_bf16[cur ^ 1]) + (size_t)dst * b.ld_bf16
-                           : nullptr;
+  uint8_t* op_next = static_cast<uint8_t*>(b.state_bf16[cur ^ 1]);
+  const int op_es = b.operand_fmt == TTL_OPERAND_TF32 ? 4 : 2;
+  void* o16 = op_next ? op_next + (size_t)dst * b.ld_bf16 * op_es : nullptr;
   float* o32 = b.state[cur ^ 1] ? b.state[cur ^ 1] + (size_t)dst * b.ld_state : nullptr;
   if (FAST) {
     // survivors (and, in parity mode, rows that just stopped) extend the direction block of the row
     // the actor has just read; a refilled slot starts from zeros (L == 1)
-    const __nv_bfloat16* old_dirs =
-        reinterpret_cast<const __nv_bfloat16*>(b.state_bf16[cur]) + (size_t)r * b.ld_bf16 + 7 * 48;
+    const uint8_t* old_dirs = static_cast<const uint8_t*>(b.state_bf16[cur]) +
+                              ((size_t)r * b.ld_bf16 + 7 * 48) * (FMT == TTL_OPERAND_TF32 ? 4 : 2);
     const float3 prev_tip = make_float3(rec.tx, rec.ty, rec.tz);
-    if (FAST >= 2 && build_state_row_c45_bf16_dedup(v, prm, L, tip, o16, smem_f, lane, old_dirs, prev_tip)) return;
-    build_state_row_c45_bf16(v, prm, P, L, tip, o16, b.ld_bf16, smem_f, lane, pf, (pf & 8) ? nullptr : old_dirs,
-                             prev_tip);
+    build_state_row_c45_op<FMT>(v, prm, P, L, tip, o16, b.ld_bf16, smem_f, lane, pf, (pf & 8) ? nullptr : old_dirs,
+                                prev_tip, b.ctrl + 14);
   }
   else
-    build_state_row(v, prm, P, L, tip, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout);
+    build_state_row(v, prm, P, L, tip, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout, b.operand_fmt);
 }
 
 // reset: alive[0] = identity, state goes to state[0]
@@ -1200,12 +1064,11 @@ __global__ void __launch_bounds__(kStateWarps * 32) reset_state_kernel(ttl_volum
   if (r >= min(b.n, b.n_slots)) return;
   const int row = b.order ? b.order[r] : r;
   const float* P = b.points + (size_t)row * b.max_pts * 3;
-  __nv_bfloat16* o16 = b.state_bf16[0]
-                           ? reinterpret_cast<__nv_bfloat16*>(b.state_bf16[0]) + (size_t)r * b.ld_bf16
-                           : nullptr;
+  const int op_es = b.operand_fmt == TTL_OPERAND_TF32 ? 4 : 2;
+  void* o16 = b.state_bf16[0] ? static_cast<uint8_t*>(b.state_bf16[0]) + (size_t)r * b.ld_bf16 * op_es : nullptr;
   float* o32 = b.state[0] ? b.state[0] + (size_t)r * b.ld_state : nullptr;
   build_state_row(v, prm, P, 1, make_float3(P[0], P[1], P[2]), o32, b.ld_state, o16, b.ld_bf16, smem_f, lane,
-                  b.bf16_layout);
+                  b.bf16_layout, b.operand_fmt);
 }
 
 // stand-alone _format_state for arbitrary streamlines [n][L][3]
@@ -1306,15 +1169,13 @@ constexpr int kStateSmem = kStateWarps * kWarpSmemBytes;
 int state_kernels_ready() {
   static bool done = false;
   if (done) return 0;
-  cudaError_t e = cudaFuncSetAttribute(build_state_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+  cudaError_t e = cudaFuncSetAttribute(build_state_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(build_state_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+    e = cudaFuncSetAttribute(build_state_kernel<1, 6, TTL_OPERAND_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(build_state_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+    e = cudaFuncSetAttribute(build_state_kernel<1, 6, TTL_OPERAND_FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(build_state_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(build_state_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
+    e = cudaFuncSetAttribute(build_state_kernel<1, 6, TTL_OPERAND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(reset_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
@@ -1333,18 +1194,26 @@ int check_common(const ttl_volume* vol, const ttl_params* prm) {
 }
 
 // bf16_layout 1 needs the order-8 volume and room for 7*48 + 3*n_dirs columns; without fp32 rows
-// the bf16 rows must exist
+// the operand rows must exist.  Layout 0 (fp32 rows + a 16-bit copy) has no tf32 operand: a tf32 actor
+// packs from the fp32 rows itself.
 int check_layout(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b) {
-  if (!b->rank_rec[0] || !b->rank_rec[1] || !b->step_tip) return TTL_ERR_BAD_ARG;
+  if (!b->rank_rec[0] || !b->rank_rec[1] || !b->step_tip || !b->sg_stops || !b->grp_stops) return TTL_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(b->rank_rec[0]) | reinterpret_cast<uintptr_t>(b->rank_rec[1]) |
        reinterpret_cast<uintptr_t>(b->step_tip)) & 15)
     return TTL_ERR_BAD_ARG;
-  if (b->bf16_layout == 0) return (b->state[0] && b->state[1]) ? 0 : TTL_ERR_BAD_ARG;
+  if (b->operand_fmt != TTL_OPERAND_BF16 && b->operand_fmt != TTL_OPERAND_FP16 && b->operand_fmt != TTL_OPERAND_TF32)
+    return TTL_ERR_BAD_ARG;
+  if (b->bf16_layout == 0) {
+    if (b->operand_fmt == TTL_OPERAND_TF32) return TTL_ERR_UNSUPPORTED;
+    return (b->state[0] && b->state[1]) ? 0 : TTL_ERR_BAD_ARG;
+  }
   if (b->bf16_layout != 1) return TTL_ERR_BAD_ARG;
   if (vol->C != 45 || vol->CP != 48) return TTL_ERR_UNSUPPORTED;
   if (!b->state_bf16[0] || !b->state_bf16[1] || (b->ld_bf16 & 7)) return TTL_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(b->state_bf16[0]) | reinterpret_cast<uintptr_t>(b->state_bf16[1])) & 15)
+    return TTL_ERR_BAD_ARG;
   if (7 * 48 + 3 * prm->n_dirs > b->ld_bf16) return TTL_ERR_UNSUPPORTED;
-  if (b->state[0] || b->state[1]) return TTL_ERR_BAD_ARG;   // layout 1 is the bf16-only mode
+  if (b->state[0] || b->state[1]) return TTL_ERR_BAD_ARG;   // layout 1 is the operand-only mode
   return 0;
 }
 
@@ -1425,51 +1294,45 @@ static void launch_propagate(const ttl_volume* vol, const ttl_params* prm, const
 
 // A/B knobs of the state kernel (TTL_STATE_OPTIONS or ttl_state_options()): bits 0-1 prefetch the
 // row's lines into L1 (1) / L2 (2) ahead of the gathers, bit 3 recompute the direction block from the
-// fp32 points instead of shifting the previous row's, bit 4 the deduplicated 32-voxel gather instead
-// of the 56-corner one (bits 5-6: its CTAs per SM, 2/3/4).  Default 0: every alternative was
-// measured slower or equal.
+// fp32 points instead of shifting the previous row's.  Default 0: every alternative was measured
+// slower or equal.
 static std::atomic<int> g_state_opts{-1};
 static int state_prefetch_level() {
   int v = g_state_opts.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("TTL_STATE_OPTIONS");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 127) v = 0;
+    if (v < 0 || v > 15) v = 0;
     g_state_opts.store(v);
   }
-  return v;
+  return v & 11;
 }
 
 static int launch_build_state(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int cur,
                               int n_upper, cudaStream_t s) {
   int rc = state_kernels_ready();
   if (rc) return rc;
-  // the bf16-only path keeps just the corner table in shared memory: a small allocation leaves
+  // the operand-only path keeps just the corner table in shared memory: a small allocation leaves
   // the SM's 228 KB to L1, which is what dedupes the overlapping trilinear corners
   const int warp_smem = b->bf16_layout == 1 ? kWarpSmemSmall : kWarpSmemBytes;
-  const bool dedup = b->bf16_layout == 1 && prm->n_dirs == 100 && b->ld_bf16 == 640 && prm->step_vox > 0.0 &&
-                     prm->step_vox < 1.0 && (state_prefetch_level() & 16);
-  const int occ = (state_prefetch_level() >> 5) & 3;
-  if (dedup && occ == 0)
+  const int grid = ttl_div_up(n_upper, kStateWarps), smem = kStateWarps * warp_smem;
+  const int pf = state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0);
+  if (b->bf16_layout == 1 && b->operand_fmt == TTL_OPERAND_TF32)
     TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<2, 2>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
-                                kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0)));
-  else if (dedup && occ == 1)
+               ttl_launch_chain(build_state_kernel<1, 6, TTL_OPERAND_TF32>, grid, kStateWarps * 32, smem, s, *vol, *prm,
+                                *b, cur, warp_smem, pf));
+  else if (b->bf16_layout == 1 && b->operand_fmt == TTL_OPERAND_FP16)
     TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<2, 3>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
-                                kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0)));
-  else if (dedup)
-    TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<2, 4>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
-                                kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0)));
+               ttl_launch_chain(build_state_kernel<1, 6, TTL_OPERAND_FP16>, grid, kStateWarps * 32, smem, s, *vol, *prm,
+                                *b, cur, warp_smem, pf));
   else if (b->bf16_layout == 1)
     TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<1, 6>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
-                                kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0)));
+               ttl_launch_chain(build_state_kernel<1, 6, TTL_OPERAND_BF16>, grid, kStateWarps * 32, smem, s, *vol, *prm,
+                                *b, cur, warp_smem, pf));
   else
     TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<0, 1>, ttl_div_up(n_upper, kStateWarps), kStateWarps * 32,
-                                kStateWarps * warp_smem, s, *vol, *prm, *b, cur, warp_smem, (g_ttl_pdl.load() == 1 ? 4 : 0)));
+               ttl_launch_chain(build_state_kernel<0, 1, 0>, grid, kStateWarps * 32, smem, s, *vol, *prm, *b, cur,
+                                warp_smem, (g_ttl_pdl.load() == 1 ? 4 : 0)));
   return 0;
 }
 
@@ -1483,13 +1346,13 @@ static int check_step_args(const ttl_volume* vol, const ttl_params* prm, const t
   rc = check_layout(vol, prm, b);
   if (rc) return rc;
   if (*n_upper > b->n_slots) *n_upper = b->n_slots;
-  if (*n_upper > 0 && (ttl_div_up(*n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->grp_prefix ||
+  if (*n_upper > 0 && (ttl_div_up(*n_upper, kGroup) > b->max_groups || !b->grp_stops || !b->sg_stops ||
                        !b->rank_rec[0] || !b->rank_rec[1] || !b->step_tip))
     return TTL_ERR_BAD_ARG;
   return 0;
 }
 
-void ttl_state_options(int32_t bits) { g_state_opts.store(bits & 127); }
+void ttl_state_options(int32_t bits) { g_state_opts.store(bits & 15); }
 
 int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
                  const float* actions, int32_t lda, const double* noise, int32_t n_upper,
@@ -1499,7 +1362,7 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
   int rc = check_step_args(vol, prm, b, cur, &n_upper);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  const ActionSrc src = {actions, lda, nullptr, 0, nullptr, n_upper};
+  const ActionSrc src = {actions, lda, nullptr, 0, 1, nullptr, n_upper};
   launch_propagate(vol, prm, b, cur, src, noise, 0, n_upper, s);
   rc = launch_build_state(vol, prm, b, cur, n_upper, s);
   if (rc) return rc;
@@ -1508,15 +1371,16 @@ int ttl_env_step(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* 
 }
 
 int ttl_env_step_head(const ttl_volume* vol, const ttl_params* prm, const ttl_batch* b, int32_t cur,
-                      const float* head_partial, int32_t n_tiles, const float* head_bias,
+                      const float* head_partial, int32_t n_tiles, int32_t tiles_per_256, const float* head_bias,
                       int32_t n_upper, void* stream) {
   if (n_upper <= 0) return 0;
-  if (!head_partial || !head_bias || n_tiles < 1 || (reinterpret_cast<uintptr_t>(head_partial) & 15))
+  if (!head_partial || !head_bias || n_tiles < 1 || (reinterpret_cast<uintptr_t>(head_partial) & 15) ||
+      (tiles_per_256 != 1 && tiles_per_256 != 2 && tiles_per_256 != 4))
     return TTL_ERR_BAD_ARG;
   int rc = check_step_args(vol, prm, b, cur, &n_upper);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  const ActionSrc src = {nullptr, 0, head_partial, n_tiles, head_bias, n_upper};
+  const ActionSrc src = {nullptr, 0, head_partial, n_tiles, tiles_per_256, head_bias, n_upper};
   launch_propagate(vol, prm, b, cur, src, nullptr, 0, n_upper, s);
   rc = launch_build_state(vol, prm, b, cur, n_upper, s);
   if (rc) return rc;
@@ -1532,7 +1396,7 @@ int ttl_env_step_begin(const ttl_volume* vol, const ttl_params* prm, const ttl_b
   int rc = check_step_args(vol, prm, b, cur, &n_upper);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  const ActionSrc src = {actions, lda, nullptr, 0, nullptr, n_upper};
+  const ActionSrc src = {actions, lda, nullptr, 0, 1, nullptr, n_upper};
   launch_propagate(vol, prm, b, cur, src, noise, 1, n_upper, s);
   TTL_CHECK_LAST();
   return 0;

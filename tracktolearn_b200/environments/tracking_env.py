@@ -30,8 +30,14 @@ class _BatchBuffers(object):
     ``rows``: seeds held by the batch (one streamline buffer row each); ``slots``: streamlines
     tracked at once (== rows unless the streaming tracker refills freed slots)."""
 
-    def __init__(self, rows, slots, max_pts, state_size, device, fp32_state=True):
+    def __init__(self, rows, slots, max_pts, state_size, device, fp32_state=True, operand='bf16'):
         self.fp32_state = fp32_state
+        self.operand = operand          # element type of the actor operand rows: 'bf16' / 'fp16' / 'tf32'
+        if operand not in _lib.OPERAND_OF_PRECISION:
+            raise ValueError('operand rows come in bf16, fp16 or tf32, not %r' % (operand,))
+        if fp32_state and operand == 'tf32':
+            raise ValueError('tf32 operand rows exist in the operand-only mode; with fp32 state rows a tf32 '
+                             'actor packs its operand from them')
         self.rows = rows
         self.slots = slots
         self.max_pts = max_pts
@@ -56,13 +62,15 @@ class _BatchBuffers(object):
                        torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device)]
                       if fp32_state else [None, None])
         self.ctrl_host = torch.zeros((16,), dtype=torch.int32).pin_memory()
-        # bf16 copy of the state rows, zero padded to a multiple of 64: the actor's TMA operand
+        # copy of the state rows in the actor's operand type, zero padded to a multiple of 64 columns:
+        # the actor's TMA operand
         self.ld_bf16 = (state_size + 63) // 64 * 64
-        self.state_bf16 = [torch.zeros((slots, self.ld_bf16), dtype=torch.bfloat16, device=device),
-                           torch.zeros((slots, self.ld_bf16), dtype=torch.bfloat16, device=device)]
+        op_dtype = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'tf32': torch.float32}[operand]
+        self.state_bf16 = [torch.zeros((slots, self.ld_bf16), dtype=op_dtype, device=device),
+                           torch.zeros((slots, self.ld_bf16), dtype=op_dtype, device=device)]
         self.max_groups = (slots + 31) // 32 + 1
         self.grp_stops = torch.zeros((self.max_groups,), **i32)
-        self.grp_prefix = torch.zeros((self.max_groups,), **i32)
+        self.sg_stops = torch.zeros((2 * ((self.max_groups + 63) // 64),), **i32)
         # per-rank records {row, npts, tip, previous point} of the two alive lists and the points added
         # by the step in flight (ttl_batch.rank_rec / step_tip)
         self.rank_rec = [torch.zeros((pad, 8), dtype=torch.float32, device=device),
@@ -78,7 +86,8 @@ class _BatchBuffers(object):
                        stop=self.stop.data_ptr(), dest=self.dest.data_ptr(),
                        step_flags=self.step_flags.data_ptr(), reward=self.reward.data_ptr(),
                        ld_bf16=self.ld_bf16, max_groups=self.max_groups,
-                       grp_stops=self.grp_stops.data_ptr(), grp_prefix=self.grp_prefix.data_ptr())
+                       grp_stops=self.grp_stops.data_ptr(), sg_stops=self.sg_stops.data_ptr(),
+                       operand_fmt=_lib.OPERAND_OF_PRECISION[self.operand])
         b.state_bf16[0] = self.state_bf16[0].data_ptr()
         b.state_bf16[1] = self.state_bf16[1].data_ptr()
         b.rank_rec[0] = self.rank_rec[0].data_ptr()
@@ -97,32 +106,36 @@ class TrackingEnvironment(BaseEnv):
     """Reference: environments/tracking_env.py:13."""
 
     # ------------------------------------------------------------------------------ reset
-    def _ensure_buffers(self, rows, slots, fp32_state=True):
+    def _ensure_buffers(self, rows, slots, fp32_state=True, operand='bf16'):
         need_pts = self.max_nb_steps + 1
         S = self.get_state_size()
         bb = self._batch
         if (bb is None or bb.rows < rows or bb.slots < slots or bb.max_pts != need_pts
-                or bb.state_size != S or bb.fp32_state != fp32_state):
+                or bb.state_size != S or bb.fp32_state != fp32_state or bb.operand != operand):
             rows = max(rows, bb.rows if bb is not None else 0)
             slots = max(slots, bb.slots if bb is not None else 0)
             self._batch = None
-            bb = _BatchBuffers(rows, slots, need_pts, S, self.device, fp32_state)
+            bb = _BatchBuffers(rows, slots, need_pts, S, self.device, fp32_state, operand)
             self._batch = bb
         return bb
 
-    def _start(self, initial_points, n_slots=None, fp32_state=True, locality=False):
+    def _start(self, initial_points, n_slots=None, fp32_state=True, locality=False, operand=None):
         """``n_slots`` < N turns on the streaming tracker: only n_slots streamlines are alive
         at once and slots freed by stopped ones take the next seeds in the same step.
-        ``fp32_state=False``: only the bf16 actor operand is produced (no fp32 state tensor).
+        ``fp32_state=False``: only the actor's operand rows are produced (no fp32 state tensor), in the
+        element type ``operand`` ('bf16', 'fp16' or 'tf32'; default: the env's ``operand`` attribute).
         ``locality``: seeds take slots in voxel raster order instead of row order (ttl_batch.order);
         rows, results and the output order are unchanged."""
         if not fp32_state and (self._n_coefs != 45 or 7 * 48 + 3 * self.n_dirs > (self.get_state_size() + 63) // 64 * 64):
-            fp32_state = True      # the bf16-only layout is specialised for the order-8 volume
+            fp32_state = True      # the operand-only layout is specialised for the order-8 volume
+        operand = operand or getattr(self, 'operand', 'bf16')
+        if fp32_state and operand == 'tf32':
+            operand = 'bf16'       # unused copy: a tf32 actor packs from the fp32 rows
         self.initial_points = initial_points
         N = initial_points.shape[0]
         streaming = n_slots is not None and n_slots < N
         slots = n_slots if streaming else max(N, 1)
-        bb = self._ensure_buffers(max(N, 1), slots, fp32_state)
+        bb = self._ensure_buffers(max(N, 1), slots, fp32_state, operand)
         self._n = N
         self._b = bb.as_struct(N, slots)
         self._params.refill = int(streaming)
@@ -158,7 +171,7 @@ class TrackingEnvironment(BaseEnv):
         """Reference: tracking_env.py:91-133."""
         return self._start(self.seeds[start:end])
 
-    def reset_streaming(self, start, end, n_slots, fp32_state=True, locality=True):
+    def reset_streaming(self, start, end, n_slots, fp32_state=True, locality=True, operand=None):
         """Like ``reset`` but at most ``n_slots`` streamlines are tracked at once; the others
         wait in the batch and take over slots as streamlines stop (device-side refill).
         With ``fp32_state=False`` the fp32 state tensor is not materialised: the step kernel
@@ -168,7 +181,7 @@ class TrackingEnvironment(BaseEnv):
         gathers share cache lines (the reference shuffles the seeds, tracker.py:94; the rows -- and
         with them every per-seed result and the output order -- stay in the shuffled order)."""
         return self._start(self.seeds[start:end], n_slots=n_slots, fp32_state=fp32_state,
-                           locality=locality and os.environ.get('TTL_LOCALITY', '1') != '0')
+                           locality=locality and os.environ.get('TTL_LOCALITY', '1') != '0', operand=operand)
 
     def nreset(self, n_seeds):
         """Reference: tracking_env.py:47-89."""
@@ -223,11 +236,11 @@ class TrackingEnvironment(BaseEnv):
             raise RuntimeError('step() called twice without harvest()')
         if self._oracle is not None:
             raise RuntimeError('step_device_head does not consult the oracle; use step_device')
-        partial, n_tiles, bias = head
+        partial, n_tiles, tiles_per_256, bias = head
         _lib.check(self._lib.ttl_env_step_head(
             ctypes.byref(self._volume), ctypes.byref(self._params), ctypes.byref(self._b), self._cur,
-            partial, int(n_tiles), bias, int(self._n_alive_host), _lib.stream_ptr(self.device)),
-            'ttl_env_step_head')
+            partial, int(n_tiles), int(tiles_per_256), bias, int(self._n_alive_host),
+            _lib.stream_ptr(self.device)), 'ttl_env_step_head')
         self.length += 1
         self._pending_harvest = True
 
@@ -270,9 +283,20 @@ class TrackingEnvironment(BaseEnv):
         return (0 if self._batch.fp32_state else 1, self._n_coefs, self._volume.CP, 7)
 
     def current_state_bf16(self):
-        """bf16, zero-padded copy of ``current_state()`` ([slots, round_up(state_size, 64)]) that
-        the step kernel writes alongside the fp32 rows; the actor's first layer reads it by TMA."""
+        """Zero-padded copy of ``current_state()`` in the actor's operand type
+        ([slots, round_up(state_size, 64)], dtype bf16 / fp16 / fp32-holding-tf32, see ``operand_format``)
+        that the step kernel writes alongside (or instead of) the fp32 rows; the actor's first layer
+        reads it by TMA."""
         return self._batch.state_bf16[self._cur]
+
+    @property
+    def operand_format(self):
+        return self._batch.operand
+
+    def operand_saturated(self):
+        """True when an fp16 operand row had to saturate a state value (|x| > 65504) since reset
+        (valid after ``n_alive()``)."""
+        return bool(int(self._batch.ctrl_host[14]))
 
     def alive_count_tensor(self):
         """Device int32 tensor holding the alive count of the current list."""

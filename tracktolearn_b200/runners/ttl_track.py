@@ -61,7 +61,7 @@ class TrackToLearnTrack(object):
         self.fa_map = None      # the reference looks up the wrong key here: never set
         self.agent = track_dto['agent']
         self.hyperparameters = track_dto['hyperparameters']
-        self.precision = track_dto.get('precision', 'bf16')
+        self.precision = track_dto.get('precision', 'fp16')
         with open(self.hyperparameters, 'r') as json_file:
             hyperparams = json.load(json_file)
             self.algorithm = hyperparams['algorithm']
@@ -160,9 +160,11 @@ def add_track_args(parser):
                                       DEFAULT_MODEL))
     agent_group.add_argument('--n_actor', type=int, default=10000, metavar='N',
                              help='Number of streamlines to track simultaneously.\n[%(default)s]')
-    agent_group.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
-                             help='Actor arithmetic: bf16 tensor cores (tcgen05) or fp32 CUDA cores. '
-                                  '[%(default)s]')
+    agent_group.add_argument('--precision', default='fp16', choices=['fp16', 'tf32', 'bf16', 'fp32'],
+                             help='Actor arithmetic.  fp16 / tf32: tcgen05 tensor cores, outputs within 1e-3 of the '
+                                  'fp32 reference (fp16 at full rate within +-65504 -- tracking aborts with a '
+                                  'message if a value saturates; tf32 at half rate with fp32 range); bf16: tensor '
+                                  'cores, ~4e-3; fp32: CUDA cores, the reference arithmetic. [%(default)s]')
     seed_group = parser.add_argument_group('Seeding options')
     seed_group.add_argument('--npv', type=int, default=1, help='Number of seeds per voxel [%(default)s].')
     track_g = parser.add_argument_group('Tracking options')

@@ -58,6 +58,17 @@ class Tracker(object):
         for start in range(0, n_seeds, rows):
             yield start, min(start + rows, n_seeds), self.n_actor
 
+    def _check_range(self, env):
+        """The fp16 tier saturates values outside +-65504 instead of producing infinities; a tractogram
+        computed from saturated numbers would be silently wrong, so stop and say what to do."""
+        actor = self.alg.agent.actor
+        if getattr(actor, 'precision', None) != 'fp16':
+            return
+        if actor.overflowed() or env.operand_saturated():
+            from tracktolearn_b200 import _lib
+            raise _lib.TTLError('a state or activation value exceeded the fp16 range (65504) during tracking; '
+                                're-run with precision="tf32" (--precision tf32)')
+
     def track_packed(self, env, copy=True):
         """Yields a Tractogram with voxel-space packed streamlines (+ seeds, flags) per pass;
         no length filter, no space change.  ``copy=False``: each batch aliases the env's pinned
@@ -67,10 +78,13 @@ class Tracker(object):
             if slots is None or slots >= end - start:
                 state = env.reset(start, end)
             else:
-                # the bf16 actor reads the bf16 rows only: do not materialise the fp32 state
-                bf16_actor = getattr(self.alg.agent.actor, 'precision', 'fp32') == 'bf16'
-                state = env.reset_streaming(start, end, slots, fp32_state=not bf16_actor)
+                # a tensor-core actor reads its operand rows only: do not materialise the fp32 state
+                prec = getattr(self.alg.agent.actor, 'precision', 'fp32')
+                tc_actor = prec in ('bf16', 'fp16', 'tf32')
+                state = env.reset_streaming(start, end, slots, fp32_state=not tc_actor,
+                                            operand=prec if tc_actor else None)
             self.alg.validation_episode(state, env, self.prob)
+            self._check_range(env)
             yield env.get_streamlines(copy=copy)
 
     def track(self, env, tracts_format='trk'):
@@ -154,9 +168,12 @@ class Tracker(object):
                     if slots is None or slots >= end - start:
                         state = env.reset(start, end)
                     else:
-                        bf16_actor = getattr(self.alg.agent.actor, 'precision', 'fp32') == 'bf16'
-                        state = env.reset_streaming(start, end, slots, fp32_state=not bf16_actor)
+                        prec = getattr(self.alg.agent.actor, 'precision', 'fp32')
+                        tc_actor = prec in ('bf16', 'fp16', 'tf32')
+                        state = env.reset_streaming(start, end, slots, fp32_state=not tc_actor,
+                                                    operand=prec if tc_actor else None)
                     self.alg.validation_episode(state, env, self.prob)
+                    self._check_range(env)
                     pts, offsets = env.get_streamlines_device()
                     lens = lengths_packed(pts, offsets)
                     keep = (lens >= lo) & (lens <= hi)
