@@ -127,3 +127,29 @@ def test_tracker_compress_option():
         shorter += len(b.streamline) < len(a.streamline)
     assert shorter > len(plain) // 2
     assert torch.cuda.is_available()
+
+
+@pytest.mark.gpu
+def test_tracker_compress_tolerance_is_in_mm():
+    """`--compress` is given in mm; the streamlines are compressed in voxel space with
+    compress / voxel_size (reference tracking/tracker.py:103,123-125).  On a 2 mm volume a 0.05 mm
+    tolerance is 0.025 voxels."""
+    from tests.test_tracker_gpu import _setup
+    from tracktolearn_b200.tracking.tracker import Tracker
+    env, alg, sub, seeds, sd = _setup(precision='fp16', vox=2.0)
+    assert abs(np.mean(np.abs(np.diag(env.affine_vox2rasmm))[:3]) - 2.0) < 1e-12
+    seeds0 = np.array(seeds)
+    env.seeds = seeds0.copy()
+    np.random.seed(0)
+    plain = list(Tracker(alg, 256, min_length=5, max_length=200).track(env, 'tck'))
+    env.seeds = seeds0.copy()
+    np.random.seed(0)
+    comp = list(Tracker(alg, 256, compress=0.05, min_length=5, max_length=200).track(env, 'tck'))
+    assert len(plain) == len(comp) > 50
+    differs_from_unscaled = 0
+    for a, b in zip(plain, comp):
+        vox = (a.streamline / 2.0).astype(np.float32)            # tck space = 2 * voxel space, exactly
+        want = O.compress_streamline(vox, 0.05 / 2.0).astype(np.float64) * 2.0
+        np.testing.assert_allclose(b.streamline, want, rtol=0, atol=1e-6)
+        differs_from_unscaled += len(O.compress_streamline(vox, 0.05)) != len(want)
+    assert differs_from_unscaled > 0        # the unscaled tolerance would have kept fewer points

@@ -20,7 +20,7 @@ def _round_like_operand(x, prec):
     return t.to(OP_DTYPE[prec]).float().numpy()
 
 
-def _setup(shape=(32, 36, 30), n_seeds=900, precision='fp32'):
+def _setup(shape=(32, 36, 30), n_seeds=900, precision='fp32', vox=1.0):
     from tests.gpu_helpers import make_gpu_env
     from tracktolearn_b200.algorithms.sac_auto import SACAuto
     sub = {k: (v.numpy() if v is not None else None) for k, v in synthetic.make_subject(shape, seed=11).items()}
@@ -28,7 +28,7 @@ def _setup(shape=(32, 36, 30), n_seeds=900, precision='fp32'):
     seeds = synthetic.seeds_from_mask(synthetic.ellipsoid_mask(shape, frac=0.36).numpy(), 1, rs)
     rs.shuffle(seeds)
     seeds = seeds[:n_seeds]
-    g = {'meta_shape': np.asarray(shape), 'meta': np.asarray([1.0, 0.75, 30.0, 30.0, 0.1, 40.0, 0.75])}
+    g = {'meta_shape': np.asarray(shape), 'meta': np.asarray([vox, 0.75 * vox, 30.0, 30.0 * vox, 0.1, 40.0, 0.75])}
     env, _ = make_gpu_env(g, True, False, sub=sub, seeds=seeds)
     sd = synthetic.actor_state_dict(615, '128-128-128', seed=5, kind='tracking')
     alg = SACAuto(615, 3, '128-128-128', n_actors=256, device=torch.device('cuda:0'), precision=precision)

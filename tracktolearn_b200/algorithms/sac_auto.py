@@ -42,6 +42,7 @@ class SACAuto(RLAlgorithm):
                                       alpha=self.alpha, device=self.device)
         self.learner.actor.load_state_dict(actor.state_dict())
         self.learner.target_actor.load_state_dict(actor.state_dict())
+        self.agent.attach_learner(self.learner)        # a critic loaded from a checkpoint moves into the learner
         self.learner.broadcast_parameters()
         actor.share_parameters(self.learner.actor.state_dict())
         if replay_size is not None:

@@ -270,12 +270,39 @@ class MaxEntropyActor(object):
 
 
 class SACActorCritic(object):
-    """Reference: algorithms/shared/offpolicy.py:407-482 (+ ActorCritic base :234-372)."""
+    """Reference: algorithms/shared/offpolicy.py:407-482 (+ ActorCritic base :234-372).
+
+    The actor is the device forward above.  The critic (offpolicy.py:183-232, two Q networks over
+    concat(state, action)) is not evaluated on the tracking path: it lives either in the learner that
+    ``SACAuto.enable_training`` attaches (torch autograd modules, algorithms/sac_train.py) or, before
+    that, as the state dict a checkpoint brought.  ``save`` always writes both files and ``load`` always
+    reads both, like the reference."""
 
     def __init__(self, state_dim, action_dim, hidden_dims, device, precision='fp16'):
         self.device = torch.device(device)
         self.actor = MaxEntropyActor(state_dim, action_dim, hidden_dims, self.device, precision)
-        self.critic_state_dict = None   # carried for save/load symmetry; not evaluated here
+        self.hidden_dims = hidden_dims
+        self.critic_state_dict = None   # q1.* / q2.* tensors of a loaded checkpoint (no learner yet)
+        self.learner = None             # set by SACAuto.enable_training
+
+    def attach_learner(self, learner):
+        """Training starts: the learner's critic takes over a critic loaded earlier and from now on is
+        what ``state_dict`` / ``save`` see."""
+        if self.critic_state_dict is not None:
+            learner.critic.load_state_dict({k: v.to(self.device) for k, v in self.critic_state_dict.items()})
+            learner.target_critic.load_state_dict(learner.critic.state_dict())
+        self.learner = learner
+        self.critic_state_dict = None
+
+    def _critic_state(self):
+        if self.learner is not None:
+            return {k: v.detach().clone() for k, v in self.learner.critic.state_dict().items()}
+        if self.critic_state_dict is None:
+            # never trained, never loaded: the freshly initialised critic the reference's constructor builds
+            from tracktolearn_b200.algorithms.sac_train import TorchDoubleCritic
+            widths = [int(w) for w in format_widths(self.hidden_dims)]
+            self.critic_state_dict = TorchDoubleCritic(self.actor.state_dim, self.actor.action_dim, widths).state_dict()
+        return self.critic_state_dict
 
     def act(self, state, probabilistic=1.0):
         return self.actor(state, probabilistic)
@@ -290,27 +317,37 @@ class SACActorCritic(object):
         return self.actor.parameters()
 
     def load_state_dict(self, state_dict):
+        """Reference: offpolicy.py:300-310."""
         actor_state_dict, critic_state_dict = state_dict
+        if self.learner is not None:
+            # the inference actor aliases the learner's parameters: load through the module
+            self.learner.actor.load_state_dict(actor_state_dict)
+            self.learner.target_actor.load_state_dict(actor_state_dict)
+            self.actor.refresh_weights()
+            if critic_state_dict is not None:
+                self.learner.critic.load_state_dict(critic_state_dict)
+                self.learner.target_critic.load_state_dict(critic_state_dict)
+            return
         self.actor.load_state_dict(actor_state_dict)
         self.critic_state_dict = critic_state_dict
 
     def state_dict(self):
-        return self.actor.state_dict(), self.critic_state_dict
+        """Reference: offpolicy.py:312-315 -> (actor state dict, critic state dict)."""
+        return self.actor.state_dict(), self._critic_state()
 
     def save(self, path, filename):
-        """Reference: offpolicy.py:327-340."""
-        if self.critic_state_dict is not None:
-            torch.save(self.critic_state_dict, pjoin(path, filename + "_critic.pth"))
-        torch.save({k: v.cpu() for k, v in self.actor.state_dict().items()},
+        """Reference: offpolicy.py:327-340: <filename>_critic.pth and <filename>_actor.pth, CPU tensors
+        under the reference's keys (q1.* / q2.*, layers.*)."""
+        torch.save({k: v.detach().cpu() for k, v in self._critic_state().items()},
+                   pjoin(path, filename + "_critic.pth"))
+        torch.save({k: v.detach().cpu() for k, v in self.actor.state_dict().items()},
                    pjoin(path, filename + "_actor.pth"))
 
     def load(self, path, filename):
-        """Reference: offpolicy.py:342-357 (both files are read; the critic is kept as-is)."""
-        critic_file = pjoin(path, filename + '_critic.pth')
-        if os.path.exists(critic_file):
-            self.critic_state_dict = torch.load(critic_file, map_location='cpu')
-        self.actor.load_state_dict(torch.load(pjoin(path, filename + '_actor.pth'),
-                                              map_location=self.device))
+        """Reference: offpolicy.py:342-357 (both files are read, a missing one raises)."""
+        critic = torch.load(pjoin(path, filename + '_critic.pth'), map_location='cpu')
+        actor = torch.load(pjoin(path, filename + '_actor.pth'), map_location=self.device)
+        self.load_state_dict((actor, critic))
 
     def eval(self):
         self.actor.eval()

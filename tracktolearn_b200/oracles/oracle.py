@@ -154,6 +154,23 @@ class OracleSingleton(object):
                     if n else np.zeros((0, 3), np.float32))
         if len(offsets) <= 1:
             return np.zeros((0,), dtype=np.float32)
-        pts = torch.from_numpy(data.reshape(-1, 3)).pin_memory().to(self.device, non_blocking=True)
-        off = torch.from_numpy(offsets).pin_memory().to(self.device, non_blocking=True)
-        return self.predict_device(pts, off).cpu().numpy()
+        # grow-only pinned staging buffers (a fresh cudaHostAlloc per call costs more than the copy)
+        h_pts = self._pinned('pts', data.size, torch.float32)
+        h_off = self._pinned('off', offsets.size, torch.int64)
+        h_pts.copy_(torch.from_numpy(data.reshape(-1)))
+        h_off.copy_(torch.from_numpy(offsets))
+        pts = h_pts.to(self.device, non_blocking=True).view(-1, 3)
+        off = h_off.to(self.device, non_blocking=True)
+        scores = self.predict_device(pts, off)
+        h_out = self._pinned('scores', scores.numel(), torch.float32)
+        h_out.copy_(scores, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return h_out.numpy().copy()
+
+    def _pinned(self, name, numel, dtype):
+        cache = self.__dict__.setdefault('_pinned_cache', {})
+        buf = cache.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.empty((max(int(numel * 1.25), 1024),), dtype=dtype).pin_memory()
+            cache[name] = buf
+        return buf[:numel]

@@ -22,7 +22,10 @@ from tracktolearn_b200.io.streamlines import detect_format
 from tracktolearn_b200.tracking.tracker import Tracker
 
 _ROOT = os.sep.join(os.path.normpath(os.path.dirname(__file__)).split(os.sep)[:-2])
-DEFAULT_MODEL = os.path.join(_ROOT, 'models')
+# The reference defaults to its bundled agent (<repo>/models, runners/ttl_track.py:34).  The weights
+# are not part of this repository: point TTL_MODEL_DIR at a directory in the reference's layout
+# (last_model_state_actor.pth, last_model_state_critic.pth, hyperparameters.json) to get the same default.
+DEFAULT_MODEL = os.environ.get('TTL_MODEL_DIR', os.path.join(_ROOT, 'models'))
 
 
 class TrackToLearnTrack(object):
@@ -189,6 +192,9 @@ def verify_agent_option(parser, args):
        (args.agent is None and args.hyperparameters is not None):
         parser.error('You must specify both --agent and --hyperparameters arguments or use the default model.')
     if args.agent is None:
+        if not os.path.exists(join(DEFAULT_MODEL, 'last_model_state_actor.pth')):
+            parser.error('no agent given and no default agent at %s (the reference\'s bundled weights are not '
+                         'shipped here): pass --agent and --hyperparameters, or set TTL_MODEL_DIR' % DEFAULT_MODEL)
         args.agent = DEFAULT_MODEL
         args.hyperparameters = join(DEFAULT_MODEL, 'hyperparameters.json')
 

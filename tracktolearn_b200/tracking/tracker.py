@@ -69,23 +69,40 @@ class Tracker(object):
             raise _lib.TTLError('a state or activation value exceeded the fp16 range (65504) during tracking; '
                                 're-run with precision="tf32" (--precision tf32)')
 
+    def _run_pass(self, env, start, end, slots):
+        """Track seeds [start, end) of the env: one streaming pass (or one plain batch)."""
+        if slots is None or slots >= end - start:
+            state = env.reset(start, end)
+        else:
+            # a tensor-core actor reads its operand rows only: do not materialise the fp32 state
+            prec = getattr(self.alg.agent.actor, 'precision', 'fp32')
+            tc_actor = prec in ('bf16', 'fp16', 'tf32')
+            state = env.reset_streaming(start, end, slots, fp32_state=not tc_actor,
+                                        operand=prec if tc_actor else None)
+        self.alg.validation_episode(state, env, self.prob)
+        self._check_range(env)
+
     def track_packed(self, env, copy=True):
         """Yields a Tractogram with voxel-space packed streamlines (+ seeds, flags) per pass;
         no length filter, no space change.  ``copy=False``: each batch aliases the env's pinned
         staging buffers and must be consumed before the next one is requested."""
         self.alg.agent.eval()
         for start, end, slots in self._passes(env):
-            if slots is None or slots >= end - start:
-                state = env.reset(start, end)
-            else:
-                # a tensor-core actor reads its operand rows only: do not materialise the fp32 state
-                prec = getattr(self.alg.agent.actor, 'precision', 'fp32')
-                tc_actor = prec in ('bf16', 'fp16', 'tf32')
-                state = env.reset_streaming(start, end, slots, fp32_state=not tc_actor,
-                                            operand=prec if tc_actor else None)
-            self.alg.validation_episode(state, env, self.prob)
-            self._check_range(env)
+            self._run_pass(env, start, end, slots)
             yield env.get_streamlines(copy=copy)
+
+    def track_gathered(self, env, copy=True):
+        """``track_packed`` for one process per GPU (torchrun): every rank tracks ITS seeds (the caller
+        sharded ``env.seeds``, parallel.shard_seeds) and after each pass the packed streamlines of all
+        ranks are gathered on rank 0 in rank order -- the order one GPU would have produced
+        (tracker.py:106-145 collects batch after batch the same way).  Yields the merged Tractogram on
+        rank 0 and None elsewhere; without torch.distributed it is ``track_packed``.  All ranks must make
+        the same number of passes."""
+        from tracktolearn_b200 import parallel
+        self.alg.agent.eval()
+        for start, end, slots in self._passes(env):
+            self._run_pass(env, start, end, slots)
+            yield parallel.gather_env_streamlines(env, copy=copy)
 
     def track(self, env, tracts_format='trk'):
         """Reference: tracking/tracker.py:62-150.  ``tracts_format``: 'trk' / 'tck' (or the
@@ -98,13 +115,14 @@ class Tracker(object):
             vox_size = np.mean(np.abs(affine)[np.diag_indices(4)][:3])
             scaled_min_length = self.min_length / vox_size
             scaled_max_length = self.max_length / vox_size
+            compress_th_vox = self.compress / vox_size        # tracker.py:103: --compress is in mm
             for batch in self.track_packed(env):
                 lens = streamline_lengths(batch.data, batch.offsets)
                 keep = (scaled_min_length <= lens) & (lens <= scaled_max_length)
                 seeds = batch.data_per_streamline['seeds']
                 data, offsets = batch.data, batch.offsets
                 if self.compress:     # tracker.py:123-125, on the device for the whole batch
-                    data, offsets = self._compress(env, data, offsets)
+                    data, offsets = self._compress(env, data, offsets, compress_th_vox)
                 for i in np.nonzero(keep)[0]:
                     s = np.array(data[offsets[i]:offsets[i + 1]])
                     if is_trk:
@@ -117,11 +135,12 @@ class Tracker(object):
 
         return tracking_generator()
 
-    def _compress(self, env, data, offsets):
-        """dipy ``compress_streamlines(streamline, self.compress)`` (tracker.py:123-125) for a packed
-        batch, on the env's device; returns host arrays."""
+    def _compress(self, env, data, offsets, tol_vox):
+        """dipy ``compress_streamlines(streamline, compress_th_vox)`` (tracker.py:103,123-125: the
+        tolerance given in mm divided by the voxel size, the streamlines being in voxel space) for a
+        packed batch, on the env's device; returns host arrays."""
         from tracktolearn_b200.tracking.postprocess import compress_packed
-        d, o = compress_packed(data, offsets, tol_error=float(self.compress), device=env.device)
+        d, o = compress_packed(data, offsets, tol_error=float(tol_vox), device=env.device)
         return d.cpu().numpy(), o.cpu().numpy()
 
     def track_to_file(self, env, path, dims, voxel_sizes):
@@ -164,16 +183,7 @@ class Tracker(object):
                 new_off = torch.zeros((1,), dtype=torch.int64, device=env.device)
                 seeds_kept = np.zeros((0, 3))
                 if ip < len(passes) and passes[ip][1] > passes[ip][0]:
-                    start, end, slots = passes[ip]
-                    if slots is None or slots >= end - start:
-                        state = env.reset(start, end)
-                    else:
-                        prec = getattr(self.alg.agent.actor, 'precision', 'fp32')
-                        tc_actor = prec in ('bf16', 'fp16', 'tf32')
-                        state = env.reset_streaming(start, end, slots, fp32_state=not tc_actor,
-                                                    operand=prec if tc_actor else None)
-                    self.alg.validation_episode(state, env, self.prob)
-                    self._check_range(env)
+                    self._run_pass(env, *passes[ip])
                     pts, offsets = env.get_streamlines_device()
                     lens = lengths_packed(pts, offsets)
                     keep = (lens >= lo) & (lens <= hi)
@@ -182,7 +192,7 @@ class Tracker(object):
                     new_off = torch.zeros((int(keep.sum().item()) + 1,), dtype=torch.int64, device=pts.device)
                     torch.cumsum(npts[keep], 0, out=new_off[1:])
                     if self.compress:     # after the length filter, before the space change (tracker.py:120-129)
-                        data, new_off = compress_packed(data, new_off, tol_error=float(self.compress))
+                        data, new_off = compress_packed(data, new_off, tol_error=float(self.compress) / float(vox_size))
                     d64 = data.to(torch.float64)
                     if fmt == 'trk':
                         out = ((d64 + 0.5) * float(vox_size)).to(torch.float32)
