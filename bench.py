@@ -169,6 +169,18 @@ class ClockSampler(object):
     def mark_end(self):
         self.t_end = time.monotonic()
 
+    def median_between(self, t0, t1):
+        """Median SM clock of the samples read in [t0, t1 + 40 ms] (None when there is none)."""
+        sm = []
+        for (t, r) in list(self.rows):
+            if t0 <= t <= t1 + 0.04:
+                f = [x.strip() for x in r.split(',')]
+                try:
+                    sm.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        return float(np.median(sm)) if sm else None
+
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
@@ -444,7 +456,7 @@ def roofline_of(prec, prof, rows, pk, tf32_peak, traffic):
     return r
 
 
-def run_tier(env, actor_sd, prec, args, dev, lib, barrier, sampler=None):
+def run_tier(env, actor_sd, prec, args, dev, lib, barrier, sampler=None, is_main=False):
     """Device-resident steady state of one precision tier: inputs already in HBM, K timed steps."""
     import torch
     from tracktolearn_b200 import _lib
@@ -470,14 +482,17 @@ def run_tier(env, actor_sd, prec, args, dev, lib, barrier, sampler=None):
     barrier()
     if sampler is not None:
         sampler.wait_first(2.0)
-        sampler.mark_begin()
+        if is_main:
+            sampler.mark_begin()
+    t_begin = time.monotonic()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
         runner.step()
     ev1.record(stream)
     barrier()
-    if sampler is not None:
+    t_end = time.monotonic()
+    if sampler is not None and is_main:
         sampler.mark_end()
     elapsed_ms = ev0.elapsed_time(ev1)
     # kernels launched one by one + kernels replayed from the captured step graphs
@@ -497,8 +512,10 @@ def run_tier(env, actor_sd, prec, args, dev, lib, barrier, sampler=None):
     lib.ttl_prof_enable(0)
     env.n_alive()
     saturated = bool(actor.overflowed() or env.operand_saturated())
+    time.sleep(0.03)          # let the last clock samples of this leg arrive
+    sm_mhz = sampler.median_between(t_begin, t_end) if sampler is not None else None
     return alg, {'elapsed_ms': elapsed_ms, 'units': units, 'gpu_launches': gpu_launches, 'alive_end': alive_end,
-                 'prof': prof, 'saturated': saturated}
+                 'prof': prof, 'saturated': saturated, 'sm_mhz': sm_mhz}
 
 
 def run_e2e(env, alg, dev, world, barrier):
@@ -646,7 +663,7 @@ def main_gpu(args):
     sampler.start()
     results, alg_main = {}, None
     for prec in order:
-        alg, r = run_tier(env, actor_sd, prec, args, dev, lib, barrier, sampler if prec == main else None)
+        alg, r = run_tier(env, actor_sd, prec, args, dev, lib, barrier, sampler, prec == main)
         results[prec] = r
         if prec == main:
             alg_main = alg
@@ -678,7 +695,7 @@ def main_gpu(args):
         tiers[prec] = {'value': units_all / (ms * 1e-3), 'unit': 'streamline-steps/s', 'ms_per_step': ms / args.steps,
                        'tolerance': TIER_NOTE[prec], 'roofline': roofline_of(prec, r['prof'], r['alive_end'], pk,
                                                                               tf32_peak, traffic),
-                       'kernels': kernels, 'saturated': r['saturated']}
+                       'kernels': kernels, 'saturated': r['saturated'], 'sm_mhz_timed_region': r['sm_mhz']}
     e2e_out = None
     if e2e is not None:
         ms, units_all = reduce(e2e['ms'], e2e['units'])

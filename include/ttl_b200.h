@@ -90,8 +90,7 @@ typedef struct ttl_batch {
                               [4],[5] int64 streamline-steps so far; [6] next unseeded row;
                               [8] survivors of the last step; [9] rows refilled in the last step;
                               [10] first row refilled in the last step; [12],[13] ping-pong copies of
-                              [6] used by the step kernels; [14] set when an fp16 operand row
-                              saturated (|value| > 65504); others reserved */
+                              [6] used by the step kernels; others reserved */
   uint8_t* stop;           /* [n_slots+16] per rank (position in the alive list): stopped this step */
   int32_t* dest;           /* [n_slots] per rank: row of state[next] that holds its new state */
   int32_t* step_flags;     /* [n_slots] per rank: flags raised this step */
@@ -122,7 +121,9 @@ typedef struct ttl_batch {
                               the streamline buffer for the same purpose) */
   float* step_tip;         /* [n_slots+16][4] per rank of alive[cur]: the point added this step */
   int32_t operand_fmt;     /* element type of state_bf16 rows: TTL_OPERAND_BF16 / _FP16 (2 bytes) or
-                              TTL_OPERAND_TF32 (fp32 words rounded to tf32; bf16_layout 1 only) */
+                              TTL_OPERAND_TF32 (fp32 words rounded to tf32; bf16_layout 1 only).  FP16 rows
+                              saturate at +-65504: a state value is a convex combination of SH coefficients
+                              or a step vector, so the caller checks the volume's range once */
   const int32_t* order;    /* NULL, or a permutation [n] of the rows: the order in which seeds take slots
                               (slot k of reset gets row order[k]; refills continue from there).  Rows
                               keep their identity -- results, flags and the output order are per row --

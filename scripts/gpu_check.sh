@@ -17,7 +17,7 @@ try:
     print('value %.1f M  %.1f us/step  e2e %.1f M  launches %d' % (d['value'] / 1e6, d['ms_per_step'] * 1e3, (d['e2e'] or {}).get('value', 0) / 1e6, d['gpu_launches']))
     for p, t in d['tiers'].items():
         r = t['roofline'] or {}
-        print(p, '%.1f M  %.1f us/step  dense %.1f us  %.0f TF  frac %.3f' % (t['value'] / 1e6, t['ms_per_step'] * 1e3, r.get('avg_launch_us', 0), r.get('achieved', 0), r.get('frac', 0)),
+        print(p, '%.1f M  %.1f us/step  dense %.1f us  %.0f TF  frac %.3f  %s MHz' % (t['value'] / 1e6, t['ms_per_step'] * 1e3, r.get('avg_launch_us', 0), r.get('achieved', 0), r.get('frac', 0), t.get('sm_mhz_timed_region')),
               {k: round(v['avg_us'], 1) for k, v in t['kernels'].items()})
     print('clocks', d['clocks'])
     if d.get('sharded'):

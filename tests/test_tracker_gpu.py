@@ -64,7 +64,7 @@ def test_streaming_refill_equals_batch_tracking(prec):
     """Streaming tracker (256 slots over 900 seeds) gives, seed for seed, bit-identical
     streamlines to tracking the seeds in consecutive batches (same kernels, same order of
     arithmetic per streamline)."""
-    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    env, alg, sub, seeds, sd = _setup(precision=prec)
     n = len(seeds)
     batches = []
     for start in range(0, n, 256):
@@ -107,7 +107,7 @@ def test_bf16_only_state_mode_tracks_the_same_streamlines(prec):
     """Streaming with the fp32 state tensor materialised vs the operand-only mode (channel-padded
     operand layout, permuted first-layer weights): same operand values, only the K order of the
     first GEMM differs, so trajectories agree to float rounding."""
-    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    env, alg, sub, seeds, sd = _setup(precision=prec)
     n = len(seeds)
     st = env.reset_streaming(0, n, 256, fp32_state=True)
     alg.validation_episode(st, env, 0.0)
@@ -130,7 +130,7 @@ def test_fused_head_step_is_bit_identical_to_action_round_trip(prec):
     """Device loop with the env step reading tanh(mu) from the actor's fused output layer
     (ttl_env_step_head) vs actor -> action buffer -> ttl_env_step: same streamlines, bit for bit,
     in both state modes."""
-    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    env, alg, sub, seeds, sd = _setup(precision=prec)
     n = len(seeds)
     for fp32_state in (True, False):
         out = []
@@ -154,7 +154,7 @@ def test_bf16_direction_block_is_the_rounded_point_differences(prec):
     must equal, bit for bit, bf16(points[L-1-k] - points[L-2-k]) recomputed from the fp32 streamline
     buffer (env.py:549-563), zero padded."""
     from tracktolearn_b200.algorithms.rl import StepRunner
-    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    env, alg, sub, seeds, sd = _setup(precision=prec)
     n = len(seeds)
     env.reset_streaming(0, n, 256, fp32_state=False)
     runner = StepRunner(env, alg.agent.actor, 0.0, use_graph=False)
@@ -188,7 +188,7 @@ def test_state_kernel_variants_write_identical_rows(prec):
     prefetch (bit 1), produce bit-identical operand rows, hence bit-identical streamlines."""
     from tracktolearn_b200 import _lib
     lib = _lib.load()
-    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    env, alg, sub, seeds, sd = _setup(precision=prec)
     n = len(seeds)
     out, rows = [], []
     try:
@@ -218,7 +218,7 @@ def test_state_kernel_variants_write_identical_rows(prec):
 def test_cuda_graph_replay_equals_plain_launches(prec):
     """validation_episode with the step replayed from two captured CUDA graphs (one per ping-pong
     parity; programmatic-dependent-launch edges inside) vs plain launches: same streamlines."""
-    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    env, alg, sub, seeds, sd = _setup(precision=prec)
     n = len(seeds)
     out = []
     try:
@@ -242,7 +242,7 @@ def test_locality_order_does_not_change_any_streamline(prec):
     """Streaming tracker with the seeds entering the slots in voxel raster order (ttl_batch.order) vs
     in row order: every row holds the same streamline, bit for bit, and the output order is the
     rows' (shuffled) order in both."""
-    env, alg, sub, seeds, sd = _setup(precision='bf16')
+    env, alg, sub, seeds, sd = _setup(precision=prec)
     n = len(seeds)
     out = []
     for loc in (False, True):

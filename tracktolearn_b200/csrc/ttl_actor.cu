@@ -279,12 +279,14 @@ __global__ void __launch_bounds__(256) dense_f32_kernel(const float* __restrict_
 // Host side: TMA descriptors, plan
 // ==========================================================================================
 // row-major [rows][cols] tensor of KIND elements, box = [box_rows][128 bytes], 128-byte swizzle.
-int make_tmap(CUtensorMap* map, int kind, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// pitch: elements between consecutive rows (0 = cols).
+int make_tmap(CUtensorMap* map, int kind, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+              uint64_t pitch = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return TTL_ERR_DRIVER;
   const int es = kind_esize(kind);
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * (uint64_t)es};
+  cuuint64_t strides[1] = {(pitch ? pitch : cols) * (uint64_t)es};
   cuuint32_t box[2] = {(cuuint32_t)kind_bk(kind), box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = kind == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -414,7 +416,11 @@ struct ttl_actor_plan {
   int n_pad[TTL_ACTOR_MAX_LAYERS];   // padded fan-out of layer i (= k_pad[i+1], multiple of 64)
   void* wq[TTL_ACTOR_MAX_LAYERS];
   float* bq[TTL_ACTOR_MAX_LAYERS];
-  void* act[2];                      // ping-pong activations [max_rows][max_kpad]
+  void* act_in;                      // packed first-layer operand rows [max_rows][k_pad[0]] (ttl_actor_forward)
+  void* act[2];                      // ping-pong activations [max_rows][act_pitch]: ONE pitch for every layer, so
+                                     // that a row occupies the same bytes whichever layer wrote it -- in the
+                                     // fused launch layers run concurrently on different rows of these buffers
+  int act_pitch;
   float* f32[2];                     // fp32-tier scratch [F32_CHUNK][max_width]
   float* head_partial;               // fused head partials [max_rows][16][8]
   unsigned* flags;                   // inter-layer dependency counts + ticket (mlp_pair_kernel)
@@ -439,8 +445,9 @@ constexpr int kHeadTilesMax = 16;
 
 struct Layout {
   int64_t total;
-  int64_t off_w[TTL_ACTOR_MAX_LAYERS], off_b[TTL_ACTOR_MAX_LAYERS], off_act[2], off_f32[2], off_hp, off_w0_alt,
-      off_flags;
+  int64_t off_w[TTL_ACTOR_MAX_LAYERS], off_b[TTL_ACTOR_MAX_LAYERS], off_act_in, off_act[2], off_f32[2], off_hp,
+      off_w0_alt, off_flags;
+  int act_pitch;
   int k_pad[TTL_ACTOR_MAX_LAYERS], n_pad[TTL_ACTOR_MAX_LAYERS];
   int max_kpad, max_width, flag_stride;
 };
@@ -469,7 +476,10 @@ int plan_layout(const ttl_actor_weights* w, int max_rows, int precision, Layout*
     L->off_w[i] = kind < 0 ? 0 : take((int64_t)L->n_pad[i] * L->k_pad[i] * es);
     L->off_b[i] = kind < 0 ? 0 : take((int64_t)round_up(L->n_pad[i], 256) * 4);
   }
-  for (int j = 0; j < 2; ++j) L->off_act[j] = kind < 0 ? 0 : take((int64_t)max_rows * L->max_kpad * es);
+  L->act_pitch = 0;
+  for (int i = 0; i < w->n_layers - 1; ++i) L->act_pitch = L->n_pad[i] > L->act_pitch ? L->n_pad[i] : L->act_pitch;
+  L->off_act_in = kind < 0 ? 0 : take((int64_t)max_rows * L->k_pad[0] * es);
+  for (int j = 0; j < 2; ++j) L->off_act[j] = kind < 0 ? 0 : take((int64_t)max_rows * L->act_pitch * es);
   for (int j = 0; j < 2; ++j) L->off_f32[j] = kind < 0 ? take((int64_t)F32_CHUNK * L->max_width * 4) : 0;
   L->off_hp = kind < 0 ? 0 : take((int64_t)max_rows * kHeadTilesMax * 8 * 4);
   L->off_w0_alt = kind < 0 ? 0 : take((int64_t)L->n_pad[0] * L->k_pad[0] * es);
@@ -517,7 +527,7 @@ int run_tc_layers(ttl_actor_plan* p, const CUtensorMap& map_a0, const int32_t* n
     maps.w[slot] = (alt_w0 && i == 0) ? p->map_w0_alt[bi] : p->map_w[i][bi];
     a.kblocks[slot] = p->k_pad[i] / kind_bk(p->kind);
     a.n_pad[slot] = p->n_pad[i];
-    a.ldc[slot] = p->n_pad[i];
+    a.ldc[slot] = p->act_pitch;
     a.C[slot] = p->act[(i + 1) & 1];
     a.bias[slot] = p->bq[i];
   };
@@ -580,15 +590,15 @@ int run_tc_layers(ttl_actor_plan* p, const CUtensorMap& map_a0, const int32_t* n
     const void* h = p->act[nh & 1];
     if (p->kind == KIND_BF16)
       TTL_LAUNCH("head_kernel", s, head_kernel<__nv_bfloat16><<<head_grid, 256, head_smem, s>>>(
-          static_cast<const __nv_bfloat16*>(h), p->k_pad[nl - 1], k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
+          static_cast<const __nv_bfloat16*>(h), p->act_pitch, k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
           n_rows_max, probabilistic, eps, action, logp, pre));
     else if (p->kind == KIND_F16)
       TTL_LAUNCH("head_kernel", s, head_kernel<__half><<<head_grid, 256, head_smem, s>>>(
-          static_cast<const __half*>(h), p->k_pad[nl - 1], k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
+          static_cast<const __half*>(h), p->act_pitch, k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
           n_rows_max, probabilistic, eps, action, logp, pre));
     else
       TTL_LAUNCH("head_kernel", s, head_kernel<float><<<head_grid, 256, head_smem, s>>>(
-          static_cast<const float*>(h), p->k_pad[nl - 1], k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
+          static_cast<const float*>(h), p->act_pitch, k_last, w.w[nl - 1], w.b[nl - 1], n_out, n_rows_dev,
           n_rows_max, probabilistic, eps, action, logp, pre));
   }
   TTL_CHECK_LAST();
@@ -638,6 +648,8 @@ int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int3
     return 0;
   }
   for (int j = 0; j < 2; ++j) p->act[j] = ws + L.off_act[j];
+  p->act_in = ws + L.off_act_in;
+  p->act_pitch = L.act_pitch;
   p->head_partial = reinterpret_cast<float*>(ws + L.off_hp);
   p->w0_alt = ws + L.off_w0_alt;
   // the last hidden layer can carry the head when it is 6 wide and the layer fits 16 tiles of 64
@@ -647,8 +659,11 @@ int ttl_actor_plan_create(ttl_actor_plan** out, const ttl_actor_weights* w, int3
     p->bq[i] = reinterpret_cast<float*>(ws + L.off_b[i]);
     for (int b = 0; b < 3 && !rc; ++b)
       rc = make_tmap(&p->map_w[i][b], p->kind, p->wq[i], (uint64_t)L.n_pad[i], (uint64_t)L.k_pad[i], 128u >> b);
-    // A operand of layer i lives in act[i & 1] with row pitch k_pad[i]
-    if (!rc) rc = make_tmap(&p->map_a[i], p->kind, p->act[i & 1], (uint64_t)max_rows, (uint64_t)L.k_pad[i], MLP_BM);
+    // A operand of layer i: the packed state rows (i == 0) or act[i & 1] with the common pitch
+    if (!rc)
+      rc = i == 0 ? make_tmap(&p->map_a[0], p->kind, p->act_in, (uint64_t)max_rows, (uint64_t)L.k_pad[0], MLP_BM)
+                  : make_tmap(&p->map_a[i], p->kind, p->act[i & 1], (uint64_t)max_rows, (uint64_t)L.k_pad[i], MLP_BM,
+                              (uint64_t)L.act_pitch);
     if (rc) { delete p; return rc; }
   }
   pack_weights(p, s);
@@ -677,13 +692,13 @@ int ttl_actor_forward(ttl_actor_plan* p, const float* state, int32_t ld_state, c
     const int grid = ttl_div_up(tot, 256);
     if (p->kind == KIND_BF16)
       TTL_LAUNCH("pack_state_kernel", s, pack_state_kernel<KIND_BF16><<<grid, 256, 0, s>>>(
-          state, ld_state, w.in_dim[0], n_rows_dev, n_rows_max, p->act[0], p->k_pad[0], p->overflow));
+          state, ld_state, w.in_dim[0], n_rows_dev, n_rows_max, p->act_in, p->k_pad[0], p->overflow));
     else if (p->kind == KIND_F16)
       TTL_LAUNCH("pack_state_kernel", s, pack_state_kernel<KIND_F16><<<grid, 256, 0, s>>>(
-          state, ld_state, w.in_dim[0], n_rows_dev, n_rows_max, p->act[0], p->k_pad[0], p->overflow));
+          state, ld_state, w.in_dim[0], n_rows_dev, n_rows_max, p->act_in, p->k_pad[0], p->overflow));
     else
       TTL_LAUNCH("pack_state_kernel", s, pack_state_kernel<KIND_TF32><<<grid, 256, 0, s>>>(
-          state, ld_state, w.in_dim[0], n_rows_dev, n_rows_max, p->act[0], p->k_pad[0], p->overflow));
+          state, ld_state, w.in_dim[0], n_rows_dev, n_rows_max, p->act_in, p->k_pad[0], p->overflow));
     return run_tc_layers(p, p->map_a[0], n_rows_dev, n_rows_max, probabilistic, eps, action, logp, pre, s);
   }
   // Reference-precision tier; needs the row count on the host.

@@ -325,7 +325,7 @@ __global__ void reset_kernel(ttl_batch b, const double* __restrict__ seeds) {
     b.ctrl[10] = 0;
     b.ctrl[12] = n0;  // ping-pong copies of the cursor that the step kernels read / write
     b.ctrl[13] = n0;
-    b.ctrl[14] = 0;   // fp16 operand rows: a state value saturated
+    b.ctrl[14] = 0;
   }
   for (int j = i; j < 2 * super_count(b.max_groups); j += gridDim.x * blockDim.x) b.sg_stops[j] = 0;
   if (i < b.n_slots) {
@@ -819,12 +819,14 @@ __device__ __forceinline__ void write_dirs_shifted(const uint8_t* __restrict__ o
 // as the actor's first-layer operand in the element type FMT (bf16 / fp16: 2 bytes; tf32: fp32 words
 // rounded to tf32).  Point p owns columns [48p, 48p+48) so every (point, chunk) work item converts its
 // float4 and stores 8 (16) aligned bytes from registers; previous directions follow at column 336.
-// No row staging: 512 B of shared memory per warp.  `sat`: set when an fp16 value saturated.
+// No row staging: 512 B of shared memory per warp.  fp16 range: a trilinear value is a convex combination
+// of coefficients and a direction is at most a step long, so the host checks max |coefficient| <= 65504
+// once per volume instead of every kernel checking every value (tracking_env.py, _start).
 template <int FMT>
 __device__ void build_state_row_c45_op(const ttl_volume& v, const ttl_params& prm, const float* P, int L, float3 tip,
                                        void* __restrict__ out_v, int n_op, float* smem_f, int lane, int pf = 0,
                                        const uint8_t* __restrict__ old_dirs = nullptr,
-                                       float3 prev_tip = make_float3(0.f, 0.f, 0.f), int* sat = nullptr) {
+                                       float3 prev_tip = make_float3(0.f, 0.f, 0.f)) {
   constexpr int CP = 48, CP4 = 12, S = 7 * CP;
   constexpr int ES = FMT == TTL_OPERAND_TF32 ? 4 : 2;
   uint8_t* out = static_cast<uint8_t*>(out_v);
@@ -871,9 +873,6 @@ __device__ void build_state_row_c45_op(const ttl_volume& v, const ttl_params& pr
         *reinterpret_cast<uint4*>(d) = make_uint4(ttl_round_tf32(acc.x), ttl_round_tf32(acc.y),
                                                   ttl_round_tf32(acc.z), ttl_round_tf32(acc.w));
       } else {
-        if (FMT == TTL_OPERAND_FP16 && sat &&
-            fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w))) > 65504.f)
-          *sat = 1;
         *reinterpret_cast<uint2*>(d) = make_uint2(ttl_pack16(acc.x, acc.y, FMT), ttl_pack16(acc.z, acc.w, FMT));
       }
     }
@@ -947,14 +946,9 @@ __device__ __forceinline__ Compaction survivors_before(const ttl_batch& b, int c
   }
   const bool stopped_before = lane < pos && base + lane < n_old && b.stop[base + lane] != 0;
   before += stopped_before ? 1 : 0;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    before += __shfl_xor_sync(0xffffffffu, before, off);
-    total += __shfl_xor_sync(0xffffffffu, total, off);
-  }
   Compaction c;
-  c.keep_before = r - before;
-  c.total_keep = n_old - total;
+  c.keep_before = r - (int)__reduce_add_sync(0xffffffffu, (unsigned)before);      // REDUX: one instruction each
+  c.total_keep = n_old - (int)__reduce_add_sync(0xffffffffu, (unsigned)total);
   return c;
 }
 
@@ -1048,7 +1042,7 @@ __global__ void __launch_bounds__(kStateWarps * 32, MINB) build_state_kernel(ttl
                               ((size_t)r * b.ld_bf16 + 7 * 48) * (FMT == TTL_OPERAND_TF32 ? 4 : 2);
     const float3 prev_tip = make_float3(rec.tx, rec.ty, rec.tz);
     build_state_row_c45_op<FMT>(v, prm, P, L, tip, o16, b.ld_bf16, smem_f, lane, pf, (pf & 8) ? nullptr : old_dirs,
-                                prev_tip, b.ctrl + 14);
+                                prev_tip);
   }
   else
     build_state_row(v, prm, P, L, tip, o32, b.ld_state, o16, b.ld_bf16, smem_f, lane, b.bf16_layout, b.operand_fmt);
@@ -1166,16 +1160,25 @@ __global__ void __launch_bounds__(256) pack_kernel(ttl_batch b, const long long*
 
 constexpr int kStateSmem = kStateWarps * kWarpSmemBytes;
 
+// Operand-only state kernel at 6 CTAs per SM (40 registers).  4 (64 registers, more of a lane's 24 gathers in
+// flight) and 8 (32 registers) were measured at 70.0 and 74.7 us against 68.8 us for 50 000 rows.
+template <int FMT>
+cudaError_t launch_state_fmt(int grid, int smem, cudaStream_t s, const ttl_volume& vol, const ttl_params& prm,
+                             const ttl_batch& b, int cur, int warp_smem, int pf) {
+  static bool ready = false;
+  if (!ready) {
+    cudaError_t e = cudaFuncSetAttribute(build_state_kernel<1, 6, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kStateSmem);
+    if (e != cudaSuccess) return e;
+    ready = true;
+  }
+  return ttl_launch_chain(build_state_kernel<1, 6, FMT>, grid, kStateWarps * 32, smem, s, vol, prm, b, cur, warp_smem, pf);
+}
+
 int state_kernels_ready() {
   static bool done = false;
   if (done) return 0;
   cudaError_t e = cudaFuncSetAttribute(build_state_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(build_state_kernel<1, 6, TTL_OPERAND_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(build_state_kernel<1, 6, TTL_OPERAND_FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(build_state_kernel<1, 6, TTL_OPERAND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(reset_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStateSmem);
   if (e == cudaSuccess)
@@ -1318,17 +1321,11 @@ static int launch_build_state(const ttl_volume* vol, const ttl_params* prm, cons
   const int grid = ttl_div_up(n_upper, kStateWarps), smem = kStateWarps * warp_smem;
   const int pf = state_prefetch_level() | (g_ttl_pdl.load() ? 4 : 0);
   if (b->bf16_layout == 1 && b->operand_fmt == TTL_OPERAND_TF32)
-    TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<1, 6, TTL_OPERAND_TF32>, grid, kStateWarps * 32, smem, s, *vol, *prm,
-                                *b, cur, warp_smem, pf));
+    TTL_LAUNCH("build_state_kernel", s, launch_state_fmt<TTL_OPERAND_TF32>(grid, smem, s, *vol, *prm, *b, cur, warp_smem, pf));
   else if (b->bf16_layout == 1 && b->operand_fmt == TTL_OPERAND_FP16)
-    TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<1, 6, TTL_OPERAND_FP16>, grid, kStateWarps * 32, smem, s, *vol, *prm,
-                                *b, cur, warp_smem, pf));
+    TTL_LAUNCH("build_state_kernel", s, launch_state_fmt<TTL_OPERAND_FP16>(grid, smem, s, *vol, *prm, *b, cur, warp_smem, pf));
   else if (b->bf16_layout == 1)
-    TTL_LAUNCH("build_state_kernel", s,
-               ttl_launch_chain(build_state_kernel<1, 6, TTL_OPERAND_BF16>, grid, kStateWarps * 32, smem, s, *vol, *prm,
-                                *b, cur, warp_smem, pf));
+    TTL_LAUNCH("build_state_kernel", s, launch_state_fmt<TTL_OPERAND_BF16>(grid, smem, s, *vol, *prm, *b, cur, warp_smem, pf));
   else
     TTL_LAUNCH("build_state_kernel", s,
                ttl_launch_chain(build_state_kernel<0, 1, 0>, grid, kStateWarps * 32, smem, s, *vol, *prm, *b, cur,

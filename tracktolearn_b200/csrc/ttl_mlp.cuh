@@ -439,10 +439,12 @@ mlp_pair_kernel(const __grid_constant__ MlpMaps maps, const MlpArgs args) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) packed[j] = pack_pair<KIND>(x[2 * j], x[2 * j + 1]);
             if (KIND == KIND_F16) {
+              // running maximum of what was stored (one HMNMX2 per pair).  After ReLU the values are
+              // non-negative; without it the sign bit is dropped first.
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                __half2 a = *reinterpret_cast<__half2*>(&packed[j]);
-                __half2 mx = __hmax2(__habs2(a), *reinterpret_cast<__half2*>(&sat));
+                const uint32_t pj = relu ? packed[j] : (packed[j] & 0x7fff7fffu);
+                __half2 mx = __hmax2(*reinterpret_cast<const __half2*>(&pj), *reinterpret_cast<__half2*>(&sat));
                 sat = *reinterpret_cast<uint32_t*>(&mx);
               }
             }

@@ -126,6 +126,9 @@ class BaseEnv(object):
         X, Y, Z, C = data.shape
         CP = (C + self.CHANNEL_ALIGN - 1) // self.CHANNEL_ALIGN * self.CHANNEL_ALIGN
         raw = data.to(self.device, dtype=torch.float32).contiguous()
+        # largest coefficient magnitude (NaN-aware): fp16 operand rows hold trilinear combinations of these
+        # values, so this one number decides whether the fp16 tier can represent the states of this volume
+        self._sh_absmax = float(torch.nan_to_num(raw, nan=float('inf')).abs().max().item()) if raw.numel() else 0.0
         self._sh = torch.empty((X, Y, Z, CP), dtype=torch.float32, device=self.device)
         _lib.check(lib.ttl_pad_channels(_lib.ptr(raw), _lib.ptr(self._sh), X * Y * Z, C, CP,
                                         _lib.stream_ptr(self.device)), 'ttl_pad_channels')

@@ -131,6 +131,9 @@ class TrackingEnvironment(BaseEnv):
         operand = operand or getattr(self, 'operand', 'bf16')
         if fp32_state and operand == 'tf32':
             operand = 'bf16'       # unused copy: a tf32 actor packs from the fp32 rows
+        if operand == 'fp16' and not fp32_state and not (getattr(self, '_sh_absmax', 0.0) <= 65504.0):
+            raise _lib.TTLError('the SH volume holds values outside the fp16 range (max |c| = %g): fp16 operand '
+                                'rows would saturate; use precision="tf32"' % self._sh_absmax)
         self.initial_points = initial_points
         N = initial_points.shape[0]
         streaming = n_slots is not None and n_slots < N
@@ -294,9 +297,11 @@ class TrackingEnvironment(BaseEnv):
         return self._batch.operand
 
     def operand_saturated(self):
-        """True when an fp16 operand row had to saturate a state value (|x| > 65504) since reset
-        (valid after ``n_alive()``)."""
-        return bool(int(self._batch.ctrl_host[14]))
+        """True when fp16 operand rows cannot hold this volume's states: a state value is a convex
+        combination of SH coefficients (trilinear weights) or a step vector, so the volume's largest
+        coefficient magnitude, taken once at load time, bounds every value a row can hold."""
+        return self._batch is not None and self._batch.operand == 'fp16' and \
+            not (getattr(self, '_sh_absmax', 0.0) <= 65504.0)
 
     def alive_count_tensor(self):
         """Device int32 tensor holding the alive count of the current list."""
