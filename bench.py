@@ -54,7 +54,7 @@ STATE_SIZE = 615
 ACTOR_FLOP_PER_ROW = 2 * (615 * 1024 + 2 * 1024 * 1024 + 1024 * 6)      # 5 466 112
 DENSE_FLOP_PER_ROW = 2 * (615 * 1024 + 2 * 1024 * 1024)                 # the three tcgen05 layers
 WORKLOAD = 'whole-brain synthetic 145x174x145 1.25mm order-8 fODF, npv=20, n_actor=50000'
-BURN_IN = 128
+BURN_IN = 384
 E2E_SEEDS = 16 * N_ACTOR
 SHARDED_SHAPE = (290, 290, 290)
 SHARDED_VOXEL_MM = 0.5
@@ -472,7 +472,8 @@ def run_tier(env, actor_sd, prec, args, dev, lib, barrier, sampler=None, is_main
     # burn-in (untimed, part of preparing the workload): with slot refill the alive set needs about
     # two mean lifetimes to reach its steady-state mix of streamline ages and positions; right after
     # reset every streamline still sits on the seed shell and the gather enjoys unrepresentative L2
-    # locality
+    # locality.  384 steps (~110 ms) also let the SM clocks settle: the first ~50 ms of load in a
+    # process were measured 8 % slower than the same steps later (benchmarks/tier_repeat.py)
     for _ in range(BURN_IN + args.warmup):
         runner.step()
     env.n_alive()

@@ -37,6 +37,7 @@ def main():
     ap.add_argument('--shape', type=int, nargs=3, default=list(SHAPE))
     ap.add_argument('--no-gather', action='store_true')
     ap.add_argument('--graph', action='store_true', help='replay the step from CUDA graphs')
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'tf32', 'bf16'])
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -81,7 +82,7 @@ def main():
     seeds = seeds[:a.seeds]
     s0, s1 = parallel.shard_bounds(len(seeds), rank, world)
     env.seeds = seeds[s0:s1]
-    alg = SACAuto(B.STATE_SIZE, 3, B.HIDDEN, n_actors=a.n_actor, device=dev, precision='bf16')
+    alg = SACAuto(B.STATE_SIZE, 3, B.HIDDEN, n_actors=a.n_actor, device=dev, precision=a.precision)
     alg.agent.actor.load_state_dict(synthetic.actor_state_dict(B.STATE_SIZE, B.HIDDEN, seed=1111, kind='tracking'))
     alg.use_cuda_graph = bool(a.graph)
     tracker = Tracker(alg, a.n_actor, min_length=10.0, max_length=B.MAX_LENGTH_MM)

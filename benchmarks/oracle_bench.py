@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4]: TractOracle-Net batched scoring of finished streamlines.
 
-    python benchmarks/oracle_bench.py [--n 131072] [--cpu-n 512]
+    python benchmarks/oracle_bench.py [--n 1000000] [--cpu-n 256]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29512 benchmarks/oracle_bench.py        # N GPUs: contiguous chunks + all_gather of scores
 
 Streamlines: ragged smooth random walks, lengths U{20..267} points; model:
 n_head=4, n_layers=4, d=32, ff=2048, 128 tokens (assumed hyper-parameters, real blob missing).
@@ -36,7 +38,7 @@ def make_streamlines(n, seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=131072)
+    ap.add_argument('--n', type=int, default=1000000)
     ap.add_argument('--cpu-n', type=int, default=256)
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
     a = ap.parse_args()
@@ -44,28 +46,50 @@ def main():
     from tracktolearn_b200 import _lib, synthetic
     from tracktolearn_b200.oracles.oracle import OracleSingleton
     from tracktolearn_b200.tracking.tractogram import Tractogram
-    dev = torch.device('cuda:0')
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
     ck = synthetic.oracle_checkpoint(n_head=4, n_layers=4, input_size=384, seed=2222)
     model = OracleSingleton(ck, dev, precision=a.precision)
     data, offsets = make_streamlines(a.n)
     pts = torch.from_numpy(data).to(dev)
     off = torch.from_numpy(offsets).to(dev)
-    model.predict_device(pts, off)          # warm-up
-    torch.cuda.synchronize()
+    model.predict_device(pts, off)          # warm-up (and NCCL set-up)
+    barrier()
     lib = _lib.load()
-    lib.ttl_prof_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    scores = model.predict_device(pts, off)
+    scores = model.predict_device(pts, off)     # every rank its chunk + all_gather_into_tensor
     e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s = float(t[0]) * 1e-3
+    lib.ttl_prof_enable(1)
+    model.predict_device(pts, off)
     torch.cuda.synchronize()
-    dev_s = e0.elapsed_time(e1) * 1e-3
     prof = _lib.prof_report()
     lib.ttl_prof_enable(0)
+    barrier()
     t0 = time.perf_counter()
     host_scores = model.predict(Tractogram(data=data, offsets=offsets))
-    torch.cuda.synchronize()
+    barrier()
     host_s = time.perf_counter() - t0
+    assert np.array_equal(host_scores, scores.cpu().numpy())
+    if rank != 0:
+        dist.destroy_process_group()
+        return
     # CPU oracle on a sample
     from oracle import ttl_oracle as O
     sl = [data[offsets[i]:offsets[i + 1]] for i in range(a.cpu_n)]
@@ -74,11 +98,13 @@ def main():
     cpu_s = time.perf_counter() - t0
     err = float(np.abs(ref - host_scores[:a.cpu_n]).max())
     fwd_ms = sum(v[1] for k, v in prof.items() if k.startswith('oracle_forward'))
+    n_rank = -(-a.n // world)
     out = {
-        'metric': 'oracle streamlines/sec', 'n': a.n,
+        'metric': 'oracle streamlines/sec', 'n': a.n, 'n_gpus': world,
+        'sharding': 'contiguous chunks of streamlines per rank, all_gather_into_tensor of the scores',
         'device_resident_streamlines_per_s': a.n / dev_s,
         'host_to_host_streamlines_per_s': a.n / host_s,
-        'forward_kernel_tflops': a.n * FLOP_PER_STREAMLINE / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None,
+        'forward_kernel_tflops_rank0': n_rank * FLOP_PER_STREAMLINE / (fwd_ms * 1e-3) / 1e12 if fwd_ms else None,
         'kernels_ms': {k: v[1] for k, v in prof.items()},
         'cpu_port_streamlines_per_s': a.cpu_n / cpu_s, 'cpu_cores': os.cpu_count(), 'cpu_sample': a.cpu_n,
         'max_abs_err_vs_cpu_oracle': err,
@@ -87,6 +113,8 @@ def main():
         'flop_per_streamline': FLOP_PER_STREAMLINE,
     }
     print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

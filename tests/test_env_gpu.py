@@ -225,6 +225,46 @@ def test_episode_with_oracle_criterion_and_bonus_matches_reference_fixture():
     OracleSingleton.clear()
 
 
+def test_fp16_oracle_tier_inside_step_decides_like_the_fp32_tier():
+    """S9 / S13 with the production oracle tier (fp16 tensor cores, what `oracle_precision` defaults to):
+    the same episode as the reference fixture, once with the fp32 oracle tier and once with the fp16 one.
+    A streamline whose fp32 score never comes within 5e-3 of the 0.5 threshold must end with the same
+    flags and length in both; the fp32 run itself is pinned to the reference fixture by the test above."""
+    from tests.gpu_helpers import make_gpu_env
+    from tests.helpers import oracle_ckpt_for
+    from tracktolearn_b200.oracles.oracle import OracleSingleton
+    g = load_golden('env_oracle')
+    n = len(g['seeds'])
+    results = {}
+    borderline = np.zeros(n, dtype=bool)
+    for prec in ('fp32', 'fp16'):
+        OracleSingleton.clear()
+        env, _ = make_gpu_env(g, False, True, seeds=g['seeds'], oracle_checkpoint=oracle_ckpt_for(g),
+                              oracle_stopping=True, oracle_bonus=10.0, min_length=1.6, oracle_precision=prec)
+        assert env._oracle.precision == prec
+        env.reset(0, n)
+        rewards = np.zeros(n)
+        for t in range(int(g['n_steps'])):
+            ci = env.continue_idx.copy()
+            if len(ci) == 0:
+                break
+            st, r, done, _ = env.step(g['actions'][t][ci])
+            rewards[ci] += r
+            if prec == 'fp32' and env.length > env.min_nb_steps:
+                sc = env._oracle_scores[:len(ci)].cpu().numpy()
+                borderline[ci[np.abs(sc - 0.5) <= 5e-3]] = True
+            env.harvest()
+        results[prec] = (env.flags.copy(), env.lengths.copy(), rewards)
+    OracleSingleton.clear()
+    np.testing.assert_array_equal(results['fp32'][0], g['final_flags'])
+    clear = ~borderline
+    assert clear.mean() > 0.8, clear.mean()
+    np.testing.assert_array_equal(results['fp16'][0][clear], results['fp32'][0][clear])
+    np.testing.assert_array_equal(results['fp16'][1][clear], results['fp32'][1][clear])
+    np.testing.assert_allclose(results['fp16'][2][clear], results['fp32'][2][clear], rtol=0, atol=1e-4)
+    assert (results['fp32'][0] & 64).any()        # the ORACLE criterion did fire
+
+
 def test_empty_and_single_streamline_batches():
     """Edge sizes of the reference protocol: an empty batch (reset(k, k)), a single streamline, and a
     batch that empties while stepping -- no launch with zero rows, shapes as in the reference."""

@@ -67,3 +67,43 @@ def test_two_rank_gather_equals_single_process():
     np.testing.assert_array_equal(gseeds, seeds)
     np.testing.assert_array_equal(gflags, np.concatenate((np.arange(n0) % 7, np.arange(101 - n0) % 7)))
     assert n0 == 51
+
+
+def _score_worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    calls = []
+
+    def score_chunk(s, e):                      # stands in for TractOracle-Net: a function of the item index
+        calls.append((s, e))
+        return torch.arange(s, e, dtype=torch.float32) * 0.5 + 1.0
+    full = parallel.sharded_scores(n, score_chunk)
+    q.put((rank, full.numpy(), calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_scores_cover_every_item_once():
+    """SURVEY 8(e) row 2: contiguous chunks of streamlines per rank, all_gather_into_tensor of the scores;
+    every rank ends with all N scores in item order, each item scored by exactly one rank."""
+    for n in (1, 2, 101):
+        with socket.socket() as s:
+            s.bind(('127.0.0.1', 0))
+            port = s.getsockname()[1]
+        ctx = mp.get_context('spawn')
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_score_worker, args=(r, 2, port, n, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        got = [q.get(timeout=120) for _ in range(2)]
+        for p in procs:
+            p.join(timeout=60)
+        want = np.arange(n, dtype=np.float32) * 0.5 + 1.0
+        covered = []
+        for rank, full, calls in got:
+            np.testing.assert_array_equal(full, want)
+            covered += [i for (s, e) in calls for i in range(s, e)]
+        assert sorted(covered) == list(range(n))
+    # single process: one call over everything
+    out = parallel.sharded_scores(5, lambda s, e: torch.arange(s, e, dtype=torch.float32))
+    np.testing.assert_array_equal(out.numpy(), np.arange(5, dtype=np.float32))

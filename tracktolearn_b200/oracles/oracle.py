@@ -124,25 +124,44 @@ class OracleSingleton(object):
         cls._self = None
 
     # --------------------------------------------------------------------------- device
-    def predict_device(self, points, offsets):
-        """points [sum(L),3] fp32 and offsets [N+1] int64 on the device -> scores [N] fp32 (device)."""
-        n = int(offsets.shape[0]) - 1
+    def _predict_range(self, points, offsets, start, end):
+        """Scores of streamlines [start, end) -> fp32 tensor [end - start] on the device."""
+        n = end - start
         scores = torch.empty((max(n, 0),), dtype=torch.float32, device=self.device)
-        if n <= 0:
-            return scores
         sp = _lib.stream_ptr(self.device)
-        for s0 in range(0, n, self.batch_size):        # bounded scratch: [batch][127][3]
-            s1 = min(n, s0 + self.batch_size)
-            dirs = torch.empty((s1 - s0, 127, 3), dtype=torch.float32, device=self.device)
+        chunk = max(int(self.batch_size), 1)
+        dirs = None
+        for s0 in range(start, end, chunk):            # bounded scratch: [batch][127][3]
+            s1 = min(end, s0 + chunk)
+            if dirs is None:
+                dirs = torch.empty((min(chunk, n), 127, 3), dtype=torch.float32, device=self.device)
             _lib.check(self._lib.ttl_oracle_features(_lib.ptr(points), ctypes.c_void_p(offsets.data_ptr() + 8 * s0),
                                                      s1 - s0, _lib.ptr(dirs), sp), 'ttl_oracle_features')
-            self.forward_dirs(dirs, ctypes.c_void_p(scores.data_ptr() + 4 * s0), s1 - s0)
+            self.forward_dirs(dirs, ctypes.c_void_p(scores.data_ptr() + 4 * (s0 - start)), s1 - s0)
         return scores
 
+    def predict_device(self, points, offsets, distributed=True):
+        """points [sum(L),3] fp32 and offsets [N+1] int64 on the device -> scores [N] fp32 (device).
+
+        One process per GPU (``torch.distributed`` initialised, ``distributed=True``): every rank holds
+        the same streamlines, scores its contiguous chunk and one ``all_gather_into_tensor`` gives every
+        rank all N scores (the reference scores everything on one device,
+        oracles/oracle.py:39-89)."""
+        n = int(offsets.shape[0]) - 1
+        if n <= 0:
+            return torch.empty((0,), dtype=torch.float32, device=self.device)
+        if not distributed:
+            return self._predict_range(points, offsets, 0, n)
+        from tracktolearn_b200 import parallel
+        return parallel.sharded_scores(n, lambda s, e: self._predict_range(points, offsets, s, e), self.device)
+
     # --------------------------------------------------------------------------- host API
-    def predict(self, streamlines):
+    def predict(self, streamlines, distributed=True):
         """Reference: oracles/oracle.py:39-89.  ``streamlines``: sequence of [L_i,3] arrays (or an
-        object with packed ``data`` / ``offsets``).  Returns float32 numpy [N]."""
+        object with packed ``data`` / ``offsets``).  Returns float32 numpy [N].  Under
+        ``torch.distributed`` the work is shared between the ranks (see ``predict_device``); the oracle
+        stopping criterion inside ``step()`` scores rank-local streamlines and passes
+        ``distributed=False`` semantics by calling ``forward_dirs`` directly."""
         if hasattr(streamlines, 'offsets') and hasattr(streamlines, 'data'):
             data = np.ascontiguousarray(streamlines.data, dtype=np.float32)
             offsets = np.ascontiguousarray(streamlines.offsets, dtype=np.int64)
@@ -161,7 +180,7 @@ class OracleSingleton(object):
         h_off.copy_(torch.from_numpy(offsets))
         pts = h_pts.to(self.device, non_blocking=True).view(-1, 3)
         off = h_off.to(self.device, non_blocking=True)
-        scores = self.predict_device(pts, off)
+        scores = self.predict_device(pts, off, distributed=distributed)
         h_out = self._pinned('scores', scores.numel(), torch.float32)
         h_out.copy_(scores, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

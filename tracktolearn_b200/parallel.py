@@ -31,6 +31,29 @@ def shard_seeds(seeds, rank=None, world=None):
     return seeds[s:e]
 
 
+def sharded_scores(n_items, score_chunk, device=None):
+    """Per-item scores computed by all ranks together (oracle scoring): rank k
+    scores the contiguous chunk ``shard_bounds(n_items, k, world)`` with ``score_chunk(start, end) ->
+    float32 tensor [end - start]`` and one ``all_gather_into_tensor`` of the (padded) chunks hands every
+    rank the full ``[n_items]`` tensor, in item order.  Without torch.distributed: ``score_chunk(0, n)``."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return score_chunk(0, n_items)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = device if device is not None else _device_for_backend()
+    s, e = shard_bounds(n_items, rank, world)
+    pad = -(-n_items // world)                       # chunk sizes differ by at most one
+    mine = torch.zeros((pad,), dtype=torch.float32, device=dev)
+    if e > s:
+        mine[:e - s] = score_chunk(s, e).to(dev, dtype=torch.float32).reshape(-1)
+    full = torch.empty((world * pad,), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(full, mine)
+    parts = []
+    for r in range(world):
+        rs, re = shard_bounds(n_items, r, world)
+        parts.append(full[r * pad:r * pad + (re - rs)])
+    return torch.cat(parts) if parts else full[:0]
+
+
 def _device_for_backend():
     if dist.get_backend() == 'nccl':
         return torch.device('cuda', torch.cuda.current_device())
