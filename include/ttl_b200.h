@@ -204,6 +204,17 @@ int ttl_env_step_finish(const ttl_volume* vol, const ttl_params* prm, const ttl_
                         const float* scores, int32_t use_stop, int32_t min_pts_stop, int32_t min_pts_reward,
                         float bonus, int32_t n_upper, void* stream);
 
+/* Re-orders the alive list alive[cur] by the voxel raster index of every streamline's tip (radix sort of
+ * the keys + one pass moving rank records, alive ids and operand rows into the cur ^ 1 buffers); the
+ * caller flips cur afterwards, as after a step.  Operand-only device mode only (bf16_layout 1): there the
+ * position of a streamline in the list is free, rows keep their identity and every per-row result is
+ * unchanged.  No counterpart in the reference; it restores the gather locality of env.py:538-541 after
+ * streamlines that were seeded together have drifted apart.  workspace: device,
+ * ttl_env_resort_workspace_bytes(n_slots) bytes. */
+int64_t ttl_env_resort_workspace_bytes(int32_t n_slots);
+int ttl_env_resort(const ttl_volume* vol, const ttl_batch* b, int32_t cur, int32_t n_upper, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
 /* state[cur^1][dest[r]] -> out[r] for r < n_rows: the `self.state[self.continue_idx]` that
  * step() returns, in the order of the pre-harvest alive list (tracking_env.py:217-218). */
 int ttl_env_gather_step_state(const ttl_batch* b, int32_t cur, int32_t n_rows, float* out,

@@ -79,8 +79,9 @@ def test_edges_state_flags_reward():
 
 @pytest.mark.parametrize('noisy', [True, False])
 def test_long_episode_matches_oracle(noisy):
-    """Bigger batch, oracle-driven comparison: 64^3 volume (BASELINE config 1 shape), 1500
-    seeds, random-walk actions, every step compared (points, flags, dones, alive order)."""
+    """Bigger batch, oracle-driven comparison: 40x44x36 volume, 1500 seeds, random-walk actions, every
+    step compared (points, flags, dones, alive order).  (The exact BASELINE configs[0] shape -- 64^3,
+    4096 streamlines -- is tests/test_tracker_gpu.py::test_config0_shape_closed_loop_matches_oracle.)"""
     from tests.gpu_helpers import make_gpu_env
     from tracktolearn_b200 import synthetic
     shape = (40, 44, 36)

@@ -1,7 +1,9 @@
-"""BASELINE.json configs[1] at full size (145x174x145 volume, 50 000 slots): size-independent
-properties of a whole tracked batch, and the stopping criteria / state of a sample of its streamlines
-re-evaluated by the CPU oracle on the device's own points ("identical inputs": the oracle sees exactly
-the streamlines the device produced, so no closed-loop drift enters the comparison)."""
+"""BASELINE.json configs[1] (145x174x145, 1.25 mm) and configs[2] (290^3, 0.5 mm: a 4.7 GB channel-padded
+volume, byte offsets beyond 2^32) at full size with 50 000 slots: size-independent properties of a whole
+tracked batch, and the stopping criteria / state of a sample of its streamlines re-evaluated by the CPU
+oracle on the device's own points ("identical inputs": the oracle sees exactly the streamlines the device
+produced, so no closed-loop drift enters the comparison).  The actor runs in the product's default tier
+(fp16 tensor cores)."""
 import numpy as np
 import pytest
 import torch
@@ -10,15 +12,15 @@ from oracle import ttl_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-SHAPE = (145, 174, 145)
-VOXEL_MM = 1.25
-STEP_MM = VOXEL_MM / 0.9987237 * 0.75
+CONFIGS = {'configs1_145x174x145': ((145, 174, 145), 1.25), 'configs2_290cubed': ((290, 290, 290), 0.5)}
 N_SEEDS = 120000
 N_ACTOR = 50000
 
 
-@pytest.fixture(scope='module')
-def tracked():
+@pytest.fixture(scope='module', params=list(CONFIGS))
+def tracked(request):
+    SHAPE, VOXEL_MM = CONFIGS[request.param]
+    STEP_MM = VOXEL_MM / 0.9987237 * 0.75
     from tracktolearn_b200 import synthetic
     from tracktolearn_b200.algorithms.sac_auto import SACAuto
     from tracktolearn_b200.datasets.utils import MRIDataVolume
@@ -40,12 +42,16 @@ def tracked():
     seeds = random_seeds_from_mask(sub['seed_mask'].cpu().numpy(), 3, rs)
     rs.shuffle(seeds)
     env.seeds = seeds[:N_SEEDS]
-    alg = SACAuto(615, 3, '1024-1024-1024', n_actors=N_ACTOR, device=dev, precision='bf16')
+    alg = SACAuto(615, 3, '1024-1024-1024', n_actors=N_ACTOR, device=dev, precision='fp16')
     alg.agent.actor.load_state_dict(synthetic.actor_state_dict(615, '1024-1024-1024', seed=1111, kind='tracking'))
     tracker = Tracker(alg, N_ACTOR, min_length=10.0, max_length=300.0)
     batches = list(tracker.track_packed(env, copy=True))
     assert len(batches) == 1
-    return env, batches[0], {'sh': sub['sh'].cpu().numpy(), 'mask': sub['mask'].cpu().numpy()}
+    host = {'sh': sub['sh'].cpu().numpy(), 'mask': sub['mask'].cpu().numpy(), 'step_vox': STEP_MM / VOXEL_MM}
+    del sub
+    yield env, batches[0], host
+    env._batch = None
+    torch.cuda.empty_cache()
 
 
 def test_whole_batch_properties(tracked):
@@ -65,12 +71,16 @@ def test_whole_batch_properties(tracked):
     # every streamline starts on its seed (float32 of the float64 seed)
     first = t.data[t.offsets[:-1]]
     np.testing.assert_array_equal(first, env.seeds.astype(np.float32))
-    # every segment has the step length r (positions to 1e-5 voxel, north_star tolerance)
+    # every segment has the step length r.  Positions are float32 like the reference's streamline buffer
+    # (tracking_env.py:116): at coordinates up to 290 one ulp is 3e-5 voxel, so a segment length recomputed
+    # from two stored points is off by up to sqrt(3) ulp; 1e-5 (north_star's position tolerance) where the
+    # coordinates allow it.
     seg = np.linalg.norm(np.diff(t.data.astype(np.float64), axis=0), axis=1)
     inner = np.ones(len(seg), dtype=bool)
     inner[t.offsets[1:-1] - 1] = False
-    r = STEP_MM / VOXEL_MM
-    assert np.abs(seg[inner] - r).max() < 1e-5
+    r = tracked[2]['step_vox']
+    tol = max(1e-5, float(np.sqrt(3.0) * np.spacing(np.float32(t.data.max()))))
+    assert np.abs(seg[inner] - r).max() < tol
     assert env.n_alive() == 0
     assert lens.mean() > 20                                  # the synthetic field is trackable
 

@@ -135,8 +135,14 @@ class MaxEntropyActor(object):
         nbytes = self._lib.ttl_actor_workspace_bytes(ctypes.byref(w), rows, prec)
         if nbytes < 0:
             raise _lib.TTLError('unsupported actor architecture %s' % (self._dims,))
-        self._workspace = torch.zeros((nbytes + 1024,), dtype=torch.uint8, device=self.device)
-        base = (self._workspace.data_ptr() + 1023) // 1024 * 1024
+        # GUARD (class attribute / TTL_GUARD=1): 4 KB of 0xA5 on either side of the plan's workspace,
+        # verified by check_guards() -- see environments/tracking_env.py
+        g = 4096 if self.GUARD else 0
+        self._workspace = torch.full((nbytes + 1024 + 2 * g,), 0xA5 if g else 0, dtype=torch.uint8, device=self.device)
+        base = (self._workspace.data_ptr() + g + 1023) // 1024 * 1024
+        self._ws_span = (base - self._workspace.data_ptr(), int(nbytes))
+        if g:
+            self._workspace[self._ws_span[0]:self._ws_span[0] + nbytes].zero_()
         plan = ctypes.c_void_p()
         _lib.check(self._lib.ttl_actor_plan_create(ctypes.byref(plan), ctypes.byref(w), rows, prec,
                                                    ctypes.c_void_p(base), nbytes,
@@ -144,6 +150,16 @@ class MaxEntropyActor(object):
         self._plan = plan
         self._plan_rows = rows
         self._w_struct = w
+
+    GUARD = os.environ.get('TTL_GUARD', '0') == '1'
+
+    def check_guards(self):
+        """Guard bytes around the plan's workspace that a kernel overwrote (0 = clean; needs GUARD)."""
+        if self._workspace is None or not self.GUARD:
+            return 0
+        off, n = self._ws_span
+        ws = self._workspace
+        return int((ws[:off] != 0xA5).sum().item()) + int((ws[off + n:] != 0xA5).sum().item())
 
     def forward_device(self, state, probabilistic, n_rows_dev=None, n_rows=None, eps=None,
                        want_logp=True, want_pre=False, out_action=None, state_bf16=None, layout=None):

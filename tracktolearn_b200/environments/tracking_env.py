@@ -24,13 +24,43 @@ from tracktolearn_b200.environments.env import BaseEnv
 from tracktolearn_b200.tracking.tractogram import Tractogram
 
 
+GUARD_BYTES = 4096
+GUARD_FILL = 0xA5
+
+
 class _BatchBuffers(object):
     """Device buffers of one batch of streamlines (``ttl_batch`` in include/ttl_b200.h).
 
     ``rows``: seeds held by the batch (one streamline buffer row each); ``slots``: streamlines
-    tracked at once (== rows unless the streaming tracker refills freed slots)."""
+    tracked at once (== rows unless the streaming tracker refills freed slots).
+
+    ``GUARD`` (class attribute, or TTL_GUARD=1): every buffer is carved out of a larger allocation with
+    4 KB of 0xA5 on either side and ``check_guards()`` verifies that no kernel wrote there -- the
+    out-of-bounds check this package can run itself (compute-sanitizer is not available on every pool)."""
+
+    GUARD = os.environ.get('TTL_GUARD', '0') == '1'
+
+    def _zeros(self, shape, dtype, device):
+        if not self.GUARD:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        body = (n + 255) // 256 * 256
+        raw = torch.full((body + 2 * GUARD_BYTES,), GUARD_FILL, dtype=torch.uint8, device=device)
+        self._guarded.append((raw, n))
+        view = raw[GUARD_BYTES:GUARD_BYTES + n].view(dtype).view(shape)
+        view.zero_()
+        return view
+
+    def check_guards(self):
+        """Names nothing: returns the number of guard bytes that were overwritten (0 = clean)."""
+        bad = 0
+        for raw, n in self._guarded:
+            bad += int((raw[:GUARD_BYTES] != GUARD_FILL).sum().item())
+            bad += int((raw[GUARD_BYTES + n:] != GUARD_FILL).sum().item())
+        return bad
 
     def __init__(self, rows, slots, max_pts, state_size, device, fp32_state=True, operand='bf16'):
+        self._guarded = []
         self.fp32_state = fp32_state
         self.operand = operand          # element type of the actor operand rows: 'bf16' / 'fp16' / 'tf32'
         if operand not in _lib.OPERAND_OF_PRECISION:
@@ -43,39 +73,39 @@ class _BatchBuffers(object):
         self.max_pts = max_pts
         self.state_size = state_size
         self.ld_state = (state_size + 3) // 4 * 4
-        i32 = dict(dtype=torch.int32, device=device)
+        i32 = (torch.int32, device)
         pad = (slots + 127) // 128 * 128 + 16   # stop[] is read in whole 128-rank groups
-        self.points = torch.zeros((rows, max_pts, 3), dtype=torch.float32, device=device)
-        self.flags = torch.zeros((rows,), **i32)
-        self.lengths = torch.zeros((rows,), **i32)
-        self.npts = torch.zeros((rows,), **i32)
-        self.dones = torch.zeros((rows,), dtype=torch.uint8, device=device)
-        self.alive = [torch.zeros((pad,), **i32), torch.zeros((pad,), **i32)]
-        self.ctrl = torch.zeros((16,), **i32)
-        self.stop = torch.zeros((pad,), dtype=torch.uint8, device=device)
-        self.dest = torch.zeros((pad,), **i32)
-        self.step_flags = torch.zeros((pad,), **i32)
-        self.reward = torch.zeros((pad,), dtype=torch.float32, device=device)
+        self.points = self._zeros((rows, max_pts, 3), torch.float32, device)
+        self.flags = self._zeros((rows,), *i32)
+        self.lengths = self._zeros((rows,), *i32)
+        self.npts = self._zeros((rows,), *i32)
+        self.dones = self._zeros((rows,), torch.uint8, device)
+        self.alive = [self._zeros((pad,), *i32), self._zeros((pad,), *i32)]
+        self.ctrl = self._zeros((16,), *i32)
+        self.stop = self._zeros((pad,), torch.uint8, device)
+        self.dest = self._zeros((pad,), *i32)
+        self.step_flags = self._zeros((pad,), *i32)
+        self.reward = self._zeros((pad,), torch.float32, device)
         # fp32 state rows (the API's state tensor).  Without them the step kernel produces only the
         # bf16 rows, in the channel-padded column layout (ttl_batch.bf16_layout = 1).
-        self.state = ([torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device),
-                       torch.zeros((slots, self.ld_state), dtype=torch.float32, device=device)]
+        self.state = ([self._zeros((slots, self.ld_state), torch.float32, device),
+                       self._zeros((slots, self.ld_state), torch.float32, device)]
                       if fp32_state else [None, None])
         self.ctrl_host = torch.zeros((16,), dtype=torch.int32).pin_memory()
         # copy of the state rows in the actor's operand type, zero padded to a multiple of 64 columns:
         # the actor's TMA operand
         self.ld_bf16 = (state_size + 63) // 64 * 64
         op_dtype = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'tf32': torch.float32}[operand]
-        self.state_bf16 = [torch.zeros((slots, self.ld_bf16), dtype=op_dtype, device=device),
-                           torch.zeros((slots, self.ld_bf16), dtype=op_dtype, device=device)]
+        self.state_bf16 = [self._zeros((slots, self.ld_bf16), op_dtype, device),
+                           self._zeros((slots, self.ld_bf16), op_dtype, device)]
         self.max_groups = (slots + 31) // 32 + 1
-        self.grp_stops = torch.zeros((self.max_groups,), **i32)
-        self.sg_stops = torch.zeros((2 * ((self.max_groups + 63) // 64),), **i32)
+        self.grp_stops = self._zeros((self.max_groups,), *i32)
+        self.sg_stops = self._zeros((2 * ((self.max_groups + 63) // 64),), *i32)
         # per-rank records {row, npts, tip, previous point} of the two alive lists and the points added
         # by the step in flight (ttl_batch.rank_rec / step_tip)
-        self.rank_rec = [torch.zeros((pad, 8), dtype=torch.float32, device=device),
-                         torch.zeros((pad, 8), dtype=torch.float32, device=device)]
-        self.step_tip = torch.zeros((pad, 4), dtype=torch.float32, device=device)
+        self.rank_rec = [self._zeros((pad, 8), torch.float32, device),
+                         self._zeros((pad, 8), torch.float32, device)]
+        self.step_tip = self._zeros((pad, 4), torch.float32, device)
 
     def as_struct(self, n, n_slots):
         b = _lib.Batch(n=n, n_slots=n_slots, capacity=self.rows, max_pts=self.max_pts,
@@ -254,6 +284,26 @@ class TrackingEnvironment(BaseEnv):
             self._pending_harvest = False
             self._continue_idx_cache = None
         return self._batch.state[self._cur]
+
+    def resort_device(self):
+        """Re-order the alive list by tip voxel (``ttl_env_resort``) between two steps: a step without a
+        step -- the sorted list lands in the other ping-pong buffers and becomes current.  Device
+        (operand-only) mode only; per-row results are unchanged."""
+        if self._pending_harvest:
+            raise RuntimeError('resort_device() between step and harvest')
+        if self._batch.fp32_state:
+            raise _lib.TTLError('the tip sort needs the operand-only device mode (reset_streaming(fp32_state=False))')
+        n_slots = int(self._b.n_slots)
+        ws = getattr(self, '_resort_ws', None)
+        need = self._lib.ttl_env_resort_workspace_bytes(n_slots)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+            self._resort_ws = ws
+        _lib.check(self._lib.ttl_env_resort(ctypes.byref(self._volume), ctypes.byref(self._b), self._cur,
+                                            int(self._n_alive_host), _lib.ptr(ws), int(ws.numel()),
+                                            _lib.stream_ptr(self.device)), 'ttl_env_resort')
+        self._cur ^= 1
+        self._continue_idx_cache = None
 
     def n_alive(self):
         """Alive count after the last harvest (one 32-byte D2H copy + stream sync)."""
