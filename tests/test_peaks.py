@@ -115,3 +115,44 @@ def test_from_files_computes_peaks_for_the_alignment_reward(tmp_path):
     ref = O.peaks_alignment_reward(pk, pts)
     np.testing.assert_allclose(r2, ref, atol=2e-6)
     assert np.abs(r2).max() > 0.1
+
+
+def test_reference_sphere_is_used_when_dipy_is_importable(monkeypatch):
+    """environments/env.py:412-415 evaluates peaks on dipy's repulsion724 hemisphere.  dipy is not installed
+    here, so stand a minimal `dipy` in and check that the loader takes ITS vertices and edges."""
+    import sys
+    import types
+    from tracktolearn_b200.datasets import sphere
+    assert sphere.reference_hemisphere() is None or len(sphere.reference_hemisphere()[0]) == 362
+    v, e, nb = sphere.hemisphere(1)
+
+    class FakeHemi(object):
+        def __init__(self, vertices, edges):
+            self.vertices, self.edges = vertices, edges
+
+        @classmethod
+        def from_sphere(cls, s):
+            return cls(s.vertices, s.edges)
+
+        def subdivide(self, n):
+            assert n == 0
+            return self
+    dipy = types.ModuleType('dipy')
+    data = types.ModuleType('dipy.data')
+    core = types.ModuleType('dipy.core')
+    core_sphere = types.ModuleType('dipy.core.sphere')
+    asked = []
+
+    def get_sphere(name=None):
+        asked.append(name)
+        return FakeHemi(v, e)
+    data.get_sphere = get_sphere
+    core_sphere.HemiSphere = FakeHemi
+    for name, mod in (('dipy', dipy), ('dipy.data', data), ('dipy.core', core), ('dipy.core.sphere', core_sphere)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    got = sphere.reference_hemisphere()
+    assert asked == ['repulsion724']
+    np.testing.assert_array_equal(got[0], v)
+    np.testing.assert_array_equal(got[1], e)
+    np.testing.assert_array_equal(got[2], nb)
+    assert 'repulsion724' in sphere.evaluation_hemisphere()[3]

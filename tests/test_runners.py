@@ -73,9 +73,9 @@ def test_ttl_track_end_to_end(tmp_path, ext):
 
 @pytest.mark.gpu
 def test_ttl_track_compress_flag(tmp_path):
-    """`--compress t` (ttl_track.py:223-228 -> tracker.py:123-125): same streamlines, fewer points, every
-    removed point within t (voxels, as in the reference: compression runs before the space change)
-    of the chord that replaced it; end points untouched."""
+    """`--compress t` (ttl_track.py:223-228 -> tracker.py:103,123-125): same streamlines, fewer points,
+    every removed point within t mm = t / voxel_size voxels (compression runs in voxel space, before the
+    space change) of the chord that replaced it; end points untouched."""
     from tracktolearn_b200 import synthetic
     from tracktolearn_b200.io import nifti
     from tracktolearn_b200.io.streamlines import read_tck
@@ -107,4 +107,59 @@ def test_ttl_track_compress_flag(tmp_path):
         for p in a[:: max(1, len(a) // 8)]:
             t = np.clip(((p - seg0) * u).sum(1) / np.maximum((u * u).sum(1), 1e-12), 0, 1)
             dist = np.linalg.norm(seg0 + t[:, None] * u - p, axis=1).min()
-            assert dist <= 0.1 + 1e-3, dist
+            assert dist <= 0.1 / 1.25 + 1e-3, dist
+
+
+def test_training_help_option():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'sac_auto_train.py'), '--help'],
+                         capture_output=True, text=True)
+    assert out.returncode == 0
+    for flag in ('path', 'experiment', 'id', '--max_ep', '--log_interval', '--lr', '--gamma', '--alignment_weighting',
+                 '--n_actor', '--hidden_dims', '--npv', '--theta', '--min_length', '--max_length', '--step_size',
+                 '--noise', '--n_dirs', '--oracle_checkpoint', '--oracle_bonus', '--alpha', '--batch_size',
+                 '--replay_size', '--rng_seed'):
+        assert flag in out.stdout, flag
+
+
+@pytest.mark.gpu
+def test_sac_auto_train_end_to_end_then_track_with_the_trained_agent(tmp_path):
+    """configs[3]'s surface: the sac_auto_train runner trains for two episodes on a tiny synthetic subject,
+    writes <path>/model/{hyperparameters.json, last_model_state_actor.pth, last_model_state_critic.pth}
+    in the reference's layout (trainers/train.py:151-179, sac_auto_train.py:48-59), and ttl_track.py then
+    tracks with that directory."""
+    import json
+    import torch
+    from tracktolearn_b200 import synthetic
+    from tracktolearn_b200.io import nifti
+    from tracktolearn_b200.io.streamlines import read_tck
+    from tracktolearn_b200.runners.ttl_track import main as track_main
+    from tracktolearn_b200.trainers.sac_auto_train import main as train_main
+    shape = (24, 26, 22)
+    sub = synthetic.make_subject(shape, seed=5)
+    affine = np.diag([1.0, 1.0, 1.0, 1.0])
+    nifti.save(str(tmp_path / 'fodf.nii.gz'), sub['sh'].numpy(), affine)
+    nifti.save(str(tmp_path / 'mask.nii.gz'), sub['mask'].numpy(), affine)
+    nifti.save(str(tmp_path / 'seed.nii.gz'), synthetic.ellipsoid_mask(shape, frac=0.3).numpy().astype(np.uint8), affine)
+    exp = train_main([str(tmp_path / 'exp'), 'unit', 'run0', str(tmp_path / 'fodf.nii.gz'), str(tmp_path / 'seed.nii.gz'),
+                      str(tmp_path / 'mask.nii.gz'), '--max_ep', '2', '--log_interval', '1', '--n_actor', '96',
+                      '--hidden_dims', '64-64-64', '--batch_size', '64', '--replay_size', '8192',
+                      '--start_timesteps', '96', '--min_length', '3', '--max_length', '30', '--npv', '1'])
+    model = tmp_path / 'exp' / 'model'
+    hp = json.load(open(model / 'hyperparameters.json'))
+    for key in ('algorithm', 'step_size', 'voxel_size', 'max_angle', 'hidden_dims', 'n_dirs', 'target_sh_order',
+                'input_size', 'action_size', 'alpha', 'batch_size', 'replay_size', 'lr', 'gamma', 'n_actor',
+                'min_length', 'max_length', 'alignment_weighting', 'binary_stopping_threshold', 'noise'):
+        assert key in hp, key
+    assert hp['algorithm'] == 'SACAuto' and hp['input_size'] == 615 and isinstance(hp['voxel_size'], str)
+    actor = torch.load(model / 'last_model_state_actor.pth', map_location='cpu')
+    critic = torch.load(model / 'last_model_state_critic.pth', map_location='cpu')
+    assert tuple(actor['layers.0.weight'].shape) == (64, 615) and tuple(critic['q1.0.weight'].shape) == (64, 618)
+    episodes = [e for e in exp.training_log if 'avg_length' in e]
+    assert len(episodes) == 2 and all(e['avg_length'] > 1 for e in episodes)
+    assert any(e['losses'] for e in episodes)            # updates did run
+    out = str(tmp_path / 'trained.tck')
+    track_main([str(tmp_path / 'fodf.nii.gz'), str(tmp_path / 'seed.nii.gz'), str(tmp_path / 'mask.nii.gz'), out,
+                '--agent', str(model), '--hyperparameters', str(model / 'hyperparameters.json'),
+                '--n_actor', '200', '--npv', '1', '--min_length', '0', '--max_length', '60'])
+    data, offsets, _ = read_tck(out)
+    assert len(offsets) - 1 > 50

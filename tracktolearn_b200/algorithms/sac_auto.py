@@ -39,7 +39,7 @@ class SACAuto(RLAlgorithm):
         actor = self.agent.actor
         hidden = '-'.join(str(int(w)) for w in actor.hidden_layers)
         self.learner = SACAutoLearner(actor.state_dim, actor.action_dim, hidden, lr=lr, gamma=gamma,
-                                      alpha=self.alpha, device=self.device)
+                                      alpha=self.alpha, device=actor.device)
         self.learner.actor.load_state_dict(actor.state_dict())
         self.learner.target_actor.load_state_dict(actor.state_dict())
         self.agent.attach_learner(self.learner)        # a critic loaded from a checkpoint moves into the learner

@@ -6,8 +6,9 @@ adds for the B200 build is where the work lives and how it scales:
   * the networks are plain torch modules whose parameters ARE the tensors the tcgen05 inference
     actor packs its bf16 weights from, so a rollout sees new weights after one repack launch;
   * with ``torch.distributed`` initialised every optimiser step is preceded by ONE all-reduce of
-    that optimiser's flattened gradients (alpha: 1 float, actor: 10.9 MB, critic: 21.9 MB) --
-    SURVEY.md section 8(e): replicas stay in lock-step, polyak targets stay local.
+    that optimiser's gradients (alpha: 1 float, actor: 10.9 MB, critic: 21.9 MB), which live in one
+    flat buffer per optimiser and are reduced in place, asynchronously, overlapped with the next
+    backward pass -- SURVEY.md section 8(e): replicas stay in lock-step, polyak targets stay local.
 """
 import copy
 import math
@@ -67,20 +68,40 @@ class TorchDoubleCritic(nn.Module):
         return self.q1(x).squeeze(-1), self.q2(x).squeeze(-1)
 
 
-def _allreduce_mean(params):
-    """One all-reduce per optimiser: flatten the gradients, sum over ranks, divide, scatter back."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat /= dist.get_world_size()
-    o = 0
-    for g in grads:
-        g.copy_(flat[o:o + g.numel()].view_as(g))
-        o += g.numel()
+class _FlatGrads(object):
+    """The gradients of one optimiser as views into ONE flat buffer, so that the data-parallel reduction
+    is a single in-place all-reduce of that buffer with nothing to flatten or to copy back.  ``launch``
+    starts the all-reduce asynchronously (NCCL runs it on its own stream while autograd carries on with
+    the next backward pass); ``wait`` makes the averaged gradients visible before ``optimizer.step()``."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        n = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros((n,), dtype=ref.dtype, device=ref.device)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.work = None
+
+    def zero(self):
+        self.flat.zero_()
+        o = 0
+        for p in self.params:          # an optimiser's zero_grad(set_to_none=True) elsewhere must not detach the views
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * o:
+                p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def launch(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+            self.flat /= dist.get_world_size()
 
 
 class SACAutoLearner(object):
@@ -100,6 +121,9 @@ class SACAutoLearner(object):
         self.alpha_optimizer = torch.optim.Adam([self.log_alpha], lr=lr)
         self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=lr)
         self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), lr=lr)
+        self.g_alpha = _FlatGrads([self.log_alpha])
+        self.g_actor = _FlatGrads(list(self.actor.parameters()))
+        self.g_critic = _FlatGrads(list(self.critic.parameters()))
         self.total_it = 0
 
     def broadcast_parameters(self, src=0):
@@ -127,19 +151,31 @@ class SACAutoLearner(object):
         cq1, cq2 = self.critic(state, action)
         critic_loss = F.mse_loss(cq1, backup) + F.mse_loss(cq2, backup)
 
-        self.alpha_optimizer.zero_grad()
+        # sac_auto.py:220-232: three backward passes, three optimiser steps, in the reference's order.
+        # Data-parallel: each optimiser's gradients are reduced by ONE all-reduce of a flat buffer.  The
+        # temperature (one float; the actor loss deposits a stray gradient in it afterwards, which the
+        # reference discards the same way) is reduced and stepped at once; the actor's and the critic's
+        # reductions are asynchronous -- the critic's backward pass runs while the actor's 10.9 MB travel
+        # -- and are waited for just before their steps.  (The actor loss also deposits gradients in the
+        # critic; clearing the critic's buffer after the actor's backward pass is the reference's
+        # zero_grad() order.)
+        self.g_alpha.zero()
         alpha_loss.backward()
-        _allreduce_mean([self.log_alpha])
+        self.g_alpha.launch()
+        self.g_alpha.wait()
         self.alpha_optimizer.step()
 
-        self.actor_optimizer.zero_grad()
+        self.g_actor.zero()
         actor_loss.backward()
-        _allreduce_mean(list(self.actor.parameters()))
-        self.actor_optimizer.step()
+        self.g_actor.launch()
 
-        self.critic_optimizer.zero_grad()
+        self.g_critic.zero()
         critic_loss.backward()
-        _allreduce_mean(list(self.critic.parameters()))
+        self.g_critic.launch()
+
+        self.g_actor.wait()
+        self.actor_optimizer.step()
+        self.g_critic.wait()
         self.critic_optimizer.step()
 
         with torch.no_grad():

@@ -45,6 +45,8 @@ class MaxEntropyActor(object):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.TTLError('the actor forward runs on a CUDA device only (got %s)' % (self.device,))
+        if self.device.index is None:       # 'cuda' -> 'cuda:N': tensors report the indexed device
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.precision = precision
         self._lib = _lib.load()
         dims = [self.state_dim] + [int(w) for w in self.hidden_layers] + [2 * self.action_dim]

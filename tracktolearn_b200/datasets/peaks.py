@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from tracktolearn_b200 import _lib
-from tracktolearn_b200.datasets.sphere import hemisphere
+from tracktolearn_b200.datasets.sphere import evaluation_hemisphere
 from tracktolearn_b200.datasets.utils import get_sh_order_and_fullness
 
 
@@ -51,7 +51,7 @@ def sh_to_sf_matrix(vertices, order):
 
 @functools.lru_cache(maxsize=4)
 def _sphere_tables(order):
-    vertices, edges, neighbours = hemisphere(3)
+    vertices, edges, neighbours, _ = evaluation_hemisphere()     # dipy's repulsion724 when dipy is installed
     return vertices, edges, neighbours, sh_to_sf_matrix(vertices, order)
 
 

@@ -66,3 +66,51 @@ def hemisphere(subdivisions=3):
     for i, x in enumerate(nb):
         table[i, :len(x)] = sorted(x)
     return np.ascontiguousarray(v[keep]), e, table
+
+
+def _tables_from_edges(vertices, edges):
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64)
+    e = np.sort(np.asarray(edges, dtype=np.int64).reshape(-1, 2), axis=1)
+    e = np.unique(e[e[:, 0] != e[:, 1]], axis=0)
+    V = len(vertices)
+    nb = [[] for _ in range(V)]
+    for a, b in e:
+        nb[a].append(int(b))
+        nb[b].append(int(a))
+    D = max(len(x) for x in nb)
+    table = -np.ones((V, D), dtype=np.int32)
+    for i, x in enumerate(nb):
+        table[i, :len(x)] = sorted(x)
+    return vertices, e, table
+
+
+def reference_hemisphere():
+    """The sphere the reference evaluates peaks on (environments/env.py:412-415):
+    ``HemiSphere.from_sphere(get_sphere("repulsion724")).subdivide(0)`` -- 362 directions and the edges of
+    their triangulation -- taken from a dipy installation when there is one, so that load-time peaks are
+    comparable one to one with the reference's.  Returns (vertices, edges, neighbours) like ``hemisphere``,
+    or None when dipy (or its data file) is not importable."""
+    try:
+        try:
+            from dipy.data import get_sphere          # dipy >= 1.7: get_sphere(name=...)
+        except ImportError:
+            return None
+        from dipy.core.sphere import HemiSphere
+        try:
+            full = get_sphere(name='repulsion724')
+        except TypeError:
+            full = get_sphere('repulsion724')
+        hemi = HemiSphere.from_sphere(full).subdivide(0)
+        return _tables_from_edges(np.asarray(hemi.vertices), np.asarray(hemi.edges))
+    except Exception:
+        return None
+
+
+def evaluation_hemisphere():
+    """(vertices, edges, neighbours, name): dipy's repulsion724 hemisphere when available (the reference's),
+    else this package's icosphere hemisphere."""
+    ref = reference_hemisphere()
+    if ref is not None:
+        return ref + ('dipy repulsion724 hemisphere (%d directions)' % len(ref[0]),)
+    v, e, nb = hemisphere(3)
+    return v, e, nb, 'icosphere(3) hemisphere (%d directions; dipy not importable)' % len(v)

@@ -227,6 +227,25 @@ class Tracker(object):
             n = int(t.item())
         return n
 
+    def track_and_train(self, env):
+        """Reference: tracking/tracker.py:152-202.  One training "epoch": ``n_actor`` streamlines from
+        random seeds (``env.nreset``), the rollout + update loop of the algorithm (``alg._episode``:
+        sample actions, step, push transitions to the replay buffer, one gradient update per env step),
+        then the streamlines it produced.  Returns (tractogram, mean losses, reward, mean reward factors)."""
+        from collections import defaultdict
+        self.alg.agent.train()
+        mean_losses = defaultdict(list)
+        mean_reward_factors = defaultdict(list)
+        state = env.nreset(self.n_actor)
+        reward, losses, length, reward_factors = self.alg._episode(state, env)
+        train_tractogram = env.get_streamlines()
+        for step_losses in (losses if isinstance(losses, (list, tuple)) else [losses]):
+            for k, v in step_losses.items():
+                mean_losses[k].append(float(v))
+        for k, v in (reward_factors or {}).items():
+            mean_reward_factors[k].append(float(v))
+        return train_tractogram, mean_losses, reward, mean_reward_factors
+
     def track_and_validate(self, env):
         """Reference: tracking/tracker.py:204-259 (batch by batch, with rewards)."""
         self.alg.agent.eval()
