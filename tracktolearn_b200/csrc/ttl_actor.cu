@@ -836,7 +836,9 @@ int ttl_gemm_tc(const void* A, const void* W, const float* bias, void* C, int32_
                 int32_t ldc, int32_t relu, const int32_t* m_dev, int32_t precision, int32_t bn, void* stream) {
   const int kind = kind_of_precision(precision);
   if (kind < 0 || !A || !W || !bias || !C || (k % 64) || (n % 64) || ldc < n || (ldc % 16)) return TTL_ERR_BAD_ARG;
-  if ((reinterpret_cast<uintptr_t>(C) & 31) || (bn != 0 && bn != 256 && bn != 128 && bn != 64)) return TTL_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(C) & 31) || (reinterpret_cast<uintptr_t>(bias) & 15) ||
+      (bn != 0 && bn != 256 && bn != 128 && bn != 64))
+    return TTL_ERR_BAD_ARG;
   if (m <= 0) return 0;
   if (bn == 0) bn = choose_bn(m, n);
   MlpMaps maps;

@@ -235,6 +235,7 @@ mlp_pair_kernel(const __grid_constant__ MlpMaps maps, const MlpArgs args) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < n_stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 8); }
+    mbar_init(bar0 + 8u * (2 * n_stages + 5), 1);      // bias / head weights staged (see below)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -261,14 +262,28 @@ mlp_pair_kernel(const __grid_constant__ MlpMaps maps, const MlpArgs args) {
   sc.nn2 = n_layers > 2 ? (args.n_pad[2] + bn - 1) / bn : 1;
   sc.nn3 = n_layers > 3 ? (args.n_pad[3] + bn - 1) / bn : 1;
 
+  // Bias vectors and the fused head's weights go to shared memory by bulk copies that complete on their own
+  // mbarrier: issued here by one thread, awaited by the epilogue warps before their first tile, so the
+  // ~30 KB never sit on the critical path (staging them with ordinary loads cost ~4 us at the head of every
+  // launch, a quarter of a small-batch step).
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bar0 + MLP_BAR_BYTES - raw));
   float* s_head = s_bias + n_layers * args.bias_stride;
-  for (int l = 0; l < n_layers; ++l)
-    for (int t = threadIdx.x; t < args.n_pad[l]; t += MLP_THREADS) s_bias[l * args.bias_stride + t] = args.bias[l][t];
+  const uint32_t stage_bar = bar0 + 8u * (2 * n_stages + 5);
   const int head_np = args.n_pad[n_layers - 1];
   const bool has_head = HEAD_OUT > 0 && args.head_w != nullptr;
   const int head_n = has_head ? min(max(args.head_n, 1), HEAD_OUT > 0 ? HEAD_OUT : 1) : 0;
-  if (has_head) {
+  // the head weights can be copied as they are when their rows are as wide as the padded layer
+  const bool head_bulk = has_head && args.head_k == head_np && ((reinterpret_cast<uintptr_t>(args.head_w) & 15) == 0);
+  if (warp == 3 && lane == 0) {
+    uint32_t bytes = 0;
+    for (int l = 0; l < n_layers; ++l) bytes += (uint32_t)args.n_pad[l] * 4u;
+    if (head_bulk) bytes += (uint32_t)(head_n * head_np) * 4u;
+    mbar_arrive_expect_tx(stage_bar, bytes);
+    for (int l = 0; l < n_layers; ++l)
+      bulk_load(ttl_smem_u32(s_bias + l * args.bias_stride), args.bias[l], (uint32_t)args.n_pad[l] * 4u, stage_bar);
+    if (head_bulk) bulk_load(ttl_smem_u32(s_head), args.head_w, (uint32_t)(head_n * head_np) * 4u, stage_bar);
+  }
+  if (has_head && !head_bulk) {
     for (int t = threadIdx.x; t < head_n * head_np; t += MLP_THREADS) {
       const int o = t / head_np, c = t - o * head_np;
       s_head[t] = c < args.head_k ? args.head_w[(size_t)o * args.head_k + c] : 0.f;
@@ -361,6 +376,7 @@ mlp_pair_kernel(const __grid_constant__ MlpMaps maps, const MlpArgs args) {
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t sat = 0;      // fp16: running max of the stored magnitudes (packed pair)
+    mbar_wait(stage_bar, 0);       // bias vectors / head weights have landed
     for (bool ok = sc.start(cluster_id); ok; ok = sc.advance(n_clusters)) {
       int l, m_blk, n_blk;
       sc.tile(l, m_blk, n_blk);
