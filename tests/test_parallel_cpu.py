@@ -23,11 +23,11 @@ def _fake_track(seeds):
         'flags': (np.arange(len(seeds)) % 7).astype(np.int64)})
 
 
-def _worker(rank, world, port, seeds, q):
+def _worker(rank, world, port, seeds, q, via='nccl'):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     mine = parallel.shard_seeds(seeds)
-    merged = parallel.gather_tractogram(_fake_track(mine))
+    merged = parallel.gather_tractogram(_fake_track(mine), via=via)
     if rank == 0:
         q.put((merged.data, merged.offsets, merged.data_per_streamline['seeds'],
                merged.data_per_streamline['flags'], len(mine)))
@@ -45,7 +45,13 @@ def test_shard_bounds_tile_the_range():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_two_rank_gather_equals_single_process():
+import pytest
+
+
+@pytest.mark.parametrize('via', ['nccl', 'host'])
+def test_two_rank_gather_equals_single_process(via):
+    """'nccl': point-to-point into rank 0's buffers; 'host': every rank copies into a shared host arena
+    (the single-node path; here over gloo on CPU, without the page-locking)."""
     rs = np.random.RandomState(0)
     seeds = rs.uniform(0, 20, size=(101, 3))
     with socket.socket() as s:
@@ -53,7 +59,7 @@ def test_two_rank_gather_equals_single_process():
         port = s.getsockname()[1]
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, seeds, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, seeds, q, via)) for r in range(2)]
     for p in procs:
         p.start()
     data, offsets, gseeds, gflags, n0 = q.get(timeout=120)

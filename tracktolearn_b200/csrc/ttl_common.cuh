@@ -120,6 +120,39 @@ __device__ __forceinline__ float ttl_head_tree_sum(const float* __restrict__ p, 
   return acc;
 }
 
+// The first three outputs (the action means) at once, from float4 loads issued together: what the env
+// step's propagate kernel needs.  Same additions in the same order as ttl_head_tree_sum.
+__device__ __forceinline__ void ttl_head_tree_sum3(const float* __restrict__ p, int n_tiles, int tiles_per_256,
+                                                   float& ox, float& oy, float& oz) {
+  const float4* q = reinterpret_cast<const float4*>(p);      // tile t: q[2 t] = outputs 0..3
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  if (tiles_per_256 == 1 && n_tiles <= 4) {                  // the full-batch shape: up to 4 tiles of 256 columns
+    float4 v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = t < n_tiles ? __ldg(q + 2 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (t < n_tiles) { ax += v[t].x; ay += v[t].y; az += v[t].z; }
+  } else {
+    for (int t = 0; t < n_tiles; t += tiles_per_256) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[j] = (j < tiles_per_256 && t + j < n_tiles) ? __ldg(q + 2 * (t + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tiles_per_256 == 1) {
+        ax += v[0].x; ay += v[0].y; az += v[0].z;
+      } else if (tiles_per_256 == 2) {
+        ax += v[0].x + v[1].x; ay += v[0].y + v[1].y; az += v[0].z + v[1].z;
+      } else {
+        ax += (v[0].x + v[1].x) + (v[2].x + v[3].x);
+        ay += (v[0].y + v[1].y) + (v[2].y + v[3].y);
+        az += (v[0].z + v[1].z) + (v[2].z + v[3].z);
+      }
+    }
+  }
+  ox = ax; oy = ay; oz = az;
+}
+
 __device__ __forceinline__ uint32_t ttl_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

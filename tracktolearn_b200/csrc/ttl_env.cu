@@ -399,10 +399,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB) propagate_stop_kernel(
   const RankRec rec = read_rank_rec(b.rank_rec[cur], r_ld);
   float ax = 0.f, ay = 0.f, az = 0.f;
   if (src.partial) {
-    const float* hp = src.partial + (size_t)r_ld * src.n_tiles * 8;
-    ax = ttl_head_tree_sum(hp, src.n_tiles, src.tiles_per_256, 0);
-    ay = ttl_head_tree_sum(hp, src.n_tiles, src.tiles_per_256, 1);
-    az = ttl_head_tree_sum(hp, src.n_tiles, src.tiles_per_256, 2);
+    ttl_head_tree_sum3(src.partial + (size_t)r_ld * src.n_tiles * 8, src.n_tiles, src.tiles_per_256, ax, ay, az);
   } else {
     ax = src.actions[(size_t)r_ld * src.lda + 0];
     ay = src.actions[(size_t)r_ld * src.lda + 1];
@@ -923,29 +920,50 @@ __device__ __forceinline__ void build_state_row(const ttl_volume& v, const ttl_p
 //                       + sum of the group counts of r's super-group before r's group
 //                       + stopped ranks of r's own group before r (ballot over the stop flags);
 //   total stops         = sum of all super-group counters.
-// A handful of independent loads per lane and two warp reductions; all lanes return the values.
+// Every address depends on r alone (counters beyond the alive range are zero, buffers are padded past
+// n_slots), so the loads are issued at kernel entry together with the alive count they are later masked
+// with -- one memory round trip, not two -- and reduced with two REDUX instructions.
+struct CompactionLoads {
+  int sg[2];        // this lane's super-group counters (lane, lane + 32)
+  int grp[kSuper / 32];
+  int stop_lane;    // stop flag of rank base + lane
+};
 struct Compaction {
   int keep_before;   // survivors among the ranks before r
   int total_keep;    // survivors of the whole list
 };
-__device__ __forceinline__ Compaction survivors_before(const ttl_batch& b, int cur, int r, int n_old, int lane) {
-  const int g = r / kGroup, base = g * kGroup, pos = r - base;      // kGroup == 32: one flag per lane
-  const int sgr = g / kSuper;
-  const int n_groups = (n_old + kGroup - 1) / kGroup, n_super = (n_groups + kSuper - 1) / kSuper;
-  const int* sg = b.sg_stops + cur * super_count(b.max_groups);
-  int before = 0, total = 0;
-  for (int j = lane; j < n_super; j += 32) {
-    const int v = __ldcg(sg + j);
-    total += v;
-    before += j < sgr ? v : 0;
-  }
+__device__ __forceinline__ CompactionLoads compaction_loads(const ttl_batch& b, int cur, int r, int lane) {
+  const int g = r / kGroup, base = g * kGroup, sgr = g / kSuper;
+  const int n_super_max = super_count(b.max_groups);
+  const int* sg = b.sg_stops + cur * n_super_max;
+  CompactionLoads L;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) L.sg[j] = lane + 32 * j < n_super_max ? __ldcg(sg + lane + 32 * j) : 0;
 #pragma unroll
   for (int j = 0; j < kSuper / 32; ++j) {
     const int gg = sgr * kSuper + lane + 32 * j;
-    before += gg < g ? __ldcg(b.grp_stops + gg) : 0;
+    L.grp[j] = gg < g ? __ldcg(b.grp_stops + gg) : 0;
   }
-  const bool stopped_before = lane < pos && base + lane < n_old && b.stop[base + lane] != 0;
-  before += stopped_before ? 1 : 0;
+  L.stop_lane = b.stop[base + lane];
+  return L;
+}
+__device__ __forceinline__ Compaction survivors_before(const ttl_batch& b, const CompactionLoads& L, int cur, int r,
+                                                       int n_old, int lane) {
+  const int g = r / kGroup, base = g * kGroup, pos = r - base, sgr = g / kSuper;
+  const int n_super_max = super_count(b.max_groups);
+  int total = L.sg[0] + L.sg[1];
+  int before = (lane < sgr ? L.sg[0] : 0) + (lane + 32 < sgr ? L.sg[1] : 0);
+  if (n_super_max > 64) {               // more than 131 072 slots: the remaining counters, the slow way
+    const int* sg = b.sg_stops + cur * n_super_max;
+    for (int j = lane + 64; j < n_super_max; j += 32) {
+      const int v = __ldcg(sg + j);
+      total += v;
+      before += j < sgr ? v : 0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kSuper / 32; ++j) before += L.grp[j];
+  before += (lane < pos && base + lane < n_old && L.stop_lane != 0) ? 1 : 0;
   Compaction c;
   c.keep_before = r - (int)__reduce_add_sync(0xffffffffu, (unsigned)before);      // REDUX: one instruction each
   c.total_keep = n_old - (int)__reduce_add_sync(0xffffffffu, (unsigned)total);
@@ -970,13 +988,15 @@ __global__ void __launch_bounds__(kStateWarps * 32, MINB) build_state_kernel(ttl
   // kernels and in propagate_stop was measured slower (up to +38 us with all of them on), so those
   // release at exit.
   if (pf & 4) ttl_grid_dep_launch();
+  // independent loads first, all of them addressed by r alone (buffers are padded past n_slots): alive count
+  // and cursor, stop counts / flags, this rank's record and new point
   const int n_old = b.ctrl[cur];
   const int cursor = b.ctrl[12 + cur];
-  // independent loads first: stop counts / flags (rank), this rank's record and new point
-  const int r_ld = min(r, max(n_old - 1, 0));
-  const RankRec rec = read_rank_rec(b.rank_rec[cur], r_ld);
-  const float4 q = __ldg(reinterpret_cast<const float4*>(b.step_tip) + r_ld);
-  const Compaction cp = survivors_before(b, cur, r_ld, n_old, lane);
+  const CompactionLoads cl = compaction_loads(b, cur, r, lane);
+  const RankRec rec = read_rank_rec(b.rank_rec[cur], r);
+  const float4 q = __ldg(reinterpret_cast<const float4*>(b.step_tip) + r);
+  const int stop_r = b.stop[r];
+  const Compaction cp = survivors_before(b, cl, cur, r, n_old, lane);
   const int total_keep = cp.total_keep;
   const int n_new = prm.refill ? max(0, min(b.n_slots - total_keep, b.n - cursor)) : 0;
   if (r == 0 && lane == 0) {
@@ -998,7 +1018,7 @@ __global__ void __launch_bounds__(kStateWarps * 32, MINB) build_state_kernel(ttl
   }
   if (r >= n_old) return;
   const int keep_before = cp.keep_before;
-  const bool stopped = b.stop[r] != 0;
+  const bool stopped = stop_r != 0;
   int row, dst, L;
   float3 tip = make_float3(q.x, q.y, q.z);
   if (!stopped) {
