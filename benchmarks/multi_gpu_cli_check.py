@@ -44,7 +44,7 @@ def main():
         cli(common + [one] + opts)
         many = p('many.' + ext)
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n),
-               '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.join(ROOT, 'scripts', 'ttl_track.py')]
+               '--master-addr', '127.0.0.1', '--master-port', '29561', os.path.join(ROOT, 'scripts', 'ttl_track.py')]
         subprocess.check_call(cmd + common + [many] + opts, stdout=subprocess.DEVNULL)
         d1, o1, _ = reader(one)
         d2, o2, _ = reader(many)
