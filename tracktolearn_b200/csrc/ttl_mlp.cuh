@@ -165,22 +165,24 @@ static __device__ __forceinline__ void fence_proxy_async_global() {
 }
 
 // The tile list (see the header comment).  Every role of a cluster walks it with its own copy.
+// Host-callable too: tests/test_mlp_schedule_cpu.py enumerates it on the CPU and checks that every tile
+// appears exactly once and that a tile's inputs always come earlier in the list.
 struct Sched {
   int n_layers, n_m, group_m, n_groups;
   int nn0, nn1, nn2, nn3;          // n-tiles per layer (scalars: a register-indexed array would live in local memory)
   int s, l, off;
 
-  __device__ __forceinline__ int n_n_of(int layer) const {
+  __host__ __device__ __forceinline__ int n_n_of(int layer) const {
     return layer == 0 ? nn0 : (layer == 1 ? nn1 : (layer == 2 ? nn2 : nn3));
   }
-
-  __device__ __forceinline__ int block_tiles() const {
+  __host__ __device__ __forceinline__ int block_tiles() const {
     const int g = s - l;
     if (g < 0 || g >= n_groups) return 0;
-    return min(group_m, n_m - g * group_m) * n_n_of(l);
+    const int rows = n_m - g * group_m;
+    return (rows < group_m ? rows : group_m) * n_n_of(l);
   }
   // move to the block that holds tile offset `off` (counted from the current block's start)
-  __device__ __forceinline__ bool normalize() {
+  __host__ __device__ __forceinline__ bool normalize() {
     while (s < n_groups + n_layers - 1) {
       const int bt = block_tiles();
       if (off < bt) return true;
@@ -189,15 +191,15 @@ struct Sched {
     }
     return false;
   }
-  __device__ __forceinline__ bool start(int first) {
+  __host__ __device__ __forceinline__ bool start(int first) {
     s = 0; l = 0; off = first;
     return n_groups > 0 && normalize();
   }
-  __device__ __forceinline__ bool advance(int step) {
+  __host__ __device__ __forceinline__ bool advance(int step) {
     off += step;
     return normalize();
   }
-  __device__ __forceinline__ void tile(int& layer, int& m_blk, int& n_blk) const {
+  __host__ __device__ __forceinline__ void tile(int& layer, int& m_blk, int& n_blk) const {
     layer = l;
     const int nn = n_n_of(l);
     const int q = off / nn;
