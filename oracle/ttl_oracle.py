@@ -20,6 +20,10 @@ upstream: the fixtures pin this restatement.  The same holds for
 ``local_maxima`` / ``peak_directions`` / ``peaks_from_sh`` (scilpy ``get_maximas`` -> dipy
 ``peak_directions``, env.py:405-432; evaluated on this repository's own sphere because dipy's
 ``repulsion724`` data file is absent).  They have no reference-recorded fixtures: PARITY UNPINNED.
+What narrows the gap: ``tests/test_oracle_independent_cpu.py`` compares ``trilinear`` with
+``scipy.ndimage.map_coordinates(order=1, mode='nearest')`` (inside, on and outside the volume) and
+``set_number_of_points`` / ``streamline_length`` with ``numpy.interp`` over arc length -- other people's
+implementations of the same published algorithms, shipped in this image.
 
 Each function cites the reference lines it follows (paths relative to
 ``/root/reference/TrackToLearn``).
