@@ -922,54 +922,77 @@ oracle_forward_tc2_kernel(ttl_oracle_weights W, const __grid_constant__ CUtensor
         }
         __syncwarp();
         // ---- feed forward ----
+        // The chunk loop is unrolled by 6 = three ring stages (two chunks each) = two rounds of the three
+        // accumulator buffers: inside a block every buffer, barrier and half-stage offset is a compile-time
+        // constant and the three stages are per-layer values.  The issuing warp's own instruction stream
+        // (two mod-3 divisions, descriptor assembly and a dozen R2UR per chunk) was what the token warps
+        // waited for 57 % of this phase (profiles/r1_oracle_tc2_v5_ncu_full_raw.csv, source page).
         wait_x();
-        const uint32_t gpF = gp;
-        // GEMM1(c) = x . W1_c^T into acc1[b]; the caller has waited for the stage of chunk c
-        auto issue_g1 = [&](int c, uint32_t b) {
-          const uint32_t st = (gpF + (uint32_t)(c >> 1)) % NST;
-          const uint64_t d_w1 = d_ring + (uint64_t)((st * STAGE_BYTES) >> 4) + (uint64_t)(4 * (c & 1));
+        uint32_t f_bar[3], e_bar[3], f_par[3];
+        uint64_t d_w[3], d_aug[3];
+        {
+          uint32_t g = gp;
+#pragma unroll
+          for (int k = 0; k < 3; ++k, ++g) {
+            const uint32_t st = g % NST;
+            f_bar[k] = full((int)st);
+            e_bar[k] = empty((int)st);
+            f_par[k] = (g / NST) & 1u;                       // parity of pair k of block 0; flips every block
+            d_w[k] = d_ring + (uint64_t)((st * STAGE_BYTES) >> 4);
+            d_aug[k] = umma_desc_noswz(base + OFF_RING + st * STAGE_BYTES + ST_AUG, 128, 256);
+          }
+        }
+        // GEMM1 of the chunk at position u (0..5) of a block into acc1[u % 3]: x . W1^T + b1
+        auto issue_g1 = [&](int u) {
+          const int k = u >> 1, half = u & 1;
+          const uint32_t d = tmem_base + acc1_col((uint32_t)(u % 3));
+          const uint64_t d_w1 = d_w[k] + (uint64_t)(4 * half);
           // A operand from tensor memory: x (fp16, 16 columns at COL_X) and the [1 1 0..] bias slice
           // (8 columns at COL_ONES); small SS-form MMAs are bound by the shared-memory read of A
           // (measured 48 cycles for N = 64, benchmarks/micro/umma_latency.cu), TS-form runs at 32
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            tc_mma_f16_ts(tmem_base + acc1_col(b), tmem_base + COL_X + 8u * k, d_w1 + (uint64_t)(2 * k), id_64, (uint32_t)(k != 0));
-          tc_mma_f16_ts(tmem_base + acc1_col(b), tmem_base + COL_ONES,
-                        umma_desc_noswz(base + OFF_RING + st * STAGE_BYTES + ST_AUG + (c & 1) * (AUG_PAIR_BYTES / 2), 128, 256),
-                        id_64, 1u);     // + b1
-          tc_commit(acc1_full(b));
+          for (int kk = 0; kk < 2; ++kk)
+            tc_mma_f16_ts(d, tmem_base + COL_X + 8u * kk, d_w1 + (uint64_t)(2 * kk), id_64, (uint32_t)(kk != 0));
+          tc_mma_f16_ts(d, tmem_base + COL_ONES, d_aug[k] + (uint64_t)(half * ((AUG_PAIR_BYTES / 2) >> 4)), id_64, 1u);   // + b1
+          tc_commit(acc1_full((uint32_t)(u % 3)));
         };
-        auto wait_stage = [&](int c) {   // first chunk of a pair: its weights must have landed
-          const uint32_t pair = gpF + (uint32_t)(c >> 1);
-          mbar_wait(full(pair % NST), (pair / NST) & 1u);
+        auto wait_stage = [&](int k, uint32_t blk) {   // first chunk of a pair: its weights must have landed
+          mbar_wait(f_bar[k], f_par[k] ^ (blk & 1u));
           tc_fence_after();
         };
-        wait_stage(0);
-        wait_stage(2);
+        wait_stage(0, 0u);
+        if (n_chunks > 2) wait_stage(1, 0u);
         if (elect_one()) {
           tc_commit(empty(stA));     // the tokens are done with the layer's parameters
-          issue_g1(0, 0u);
-          issue_g1(1, 1u);
-          issue_g1(2, 2u);
+          issue_g1(0);
+          issue_g1(1);
+          if (n_chunks > 2) issue_g1(2);
         }
         __syncwarp();
-        uint32_t fb = 0;     // buffer of chunk c = c % 3
-        for (int c = 0; c < n_chunks; ++c) {
-          if (c + 3 < n_chunks && ((c + 3) & 1) == 0) wait_stage(c + 3);
-          wait_h(fb);
-          if (elect_one()) {
-            const uint32_t st = (gpF + (uint32_t)(c >> 1)) % NST;
-            const uint64_t d_w2 = d_ring + (uint64_t)((st * STAGE_BYTES + ST_W2 + (c & 1) * 4096) >> 4);
-            const uint32_t a_h = tmem_base + acc1_col(fb);
+        for (int c0 = 0, blk = 0; c0 < n_chunks; c0 += 6, ++blk) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_f16_ts(tmem_base + COL_B, a_h + 8u * k, d_w2 + (uint64_t)(2 * k), id_32, (uint32_t)(c != 0 || k != 0));
-            if (c & 1) tc_commit(empty(st));   // both chunks of the stage have been consumed
-            if (c + 3 < n_chunks) issue_g1(c + 3, fb);
-            if (c == n_chunks - 1) tc_commit(done);
+          for (int u = 0; u < 6; ++u) {
+            const int c = c0 + u;
+            if (c >= n_chunks) break;
+            const int un = (u + 3) % 6;                            // position of chunk c + 3 ...
+            const uint32_t blkn = (uint32_t)blk + (u + 3 >= 6 ? 1u : 0u);   // ... and its block
+            const bool more = c + 3 < n_chunks;
+            if (more && (un & 1) == 0) wait_stage(un >> 1, blkn);
+            wait_h((uint32_t)(u % 3));
+            if (elect_one()) {
+              const int k = u >> 1, half = u & 1;
+              const uint64_t d_w2 = d_w[k] + (uint64_t)((ST_W2 + half * 4096) >> 4);
+              const uint32_t a_h = tmem_base + acc1_col((uint32_t)(u % 3));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                tc_mma_f16_ts(tmem_base + COL_B, a_h + 8u * kk, d_w2 + (uint64_t)(2 * kk), id_32,
+                              (uint32_t)(u != 0 || kk != 0 || c0 != 0));
+              if (half) tc_commit(e_bar[k]);   // both chunks of the stage have been consumed
+              if (more) issue_g1(un);
+              if (c == n_chunks - 1) tc_commit(done);
+            }
+            __syncwarp();
           }
-          __syncwarp();
-          fb = fb == 2u ? 0u : fb + 1u;
         }
         gp += (uint32_t)(n_chunks / 2);
       }
