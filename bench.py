@@ -14,8 +14,10 @@ update) -- 3 kernel launches, no host involvement.
 
 What the JSON line carries (DESIGN.md section 6 says how every field is produced):
   value        device-resident steady-state throughput of the headline tier (fp16 operands: within the
-               1e-3 tolerance at the full 16-bit tensor rate); `tiers` holds the same measurement for
-               tf32 (1e-3, fp32 range, half rate) and bf16 (4e-3, outside the tolerance)
+               1e-3 tolerance at the full 16-bit tensor rate), timed on a rested chip: 384 burn-in steps,
+               2 s of idle, W warm-up steps, K timed steps; `tiers` holds the same measurement for tf32
+               (1e-3, fp32 range, half rate) and bf16 (4e-3, outside the tolerance)
+  sustained    the headline tier again after ~125 ms of continuous load (what sw_power_cap leaves)
   e2e          Tracker over 800 000 seeds per GPU from pinned host seeds to host-resident packed
                streamlines; with N > 1 the seeds are one list, shuffled once and sharded, and the timed
                region ends with the NCCL gather of every rank's streamlines on rank 0
