@@ -771,7 +771,7 @@ def main_gpu(args):
                    'what': 'Tracker.track_gathered over %d seeds per GPU (one list, one common shuffle, sharded): '
                            'pinned-host seeds H2D, full episodes incl. tail, device-side pack, %s packed '
                            'streamlines+flags D2H on rank 0; %d env steps, %d streamlines on rank 0'
-                           % (min(n_seeds, E2E_SEEDS), 'NCCL gather to rank 0, ' if world > 1 else '',
+                           % (min(n_seeds, E2E_SEEDS), 'gather on rank 0 (shared pinned host arena, NCCL carries sizes and the barrier; NCCL point-to-point when the arena is unavailable), ' if world > 1 else '',
                               e2e['steps'], e2e['streamlines'])}
 
     # ---- HBM side of the two env kernels (main tier) ---------------------------------------------
