@@ -70,7 +70,7 @@ TIER_NOTE = {
     'tf32': 'tf32 operands (11 significant bits, fp32 range), fp32 accumulate: within 1e-3, half the tensor rate',
     'bf16': 'bf16 operands (8 significant bits): ~4e-3 of the output scale, OUTSIDE the 1e-3 tolerance',
 }
-NCU_SUMMARY = os.path.join(ROOT, 'profiles', 'r2_step_ncu_summary.json')
+NCU_SUMMARY = os.path.join(ROOT, 'profiles', 'r2_final_step_ncu_summary.json')
 
 
 def workload_config(shape=SHAPE, voxel_mm=VOXEL_MM):
