@@ -75,3 +75,46 @@ def test_streamline_length_and_features():
     assert n.max() <= O.streamline_length(s) / 127 * (1 + 1e-5)
     # reversing the streamline reverses and negates the features (symmetric algorithm up to float rounding)
     np.testing.assert_allclose(f[1], -f[0][::-1], rtol=0, atol=2e-4)
+
+
+def test_hemisphere_edges_and_local_maxima_against_a_convex_hull_triangulation():
+    """The evaluation sphere's edge table against scipy's Delaunay triangulation of the same points on the
+    sphere (the convex hull of a centrally symmetric point set), and the oracle's edge-walking
+    ``local_maxima`` (dipy's algorithm restated) against a brute-force neighbourhood scan over those hull edges."""
+    from scipy.spatial import ConvexHull
+    from tracktolearn_b200.datasets.sphere import hemisphere
+    v, e, nb = hemisphere(3)
+    full = np.concatenate([v, -v])                                  # antipodal copies: index i + V  <->  i
+    V = len(v)
+    hull = ConvexHull(full)
+    he = np.concatenate([hull.simplices[:, [0, 1]], hull.simplices[:, [1, 2]], hull.simplices[:, [2, 0]]]) % V
+    he = np.sort(he[he[:, 0] != he[:, 1]], axis=1)
+    he = np.unique(he, axis=0)
+    # The icosphere's faces are a valid Delaunay triangulation except where four points are cocircular (hull picks
+    # either diagonal): every product edge whose endpoints are closer than the shortest non-edge must be a hull edge.
+    mine = {tuple(x) for x in e.tolist()}
+    theirs = {tuple(x) for x in he.tolist()}
+    assert len(mine) == len(theirs)
+    common = mine & theirs
+    assert len(common) >= 0.9 * len(mine)
+    ang = lambda a, b: np.degrees(np.arccos(np.clip(abs(float(v[a] @ v[b])), -1, 1)))
+    longest = max(ang(a, b) for a, b in mine)
+    for a, b in theirs - mine:                                      # alternative diagonals only: same length class
+        assert ang(a, b) <= longest * 1.25
+    # brute force over the hull's neighbourhoods on smooth symmetric functions: strict maxima agree
+    rs = np.random.RandomState(5)
+    neigh = [[] for _ in range(V)]
+    for a, b in e:
+        neigh[a].append(b)
+        neigh[b].append(a)
+    for _ in range(20):
+        axes = np.linalg.qr(rs.normal(size=(3, 3)))[0].T               # three orthogonal lobes: none swallows another
+        w = rs.uniform(0.3, 1.0, size=3)
+        odf = sum(wk * np.abs(v @ ax) ** 8 for wk, ax in zip(w, axes))
+        vals, idx = O.local_maxima(odf, e)
+        brute = [i for i in range(V) if all(odf[i] >= odf[j] for j in neigh[i]) and any(odf[i] > odf[j] for j in neigh[i])]
+        assert sorted(idx.tolist()) == sorted(brute)
+        assert np.all(np.diff(vals) <= 0)
+        # every lobe axis has a detected maximum within the sphere's resolution (8 degrees between vertices)
+        for ax in axes:
+            assert max(abs(float(v[i] @ ax)) for i in idx) > np.cos(np.deg2rad(9.0))
